@@ -1,0 +1,1048 @@
+// One cube = one warp.  Conflict-driven clause learning with two-watched-literal BCP, written in the lockstep
+// vocabulary of warp_lockstep.h.  Included by kernels.cu (the product, sm_100a) and by tests/emu (test-only).
+//
+// What replaces what (reference file:line):
+//   propagate()      WatchedClausesList::new_decision / process_clause / handle_implication
+//                    (BCPStrategy/WatchedClausesList.cu:46-101,103-221,253-282) — per-literal watches over a
+//                    bitmap of the static occurrence index instead of per-variable linked lists
+//   analyze()        analyze_graph / get_conflicting_assignment (ConflictAnalysis/GraphAnalyzer.cu:31-138) — first
+//                    UIP over trail + reason array instead of the dense back-edge matrix
+//   learn()          LearntClausesManager::learn_clause (ClauseLearning/LearntClausesManager.cu:16-41)
+//   cancel_until()   Backtracker::handle_backtrack + VariablesStateHandler::backtrack_to
+//                    (SATSolver/Backtracker.cu:38-75, SATSolver/VariablesStateHandler.cu:367-399)
+//   pick_branch()    DecisionMaker::decide / VSIDS::next_higher_literal
+//                    (SATSolver/DecisionMaker.cu:45-87, DecisionStrategy/VSIDS.cu:97-124)
+//   run_job()        SATSolver::solve + preprocess (SATSolver/SATSolver.cu:67-218,231-272) with the cube as
+//                    pseudo-decision levels 1..k; restarts per Restarts/GeometricRestartsManager.cu:16-31
+//
+// Canonical order (what makes every job a pure function of (formula, cube, params); the oracle follows it):
+//   * trail FIFO; for the falsified literal f = ~trail[qhead]: first its occurrence slots in ascending order, in
+//     chunks of 32 examined against the assignment at chunk start, watch moves applied, then units / conflicts
+//     committed in slot order; then the learnt clauses watching f one by one in watch-list order.
+//   * learnt clause = first-UIP clause, literals in discovery order, highest other level swapped to position 1.
+#pragma once
+#include "gpsat_device.h"
+#include "warp_lockstep.h"
+
+struct WarpSolver {
+    // ---- read-only formula index (global, L1/L2 resident)
+    int n_vars, n_clauses, n_lits, wbits_words;
+    const gint2 *cl2;
+    const int *ostart;
+    const gint2 *occ2;
+    const uint32_t *wbits0;
+    const int *vsids0;
+    const uint8_t *val0;
+    // ---- per-job state (shared memory when it fits, else this warp's global block)
+    uint8_t *val;
+    uint8_t *seen;
+    int *level;
+    int *reason;
+    int *trail;
+    int *trail_lim;
+    uint32_t *wbits;
+    int *vs;
+    int *lbuf;
+    int lbuf_words;
+    // ---- this warp's learnt arena (global): [lw_ptr | lw_size | lw_cap | hist | refs | clauses ->   <- watch vectors]
+    int *arena;
+    int arena_words;
+    int *lw_ptr, *lw_size, *lw_cap, *hist, *refs;
+    int refs_cap;
+    int clause_base;
+    // ---- warp-uniform scalars
+    int trail_size, qhead, dlevel;
+    int arena_top, watch_bot;
+    int n_learnts, max_learnts;
+    int conflicts_since_restart, restart_limit;
+    int vs_clauses;
+    int oom;
+    int use_learnts;   // 0 in propagate-only runs: no learnt arena, no VSIDS state
+    // params
+    int decision_mode, restart_first, max_iterations, share_learnts, share_max_len;
+    float restart_factor;
+    long long max_conflicts;
+    // shared pool
+    int *pool;
+    int *pool_cursor;
+    int pool_cap_words;
+    // counters (uniform) + per-lane counters
+    long long c_decisions, c_implications, c_conflicts, c_learnt_clauses, c_learnt_literals, c_restarts;
+    unsigned long long c_hash;
+    long long c_lwatchers, c_lwords;   // learnt-clause part of the counters (warp-uniform)
+    LANEVAR(unsigned, l_watchers);
+    LANEVAR(unsigned, l_words);
+
+    // -----------------------------------------------------------------------------------------------------------
+    GPSAT_DEV int lit_value(int x) const
+    {
+        int v = val[x >> 1];
+        return v >= 2 ? 2 : (v ^ (x & 1) ^ 1);
+    }
+    GPSAT_DEV bool wbit(int k) const { return (wbits[k >> 5] >> (k & 31)) & 1u; }
+
+    GPSAT_DEV void enqueue(int x, int why)
+    {
+        GPSAT_LANE_DECL
+        LANE0
+        {
+            int v = x >> 1;
+            val[v] = (uint8_t)(x & 1);
+            level[v] = dlevel;
+            reason[v] = why;
+            trail[trail_size] = x;
+        }
+        trail_size++;
+        SYNCWARP();
+    }
+
+    GPSAT_DEV void new_level()
+    {
+        GPSAT_LANE_DECL
+        LANE0 { trail_lim[dlevel] = trail_size; }
+        dlevel++;
+        SYNCWARP();
+    }
+
+    GPSAT_DEV void cancel_until(int lv)
+    {
+        GPSAT_LANE_DECL
+        if (dlevel <= lv) return;
+        const int start = trail_lim[lv];
+        LANES
+        {
+            for (int i = start + lane; i < trail_size; i += 32) {
+                int v = trail[i] >> 1;
+                val[v] = val0[v];
+            }
+        }
+        trail_size = start;
+        qhead = start;
+        dlevel = lv;
+        SYNCWARP();
+    }
+
+    // ---- learnt watch vectors --------------------------------------------------------------------------------
+    GPSAT_DEV void lw_append(int x, int cref, int blocker)
+    {
+        GPSAT_LANE_DECL
+        int n = lw_size[x], cap = lw_cap[x], ptr = lw_ptr[x];
+        if (n == cap) {
+            const int ncap = cap ? 2 * cap : 4;
+            const int nptr = watch_bot - 2 * ncap;
+            if (nptr < arena_top) {
+                oom = 1;
+                return;
+            }
+            watch_bot = nptr;
+            LANES
+            {
+                for (int i = lane; i < 2 * n; i += 32) arena[nptr + i] = arena[ptr + i];
+            }
+            SYNCWARP();
+            LANE0
+            {
+                lw_ptr[x] = nptr;
+                lw_cap[x] = ncap;
+            }
+            ptr = nptr;
+        }
+        LANE0
+        {
+            arena[ptr + 2 * n] = cref;
+            arena[ptr + 2 * n + 1] = blocker;
+            lw_size[x] = n + 1;
+        }
+        SYNCWARP();
+    }
+
+    // ---- BCP -------------------------------------------------------------------------------------------------
+    // returns GPSAT_NO_CONFLICT or the falsified clause's cref
+    GPSAT_DEV int propagate()
+    {
+        GPSAT_LANE_DECL
+        while (qhead < trail_size) {
+            const int p = trail[qhead++];
+            const int f = p ^ 1;
+
+            // (1) original clauses: occurrence slots of f whose watch bit is set
+            const int os = gpsat_ld(ostart + f), oe = gpsat_ld(ostart + f + 1);
+            for (int base = os; base < oe; base += 32) {
+                LANEVAR(int, act);    // 0 none, 1 move, 2 unit, 3 conflict
+                LANEVAR(int, alit);   // unit literal, or new occurrence slot for a move
+                LANEVAR(int, acl);    // clause cref (first literal slot)
+                LANES
+                {
+                    const int k = base + lane;
+                    LV(act) = 0;
+                    LV(alit) = 0;
+                    LV(acl) = 0;
+                    if (k < oe && wbit(k)) {
+                        const gint2 e = gpsat_ld2(occ2 + k);
+                        const int s = e.x, len = e.y;
+                        int other = -1, other_val = 2, repl = -1, nread = 0;
+                        for (int i = 0; i < len; ++i) {
+                            const gint2 q = gpsat_ld2(cl2 + s + i);
+                            nread++;
+                            if (q.y == k) continue;
+                            const int v = lit_value(q.x);
+                            if (wbit(q.y)) {
+                                other = q.x;
+                                other_val = v;
+                                if (v == 1) break;
+                            } else if (v != 0 && repl < 0) {
+                                repl = q.y;
+                            }
+                            if (other >= 0 && repl >= 0) break;
+                        }
+                        LV(l_watchers) += 1u;
+                        LV(l_words) += (unsigned)nread;
+                        LV(acl) = s;
+                        if (other_val == 1) {
+                            LV(act) = 0;
+                        } else if (repl >= 0) {
+                            LV(act) = 1;
+                            LV(alit) = repl;
+                        } else if (other_val == 2) {
+                            LV(act) = 2;
+                            LV(alit) = other;
+                        } else {
+                            LV(act) = 3;
+                        }
+                    }
+                }
+                SYNCWARP();
+                LANES
+                {
+                    if (LV(act) == 1) {
+                        const int k = base + lane, r = LV(alit);
+                        gpsat_atomic_and(wbits + (k >> 5), ~(1u << (k & 31)));
+                        gpsat_atomic_or(wbits + (r >> 5), 1u << (r & 31));
+                    }
+                }
+                SYNCWARP();
+                unsigned todo = BALLOT(LV(act) >= 2);
+                while (todo) {
+                    const int src = gpsat_ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int a = SHFL(act, src);
+                    const int s = SHFL(acl, src);
+                    const int u = SHFL(alit, src);
+                    if (a == 3) return s;
+                    const int v = lit_value(u);
+                    if (v == 2) {
+                        enqueue(u, s);
+                        c_implications++;
+                    } else if (v == 0) {
+                        return s;
+                    }
+                }
+            }
+
+            // (2) learnt clauses watching f, MiniSat order, the warp cooperating on one clause at a time
+            if (!use_learnts) continue;
+            const int wn = lw_size[f];
+            if (wn == 0) continue;
+            const int wp = lw_ptr[f];
+            c_lwatchers += wn;
+            int confl = GPSAT_NO_CONFLICT;
+            int j = 0;
+            for (int base = 0; base < wn; base += 32) {
+                LANEVAR(int, ecr);
+                LANEVAR(int, ebl);
+                LANEVAR(int, keep);   // 0 dropped, 1 kept, 2 to examine
+                LANES
+                {
+                    const int i = base + lane;
+                    LV(keep) = 0;
+                    LV(ecr) = 0;
+                    LV(ebl) = 0;
+                    if (i < wn) {
+                        LV(ecr) = arena[wp + 2 * i];
+                        LV(ebl) = arena[wp + 2 * i + 1];
+                        LV(keep) = (confl != GPSAT_NO_CONFLICT || lit_value(LV(ebl)) == 1) ? 1 : 2;
+                    }
+                }
+                SYNCWARP();
+                unsigned todo = BALLOT(LV(keep) == 2);
+                while (todo) {
+                    const int src = gpsat_ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int cref = SHFL(ecr, src);
+                    const int bl = SHFL(ebl, src);
+                    if (confl != GPSAT_NO_CONFLICT || lit_value(bl) == 1) {
+                        SETLANE(keep, src, 1);
+                        continue;
+                    }
+                    int *cl = arena + GPSAT_LEARNT_OFF(cref) + 1;
+                    const int len = cl[-1];
+                    int l0 = cl[0], l1 = cl[1];
+                    if (l0 == f) {
+                        LANE0
+                        {
+                            cl[0] = l1;
+                            cl[1] = l0;
+                        }
+                        l0 = l1;
+                        l1 = f;
+                        SYNCWARP();
+                    }
+                    const int first = l0;
+                    c_lwords += 2;
+                    if (first != bl && lit_value(first) == 1) {
+                        SETLANE(keep, src, 1);
+                        SETLANE(ebl, src, first);
+                        continue;
+                    }
+                    int found = -1;
+                    for (int b2 = 2; b2 < len && found < 0; b2 += 32) {
+                        const unsigned mm = BALLOT((b2 + lane < len) && lit_value(cl[b2 + lane]) != 0);
+                        c_lwords += (len - b2) < 32 ? (len - b2) : 32;
+                        if (mm) found = b2 + gpsat_ffs(mm) - 1;
+                    }
+                    if (found >= 0) {
+                        const int nl = cl[found];
+                        LANE0
+                        {
+                            cl[1] = nl;
+                            cl[found] = f;
+                        }
+                        SYNCWARP();
+                        lw_append(nl, cref, first);
+                        SETLANE(keep, src, 0);
+                        if (oom) {   // could not move the watch: keep the structure consistent and bail out
+                            LANE0
+                            {
+                                cl[found] = nl;
+                                cl[1] = f;
+                            }
+                            SYNCWARP();
+                            SETLANE(keep, src, 1);
+                            confl = cref;   // unwinds the loop; run_job() reports OOM
+                        }
+                        continue;
+                    }
+                    SETLANE(keep, src, 1);
+                    SETLANE(ebl, src, first);
+                    if (lit_value(first) == 0) {
+                        confl = cref;
+                    } else {
+                        enqueue(first, cref);
+                        c_implications++;
+                    }
+                }
+                const unsigned km = BALLOT(LV(keep) == 1);
+                LANES
+                {
+                    if (LV(keep) == 1) {
+                        const int dst = j + gpsat_popc(km & GPSAT_LANEMASK_LT);
+                        arena[wp + 2 * dst] = LV(ecr);
+                        arena[wp + 2 * dst + 1] = LV(ebl);
+                    }
+                }
+                j += gpsat_popc(km);
+                SYNCWARP();
+            }
+            LANE0 { lw_size[f] = j; }
+            SYNCWARP();
+            if (confl != GPSAT_NO_CONFLICT) return confl;
+        }
+        return GPSAT_NO_CONFLICT;
+    }
+
+    // ---- first-UIP analysis ----------------------------------------------------------------------------------
+    // fills lbuf[0..n_out) (lbuf[0] = asserting literal, lbuf[1] = a literal of the backjump level), returns n_out
+    GPSAT_DEV int analyze(int confl, int &bt_level)
+    {
+        GPSAT_LANE_DECL
+        int pathC = 0;
+        int p = -1;
+        int n_out = 1;
+        int index = trail_size - 1;
+        do {
+            const bool orig = confl >= 0;
+            const int s = orig ? confl : GPSAT_LEARNT_OFF(confl) + 1;
+            const int len = orig ? gpsat_ld2(cl2 + s - 1).x : arena[s - 1];
+            for (int b = 0; b < len; b += 32) {
+                LANEVAR(int, q);
+                LANEVAR(int, kind);   // 1: current level (path), 2: lower level (goes to the clause)
+                LANES
+                {
+                    LV(kind) = 0;
+                    LV(q) = 0;
+                    const int i = b + lane;
+                    if (i < len) {
+                        const int x = orig ? gpsat_ld2(cl2 + s + i).x : arena[s + i];
+                        const int v = x >> 1;
+                        LV(q) = x;
+                        if (x != p && !seen[v] && level[v] > 0) {
+                            seen[v] = 1;
+                            LV(kind) = (level[v] >= dlevel) ? 1 : 2;
+                        }
+                    }
+                }
+                SYNCWARP();
+                const unsigned m1 = BALLOT(LV(kind) == 1), m2 = BALLOT(LV(kind) == 2);
+                pathC += gpsat_popc(m1);
+                LANES
+                {
+                    if (LV(kind) == 2) lbuf[n_out + gpsat_popc(m2 & GPSAT_LANEMASK_LT)] = LV(q);
+                }
+                n_out += gpsat_popc(m2);
+                SYNCWARP();
+            }
+            // most recent seen literal on the trail
+            while (true) {
+                const unsigned m = BALLOT((index - lane >= 0) && seen[trail[index - lane] >> 1]);
+                if (m) {
+                    index -= gpsat_ffs(m) - 1;
+                    break;
+                }
+                index -= 32;
+            }
+            p = trail[index];
+            index--;
+            confl = reason[p >> 1];
+            LANE0 { seen[p >> 1] = 0; }
+            SYNCWARP();
+            pathC--;
+        } while (pathC > 0);
+        LANE0 { lbuf[0] = p ^ 1; }
+        SYNCWARP();
+
+        // backjump level = highest level among lbuf[1..); first such literal goes to position 1
+        bt_level = 0;
+        if (n_out > 1) {
+            LANEVAR(long long, best);
+            LANES
+            {
+                LV(best) = -1;
+                for (int i = 1 + lane; i < n_out; i += 32) {
+                    const long long key = ((long long)level[lbuf[i] >> 1] << 32) | (long long)(0x7fffffff - i);
+                    if (key > LV(best)) LV(best) = key;
+                }
+            }
+            const long long top = LANE_MAX_I64(best);
+            const int pos = 0x7fffffff - (int)(top & 0xffffffffll);
+            bt_level = (int)(top >> 32);
+            if (pos != 1) {
+                const int a = lbuf[1], b = lbuf[pos];
+                SYNCWARP();
+                LANE0
+                {
+                    lbuf[1] = b;
+                    lbuf[pos] = a;
+                }
+                SYNCWARP();
+            }
+        }
+        LANES
+        {
+            for (int i = 1 + lane; i < n_out; i += 32) seen[lbuf[i] >> 1] = 0;
+        }
+        SYNCWARP();
+        return n_out;
+    }
+
+    // order-sensitive checksum of a learnt clause, folded into c_hash
+    GPSAT_DEV void hash_learnt(int n_out)
+    {
+        GPSAT_LANE_DECL
+        LANEVAR(unsigned long long, part);
+        LANES
+        {
+            LV(part) = 0;
+            for (int i = lane; i < n_out; i += 32)
+                LV(part) += (unsigned long long)(lbuf[i] + 1) * (unsigned long long)(i + 1) * 0x9E3779B97F4A7C15ull;
+        }
+        const unsigned long long hsum = LANE_SUM_U64(part);
+        c_hash = c_hash * 0x100000001B3ull + hsum + (unsigned long long)n_out;
+    }
+
+    // store lbuf[0..n_out) as a learnt clause, watch positions 0 and 1; returns its cref (or NO_CONFLICT on OOM)
+    GPSAT_DEV int learn(int n_out)
+    {
+        GPSAT_LANE_DECL
+        if (n_learnts >= refs_cap || arena_top + n_out + 1 > watch_bot) {
+            oom = 1;
+            return GPSAT_NO_CONFLICT;
+        }
+        const int r = arena_top;
+        LANES
+        {
+            for (int i = lane; i < n_out; i += 32) arena[r + 1 + i] = lbuf[i];
+        }
+        LANE0
+        {
+            arena[r] = n_out;
+            refs[n_learnts] = r;
+        }
+        arena_top += n_out + 1;
+        n_learnts++;
+        SYNCWARP();
+        const int cref = GPSAT_LEARNT_CREF(r);
+        lw_append(lbuf[0], cref, lbuf[1]);
+        lw_append(lbuf[1], cref, lbuf[0]);
+        return oom ? GPSAT_NO_CONFLICT : cref;
+    }
+
+    // VSIDS::handle_clause on the learnt clause: +1 per literal, halve everything every 50 clauses
+    GPSAT_DEV void vsids_learnt(int n_out)
+    {
+        GPSAT_LANE_DECL
+        LANES
+        {
+            for (int i = lane; i < n_out; i += 32) vs[lbuf[i]] += 1;
+        }
+        SYNCWARP();
+        vs_clauses++;
+        if (vs_clauses % 50 == 0) {
+            LANES
+            {
+                for (int x = lane; x < 2 * n_vars; x += 32) vs[x] /= 2;
+            }
+            SYNCWARP();
+        }
+    }
+
+    // append a short learnt clause to the per-GPU pool (atomics on the cursor; header written last)
+    GPSAT_DEV void pool_publish(int n_out)
+    {
+        GPSAT_LANE_DECL
+        if (!share_learnts || n_out > share_max_len || pool == nullptr) return;
+        LANEVAR(int, off);
+        LANES { LV(off) = 0; }
+        LANE0 { LV(off) = gpsat_atomic_add(pool_cursor, n_out + 1); }
+        const int at = SHFL(off, 0);
+        if (at + n_out + 1 > pool_cap_words) return;   // pool full: clause stays private
+        LANES
+        {
+            for (int i = lane; i < n_out; i += 32) pool[at + 1 + i] = lbuf[i];
+        }
+        SYNCWARP();
+        gpsat_threadfence();
+        LANE0
+        {
+            pool[at] = n_out;
+            gpsat_atomic_add(pool_cursor + 1, 1);
+        }
+        SYNCWARP();
+    }
+
+    // ---- learnt database reduction ---------------------------------------------------------------------------
+    GPSAT_DEV bool locked(int r) const
+    {
+        const int x0 = arena[r + 1];
+        return lit_value(x0) == 1 && reason[x0 >> 1] == GPSAT_LEARNT_CREF(r);
+    }
+
+    // drop the longer half of the unlocked learnt clauses (len > 2), compact the arena, rebuild the watch vectors
+    GPSAT_DEV void reduce_db()
+    {
+        GPSAT_LANE_DECL
+        // 1. histogram of candidate lengths
+        LANES
+        {
+            for (int i = lane; i < 64; i += 32) hist[i] = 0;
+        }
+        SYNCWARP();
+        LANES
+        {
+            for (int i = lane; i < n_learnts; i += 32) {
+                const int r = refs[i];
+                const int len = arena[r];
+                if (len > 2 && !locked(r)) gpsat_atomic_add(hist + (len < 63 ? len : 63), 1);
+            }
+        }
+        SYNCWARP();
+        int n_cand = 0;
+        for (int b = 0; b < 64; ++b) n_cand += hist[b];
+        const int target = n_cand / 2;
+        int thr = 64, partial = 0;
+        {
+            int acc = 0;
+            for (int b = 63; b >= 3 && acc < target; --b) {
+                const int h = hist[b];
+                if (acc + h >= target) {
+                    thr = b;
+                    partial = target - acc;
+                    acc = target;
+                } else {
+                    acc += h;
+                }
+            }
+        }
+        // 2. mark (negative header) in age order, 3. compact, relocating reasons of locked clauses
+        int kept = 0;
+        int top = clause_base;
+        for (int base = 0; base < n_learnts; base += 32) {
+            LANEVAR(int, rr);
+            LANEVAR(int, ll);
+            LANEVAR(int, cls);   // 0 keep, 1 remove, 2 remove if partial budget left
+            LANES
+            {
+                const int i = base + lane;
+                LV(rr) = 0;
+                LV(ll) = 0;
+                LV(cls) = 0;
+                if (i < n_learnts) {
+                    const int r = refs[i];
+                    const int len = arena[r];
+                    LV(rr) = r;
+                    LV(ll) = len;
+                    if (len > 2 && !locked(r)) {
+                        const int b = len < 63 ? len : 63;
+                        LV(cls) = b > thr ? 1 : (b == thr ? 2 : 0);
+                    }
+                }
+            }
+            SYNCWARP();
+            const int cnt = (n_learnts - base) < 32 ? (n_learnts - base) : 32;
+            for (int t = 0; t < cnt; ++t) {
+                const int r = SHFL(rr, t);
+                const int len = SHFL(ll, t);
+                int c = SHFL(cls, t);
+                if (c == 2) {
+                    if (partial > 0) {
+                        partial--;
+                        c = 1;
+                    } else {
+                        c = 0;
+                    }
+                }
+                if (c == 1) continue;
+                if (top != r) {
+                    const int x0 = arena[r + 1];
+                    const bool lk = lit_value(x0) == 1 && reason[x0 >> 1] == GPSAT_LEARNT_CREF(r);
+                    SYNCWARP();
+                    // move down (top < r, ranges may overlap: ascending order, 32 words at a time)
+                    for (int w = 0; w < len + 1; w += 32) {
+                        LANEVAR(int, tmp);
+                        LANES
+                        {
+                            LV(tmp) = (w + lane < len + 1) ? arena[r + w + lane] : 0;
+                        }
+                        SYNCWARP();
+                        LANES
+                        {
+                            if (w + lane < len + 1) arena[top + w + lane] = LV(tmp);
+                        }
+                        SYNCWARP();
+                    }
+                    if (lk) {
+                        LANE0 { reason[x0 >> 1] = GPSAT_LEARNT_CREF(top); }
+                    }
+                }
+                LANE0 { refs[kept] = top; }
+                SYNCWARP();
+                kept++;
+                top += len + 1;
+            }
+        }
+        n_learnts = kept;
+        arena_top = top;
+        // 4. rebuild watch vectors: count, carve exact vectors from the top of the arena, fill in age order
+        LANES
+        {
+            for (int x = lane; x < 2 * n_vars; x += 32) lw_size[x] = 0;
+        }
+        SYNCWARP();
+        LANES
+        {
+            for (int i = lane; i < n_learnts; i += 32) {
+                const int r = refs[i];
+                gpsat_atomic_add(lw_size + arena[r + 1], 1);
+                gpsat_atomic_add(lw_size + arena[r + 2], 1);
+            }
+        }
+        SYNCWARP();
+        watch_bot = arena_words;
+        for (int base = 0; base < 2 * n_vars; base += 32) {
+            LANEVAR(int, cntv);
+            LANEVAR(int, ptrv);
+            LANES
+            {
+                const int x = base + lane;
+                LV(cntv) = x < 2 * n_vars ? lw_size[x] : 0;
+                LV(ptrv) = 0;
+            }
+            for (int t = 0; t < 32; ++t) {
+                const int c = SHFL(cntv, t);
+                if (c > 0) {
+                    watch_bot -= 2 * (2 * c + 4);
+                    SETLANE(ptrv, t, watch_bot);
+                }
+            }
+            LANES
+            {
+                const int x = base + lane;
+                if (x < 2 * n_vars) {
+                    lw_ptr[x] = LV(ptrv);
+                    lw_cap[x] = LV(cntv) > 0 ? 2 * LV(cntv) + 4 : 0;
+                    lw_size[x] = 0;
+                }
+            }
+            SYNCWARP();
+        }
+        if (watch_bot < arena_top) {
+            oom = 1;
+            return;
+        }
+        for (int i = 0; i < n_learnts; ++i) {
+            const int r = refs[i];
+            const int x0 = arena[r + 1], x1 = arena[r + 2];
+            lw_append(x0, GPSAT_LEARNT_CREF(r), x1);
+            lw_append(x1, GPSAT_LEARNT_CREF(r), x0);
+        }
+        max_learnts = max_learnts + max_learnts / 10 + 1;
+        if (max_learnts > refs_cap - n_vars - 2) max_learnts = refs_cap - n_vars - 2;
+    }
+
+    // ---- decisions -------------------------------------------------------------------------------------------
+    GPSAT_DEV int pick_branch()
+    {
+        GPSAT_LANE_DECL
+        if (decision_mode == GPSAT_DECIDE_VSIDS) {
+            LANEVAR(long long, best);
+            LANES
+            {
+                LV(best) = -1;
+                for (int v = lane; v < n_vars; v += 32) {
+                    if (val[v] != GPSAT_VAL_UNDEF) continue;
+                    const long long kp = ((long long)vs[2 * v + 1] << 32) | (long long)(0x7fffffff - 2 * v);
+                    const long long kn = ((long long)vs[2 * v] << 32) | (long long)(0x7fffffff - (2 * v + 1));
+                    const long long k = kp > kn ? kp : kn;
+                    if (k > LV(best)) LV(best) = k;
+                }
+            }
+            const long long top = LANE_MAX_I64(best);
+            if (top < 0) return -1;
+            const int o = 0x7fffffff - (int)(top & 0xffffffffll);   // order index: 2v = positive, 2v+1 = negative
+            return o ^ 1;
+        }
+        // shipped rule: topmost free variable, positive polarity
+        for (int base = n_vars - 1; base >= 0; base -= 32) {
+            const unsigned m = BALLOT((base - lane >= 0) && val[base - lane] == GPSAT_VAL_UNDEF);
+            if (m) return 2 * (base - (gpsat_ffs(m) - 1)) + 1;
+        }
+        return -1;
+    }
+
+    // ---- job -------------------------------------------------------------------------------------------------
+    GPSAT_DEV void reset_job()
+    {
+        GPSAT_LANE_DECL
+        LANES
+        {
+            for (int v = lane; v < n_vars; v += 32) {
+                val[v] = val0[v];
+                seen[v] = 0;
+            }
+            for (int w = lane; w < wbits_words; w += 32) wbits[w] = wbits0[w];
+            if (use_learnts) {
+                for (int x = lane; x < 2 * n_vars; x += 32) {
+                    vs[x] = vsids0[x];
+                    lw_size[x] = 0;
+                    lw_cap[x] = 0;
+                    lw_ptr[x] = 0;
+                }
+            }
+            LV(l_watchers) = 0;
+            LV(l_words) = 0;
+        }
+        trail_size = qhead = dlevel = 0;
+        arena_top = clause_base;
+        watch_bot = arena_words;
+        n_learnts = 0;
+        conflicts_since_restart = 0;
+        restart_limit = restart_first;
+        vs_clauses = n_clauses;
+        oom = 0;
+        c_decisions = c_implications = c_conflicts = c_learnt_clauses = c_learnt_literals = c_restarts = 0;
+        c_hash = 0;
+        c_lwatchers = c_lwords = 0;
+        SYNCWARP();
+    }
+
+    // Import the shared pool into this job's private database.  Pass 1: unit clauses become level-0 facts and are
+    // propagated; pass 2: longer clauses are attached with two non-false literals in front (or become facts /
+    // refute the formula).  Only records whose header is already published are read.
+    GPSAT_DEV int pool_import()
+    {
+        GPSAT_LANE_DECL
+        if (!share_learnts || pool == nullptr) return GPSAT_UNDEF;
+        int used = ((volatile int *)pool_cursor)[0];
+        if (used > pool_cap_words) used = pool_cap_words;
+        int at = 0;
+        while (at < used) {
+            const int len = ((volatile int *)pool)[at];
+            if (len <= 0 || at + 1 + len > used) break;
+            if (len == 1) {
+                const int u = pool[at + 1];
+                const int v = lit_value(u);
+                if (v == 0) return GPSAT_UNSAT;
+                if (v == 2) enqueue(u, GPSAT_REASON_NONE);
+            }
+            at += len + 1;
+        }
+        const int end_at = at;
+        if (propagate() != GPSAT_NO_CONFLICT) return GPSAT_UNSAT;
+        for (at = 0; at < end_at;) {
+            const int len = pool[at];
+            if (len >= 2 && len <= 32 && len <= lbuf_words) {
+                if ((watch_bot - arena_top) < (arena_words - clause_base) / 2) break;   // keep room for own clauses
+                LANEVAR(int, x);
+                LANEVAR(int, v);
+                LANES
+                {
+                    LV(x) = lane < len ? pool[at + 1 + lane] : 0;
+                    LV(v) = lane < len ? lit_value(LV(x)) : 0;
+                }
+                const unsigned in = len == 32 ? 0xffffffffu : ((1u << len) - 1u);
+                const unsigned mt = BALLOT(LV(v) == 1) & in;
+                const unsigned mnf = BALLOT(LV(v) != 0) & in;
+                if (!mt) {
+                    const int nf = gpsat_popc(mnf);
+                    if (nf == 0) return GPSAT_UNSAT;
+                    LANES
+                    {
+                        if (lane < len) {
+                            const bool isnf = (mnf >> lane) & 1u;
+                            const int dst = isnf ? gpsat_popc(mnf & GPSAT_LANEMASK_LT)
+                                                 : nf + gpsat_popc(~mnf & in & GPSAT_LANEMASK_LT);
+                            lbuf[dst] = LV(x);
+                        }
+                    }
+                    SYNCWARP();
+                    if (nf == 1) {
+                        enqueue(lbuf[0], GPSAT_REASON_NONE);
+                    } else if (learn(len) == GPSAT_NO_CONFLICT) {
+                        return GPSAT_JOB_OOM;
+                    }
+                }
+            }
+            at += len + 1;
+        }
+        if (propagate() != GPSAT_NO_CONFLICT) return GPSAT_UNSAT;
+        return GPSAT_UNDEF;
+    }
+
+    // Runs one cube.  mode SOLVE: full CDCL; mode PROPAGATE: stop once every cube literal is placed.
+    // returns GPSAT_SAT / GPSAT_UNSAT / GPSAT_UNDEF / GPSAT_JOB_ABORTED / GPSAT_JOB_OOM; conflict_out = falsified
+    // clause of the last conflict (cref) or NO_CONFLICT
+    GPSAT_DEV int run_job(const int *cube, int k, int mode, volatile const int *stop_flag, int &conflict_out)
+    {
+        conflict_out = GPSAT_NO_CONFLICT;
+        reset_job();
+        if (mode == GPSAT_MODE_SOLVE) {
+            const int st = pool_import();
+            if (st != GPSAT_UNDEF) return st;
+        }
+        while (true) {
+            const int confl = propagate();
+            if (oom) return GPSAT_JOB_OOM;
+            if (confl != GPSAT_NO_CONFLICT) {
+                conflict_out = confl;
+                c_conflicts++;
+                conflicts_since_restart++;
+                if (dlevel == 0 || mode == GPSAT_MODE_PROPAGATE) return GPSAT_UNSAT;
+                int bt;
+                const int n_out = analyze(confl, bt);
+                hash_learnt(n_out);
+                c_learnt_clauses++;
+                c_learnt_literals += n_out;
+                cancel_until(bt);
+                if (n_out == 1) {
+                    enqueue(lbuf[0], GPSAT_REASON_NONE);
+                } else {
+                    const int cref = learn(n_out);
+                    if (cref == GPSAT_NO_CONFLICT) return GPSAT_JOB_OOM;
+                    enqueue(lbuf[0], cref);
+                }
+                c_implications++;
+                if (decision_mode == GPSAT_DECIDE_VSIDS) vsids_learnt(n_out);
+                pool_publish(n_out);
+                if (max_conflicts && c_conflicts >= max_conflicts) return GPSAT_UNDEF;
+                if ((c_conflicts & 31) == 0 && stop_flag && *stop_flag) return GPSAT_JOB_ABORTED;
+                continue;
+            }
+            if (mode == GPSAT_MODE_PROPAGATE && dlevel >= k) return GPSAT_UNDEF;
+            if (restart_first > 0 && conflicts_since_restart >= restart_limit) {
+                conflicts_since_restart = 0;
+                restart_limit = (int)((float)restart_limit * restart_factor);
+                c_restarts++;
+                cancel_until(k < dlevel ? k : dlevel);
+            }
+            if (n_learnts >= max_learnts || (watch_bot - arena_top) < (arena_words - clause_base) / 4) {
+                reduce_db();
+                if (oom) return GPSAT_JOB_OOM;
+            }
+            int next = -1;
+            while (dlevel < k) {
+                const int x = cube[dlevel];
+                const int v = lit_value(x);
+                if (v == 1) {
+                    new_level();
+                } else if (v == 0) {
+                    return GPSAT_UNSAT;   // the cube contradicts what propagation already fixed
+                } else {
+                    next = x;
+                    break;
+                }
+            }
+            if (next < 0) {
+                if (mode == GPSAT_MODE_PROPAGATE) return GPSAT_UNDEF;
+                next = pick_branch();
+                if (next < 0) return GPSAT_SAT;
+                c_decisions++;
+                if (max_iterations && c_decisions > max_iterations) return GPSAT_UNDEF;
+            }
+            new_level();
+            enqueue(next, GPSAT_REASON_NONE);
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// glue shared by the kernel and the test-only emulator: point a WarpSolver at its memory, run one job, record it
+// ---------------------------------------------------------------------------------------------------------------
+GPSAT_DEV void gpsat_bind(WarpSolver &S, const gpsat_formula_view &F, const gpsat_solve_params &P,
+                          const gpsat_state_layout &Ly, int *state, int *arena, const gpsat_run_buffers &B)
+{
+    S.n_vars = F.n_vars;
+    S.n_clauses = F.n_clauses;
+    S.n_lits = F.n_lits;
+    S.wbits_words = F.wbits_words;
+    S.cl2 = (const gint2 *)F.cl2;
+    S.ostart = F.ostart;
+    S.occ2 = (const gint2 *)F.occ2;
+    S.wbits0 = F.wbits0;
+    S.vsids0 = F.vsids0;
+    S.val0 = F.val0;
+    S.val = (uint8_t *)(state + Ly.val);
+    S.seen = (uint8_t *)(state + Ly.seen);
+    S.level = state + Ly.level;
+    S.reason = state + Ly.reason;
+    S.trail = state + Ly.trail;
+    S.trail_lim = state + Ly.trail_lim;
+    S.wbits = (uint32_t *)(state + Ly.wbits);
+    S.vs = state + Ly.vs;
+    S.lbuf = state + Ly.lbuf;
+    S.lbuf_words = Ly.lbuf_words;
+    S.use_learnts = (P.mode == GPSAT_MODE_SOLVE) ? 1 : 0;
+    S.arena = arena;
+    S.arena_words = (int)P.arena_words;
+    S.lw_ptr = arena;
+    S.lw_size = arena + 2 * F.n_vars;
+    S.lw_cap = arena + 4 * F.n_vars;
+    S.hist = arena + 6 * F.n_vars;
+    S.refs = arena + 6 * F.n_vars + 64;
+    S.refs_cap = P.learnt_refs_cap;
+    S.clause_base = 6 * F.n_vars + 64 + P.learnt_refs_cap;
+    S.max_learnts = P.max_learnts_first;
+    S.decision_mode = P.decision;
+    S.restart_first = P.restart_first;
+    S.restart_factor = P.restart_factor;
+    S.max_iterations = P.max_iterations;
+    S.max_conflicts = P.max_conflicts;
+    S.share_learnts = P.share_learnts;
+    S.share_max_len = P.share_max_len;
+    S.pool = B.pool;
+    S.pool_cursor = B.pool_cursor;
+    S.pool_cap_words = B.pool_cap_words;
+}
+
+GPSAT_DEV void gpsat_run_and_record(WarpSolver &S, int job, const gpsat_solve_params &P, const gpsat_run_buffers &B)
+{
+    GPSAT_LANE_DECL
+    const long long c0 = B.cube_offsets[job], c1 = B.cube_offsets[job + 1];
+    const int *cube = B.cube_lits + c0;
+    const int k = (int)(c1 - c0);
+    int confl;
+    S.max_learnts = P.max_learnts_first;
+    const int status = S.run_job(cube, k, P.mode, B.stop_flag, confl);
+
+    const long long watchers = LANE_SUM_I64(S.l_watchers) + S.c_lwatchers;
+    const long long words = LANE_SUM_I64(S.l_words) + S.c_lwords;
+    LANE0
+    {
+        gpsat_job_record r;
+        r.status = status;
+        r.reserved = 0;
+        r.decisions = S.c_decisions;
+        r.implications = S.c_implications;
+        r.conflicts = S.c_conflicts;
+        r.learnt_clauses = S.c_learnt_clauses;
+        r.learnt_literals = S.c_learnt_literals;
+        r.restarts = S.c_restarts;
+        r.watchers_visited = watchers;
+        r.clause_words_read = words;
+        r.learnt_hash = (long long)S.c_hash;
+        B.records[job] = r;
+    }
+    if (P.mode == GPSAT_MODE_PROPAGATE) {
+        if (B.conflict_clause) {
+            long long cidx = -1;
+            if (status == GPSAT_UNSAT && confl != GPSAT_NO_CONFLICT && confl >= 0) cidx = gpsat_ld2(S.cl2 + confl - 1).y;
+            LANE0 { B.conflict_clause[job] = cidx; }
+        }
+        // implied literals = trail entries with a reason, cube variables excluded, trail order
+        LANES
+        {
+            for (int i = lane; i < k; i += 32) S.seen[cube[i] >> 1] = 1;
+        }
+        SYNCWARP();
+        int n_imp = 0;
+        for (int base = 0; base < S.trail_size; base += 32) {
+            LANEVAR(int, x);
+            LANEVAR(int, take);
+            LANES
+            {
+                const int i = base + lane;
+                LV(take) = 0;
+                LV(x) = 0;
+                if (i < S.trail_size) {
+                    LV(x) = S.trail[i];
+                    LV(take) = (S.reason[LV(x) >> 1] != GPSAT_REASON_NONE && !S.seen[LV(x) >> 1]) ? 1 : 0;
+                }
+            }
+            const unsigned m = BALLOT(LV(take) != 0);
+            if (B.implied) {
+                LANES
+                {
+                    if (LV(take)) {
+                        const long long dst = n_imp + gpsat_popc(m & GPSAT_LANEMASK_LT);
+                        if (dst < P.implied_stride) B.implied[(long long)job * P.implied_stride + dst] = LV(x);
+                    }
+                }
+            }
+            n_imp += gpsat_popc(m);
+        }
+        SYNCWARP();
+        LANES
+        {
+            for (int i = lane; i < k; i += 32) S.seen[cube[i] >> 1] = 0;
+        }
+        if (B.n_implied) {
+            LANE0 { B.n_implied[job] = n_imp; }
+        }
+        SYNCWARP();
+        return;
+    }
+    if (status == GPSAT_SAT) {
+        LANEVAR(int, won);
+        LANES { LV(won) = 0; }
+        LANE0 { LV(won) = (gpsat_atomic_cas(B.sat_job, -1, job) == -1) ? 1 : 0; }
+        if (SHFL(won, 0)) {
+            LANES
+            {
+                for (int v = lane; v < S.n_vars; v += 32) B.model[v] = (S.val[v] == GPSAT_VAL_FALSE) ? 0 : 1;
+            }
+            SYNCWARP();
+            gpsat_threadfence();
+            if (P.stop_on_sat) {
+                LANE0 { gpsat_atomic_cas(B.stop_flag, 0, 1); }
+            }
+        }
+    }
+}

@@ -1,0 +1,108 @@
+// Plain-data structures shared by the host API (gpsat_api.cu), the kernels (kernels.cu) and the per-warp solver
+// (cdcl_warp.inl).  No CUDA types here so the test-only lockstep emulator can include it too.
+#pragma once
+#include <stdint.h>
+#include "../../include/gpsat.h"
+
+#define GPSAT_NO_CONFLICT ((int)0x80000000)
+#define GPSAT_REASON_NONE (-1)
+// clause references: >= 0  original clause = slot of its first literal in cl2 (header at slot-1);
+//                    <= -2 learnt clause at arena word r = -2 - cref
+#define GPSAT_LEARNT_CREF(r) (-2 - (r))
+#define GPSAT_LEARNT_OFF(cref) (-2 - (cref))
+
+#define GPSAT_MODE_SOLVE 0
+#define GPSAT_MODE_PROPAGATE 1
+
+#define GPSAT_VAL_FALSE 0
+#define GPSAT_VAL_TRUE 1
+#define GPSAT_VAL_UNDEF 2
+#define GPSAT_VAL_ABSENT 4   // variable does not occur in the formula: assignable by a cube, never decided
+
+// job status beyond the public verdicts
+#define GPSAT_JOB_NOT_RUN (-1)
+#define GPSAT_JOB_ABORTED (-2)   // stopped by the early-termination flag
+#define GPSAT_JOB_OOM (-3)       // learnt arena exhausted even after reduction
+
+struct gpsat_formula_view {
+    int32_t n_vars;
+    int32_t n_clauses;
+    int32_t n_lits;
+    int32_t wbits_words;
+    const int32_t *cstart;    // n_clauses+1 : clause index -> header slot in cl2 (literals follow)
+    const void *cl2;          // int2[n_lits + n_clauses] : header (len, clause index) then (literal, occurrence slot)
+    const int32_t *ostart;    // 2*n_vars+1
+    const void *occ2;         // int2[n_lits] : (first literal slot, len) of the clause owning occurrence slot k
+    const uint32_t *wbits0;   // initial watch bitmap over occurrence slots
+    const int32_t *vsids0;    // 2*n_vars initial VSIDS counters
+    const uint8_t *val0;      // n_vars initial values: UNDEF or ABSENT
+};
+
+struct gpsat_solve_params {
+    int32_t mode;             // GPSAT_MODE_*
+    int32_t decision;         // GPSAT_DECIDE_*
+    int32_t bcp;              // GPSAT_BCP_*
+    int32_t restart_first;
+    float restart_factor;
+    int32_t max_iterations;
+    int32_t stop_on_sat;
+    int32_t share_learnts;
+    int32_t share_max_len;
+    int32_t max_learnts_first;   // learnt clauses kept before the first reduction
+    int32_t learnt_refs_cap;     // capacity of the per-warp learnt clause list
+    int64_t max_conflicts;
+    int64_t arena_words;         // per warp
+    int64_t implied_stride;      // propagate mode: words reserved per cube in `implied`
+};
+
+// word offsets (int32 units) of the per-warp state arrays inside one warp's state block
+struct gpsat_state_layout {
+    int32_t val, seen, level, reason, trail, trail_lim, wbits, vs, lbuf;
+    int32_t total_words;
+    int32_t lbuf_words;
+};
+
+struct gpsat_run_buffers {
+    const int64_t *cube_offsets;   // n_cubes+1
+    const int32_t *cube_lits;
+    int32_t n_cubes;
+    int32_t *next_job;             // atomic cursor (≙ JobsQueue::next_job_index)
+    int32_t *stop_flag;            // 0 run, 1 SAT found, 2 external stop
+    int32_t *sat_job;              // first SAT job index (-1)
+    uint8_t *model;                // n_vars, written by the SAT job that wins sat_job
+    gpsat_job_record *records;     // n_cubes
+    int32_t *implied;              // propagate mode (may be null)
+    int32_t *n_implied;            // propagate mode (may be null)
+    int64_t *conflict_clause;      // propagate mode (may be null)
+    int32_t *arena;                // n_warps * arena_words
+    int32_t *gstate;               // n_warps * layout.total_words when state is not in shared memory
+    int32_t *pool;                 // shared learnt pool words
+    int32_t *pool_cursor;          // [0] words used, [1] clauses
+    int32_t pool_cap_words;
+    int32_t state_in_smem;
+    unsigned long long deadline_ns;   // globaltimer deadline for pulling new jobs, 0 = none
+};
+
+// per-warp state block: word offsets of each array (every array starts on a 16-byte boundary)
+static inline void gpsat_make_layout(int32_t n_vars, int64_t n_lits, gpsat_state_layout *ly)
+{
+    int32_t at = 0;
+    const int32_t n = n_vars > 0 ? n_vars : 1;
+#define GPSAT_TAKE(field, words)          \
+    do {                                  \
+        ly->field = at;                   \
+        at += (((words) + 3) / 4) * 4;    \
+    } while (0)
+    GPSAT_TAKE(val, (n + 3) / 4);
+    GPSAT_TAKE(seen, (n + 3) / 4);
+    GPSAT_TAKE(level, n);
+    GPSAT_TAKE(reason, n);
+    GPSAT_TAKE(trail, n);
+    GPSAT_TAKE(trail_lim, n + 1);
+    GPSAT_TAKE(wbits, (int32_t)((n_lits + 31) / 32));
+    GPSAT_TAKE(vs, 2 * n);
+    ly->lbuf_words = (n + 1) > 64 ? (n + 1) : 64;
+    GPSAT_TAKE(lbuf, ly->lbuf_words);
+#undef GPSAT_TAKE
+    ly->total_words = at;
+}

@@ -1,0 +1,121 @@
+// Warp-lockstep vocabulary used by cdcl_warp.inl.
+//
+// The per-cube solver is written as warp-synchronous code: control flow is warp-uniform, and everything that
+// differs per lane lives inside LANES { } phases, with ballots / shuffles between phases.  On the GPU (the product)
+// these macros are the CUDA warp intrinsics and per-lane variables are registers.
+//
+// GPSAT_WARP_EMU is a TEST-ONLY build mode (tests/emu/, never part of libgpsat.so): the same source compiled by
+// g++ with the 32 lanes of a phase run one after the other, so the kernel logic can be stepped and compared with
+// the oracle on a machine without a GPU.  It is a debugging aid for the kernel source, not a CPU fallback: nothing
+// in the product links or dispatches to it, and the C ABI fails with GPSAT_E_NO_DEVICE when there is no GPU.
+//
+// Phase discipline (what makes both readings equivalent): inside one LANES phase a lane never reads memory that
+// another lane writes in that same phase, except through the commutative atomics below; phases that communicate
+// through memory are separated by SYNCWARP().
+#pragma once
+#include <stdint.h>
+
+#if defined(GPSAT_WARP_EMU)
+
+#include <cstring>
+#define GPSAT_DEV inline
+#define GPSAT_LANE_DECL
+#define LANEVAR(T, name) T name[32]
+#define LV(name) name[lane]
+#define LANES for (int lane = 0; lane < 32; ++lane)
+#define BALLOT(expr)                                      \
+    ([&]() -> unsigned {                                  \
+        unsigned m_ = 0;                                  \
+        for (int lane = 0; lane < 32; ++lane)             \
+            if (expr) m_ |= 1u << lane;                   \
+        return m_;                                        \
+    }())
+#define SHFL(name, src) (name[(src)])
+#define SETLANE(name, src, value) (name[(src)] = (value))
+#define SYNCWARP() ((void)0)
+#define LANE0 for (int lane = 0; lane < 1; ++lane)
+#define LANE_SUM_I64(name)                                \
+    ([&]() -> long long {                                 \
+        long long s_ = 0;                                 \
+        for (int l_ = 0; l_ < 32; ++l_) s_ += name[l_];   \
+        return s_;                                        \
+    }())
+#define LANE_MAX_I64(name)                                \
+    ([&]() -> long long {                                 \
+        long long s_ = name[0];                           \
+        for (int l_ = 1; l_ < 32; ++l_)                   \
+            if (name[l_] > s_) s_ = name[l_];             \
+        return s_;                                        \
+    }())
+#define LANE_SUM_U64(name)                                \
+    ([&]() -> unsigned long long {                        \
+        unsigned long long s_ = 0;                        \
+        for (int l_ = 0; l_ < 32; ++l_) s_ += name[l_];   \
+        return s_;                                        \
+    }())
+static inline void gpsat_atomic_or(uint32_t *p, uint32_t v) { *p |= v; }
+static inline void gpsat_atomic_and(uint32_t *p, uint32_t v) { *p &= v; }
+static inline int gpsat_atomic_add(int *p, int v) { int o = *p; *p += v; return o; }
+static inline int gpsat_atomic_cas(int *p, int cmp, int v) { int o = *p; if (o == cmp) *p = v; return o; }
+static inline void gpsat_threadfence() {}
+static inline int gpsat_popc(unsigned m) { return __builtin_popcount(m); }
+static inline int gpsat_ffs(unsigned m) { return __builtin_ffs((int)m); }
+struct gpsat_int2 { int x, y; };
+typedef gpsat_int2 gint2;
+static inline gint2 gpsat_ld2(const gint2 *p) { return *p; }
+static inline int gpsat_ld(const int *p) { return *p; }
+
+#else  // ---- CUDA device build ----
+
+#define GPSAT_DEV __device__ __forceinline__
+#define GPSAT_LANE_DECL const int lane = (int)(threadIdx.x & 31u);
+#define LANEVAR(T, name) T name
+#define LV(name) name
+#define LANES
+#define BALLOT(expr) __ballot_sync(0xffffffffu, (expr))
+#define SHFL(name, src) __shfl_sync(0xffffffffu, name, (src))
+#define SETLANE(name, src, value) \
+    do {                          \
+        if (lane == (src)) name = (value); \
+    } while (0)
+#define SYNCWARP() __syncwarp()
+#define LANE0 if (lane == 0)
+__device__ __forceinline__ long long gpsat_warp_sum_i64(long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ unsigned long long gpsat_warp_sum_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ long long gpsat_warp_max_i64(long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        long long w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = w > v ? w : v;
+    }
+    return v;
+}
+#define LANE_SUM_I64(name) gpsat_warp_sum_i64((long long)(name))
+#define LANE_SUM_U64(name) gpsat_warp_sum_u64((unsigned long long)(name))
+#define LANE_MAX_I64(name) gpsat_warp_max_i64((long long)(name))
+__device__ __forceinline__ void gpsat_atomic_or(uint32_t *p, uint32_t v) { atomicOr(p, v); }
+__device__ __forceinline__ void gpsat_atomic_and(uint32_t *p, uint32_t v) { atomicAnd(p, v); }
+__device__ __forceinline__ int gpsat_atomic_add(int *p, int v) { return atomicAdd(p, v); }
+__device__ __forceinline__ int gpsat_atomic_cas(int *p, int cmp, int v) { return atomicCAS(p, cmp, v); }
+__device__ __forceinline__ void gpsat_threadfence() { __threadfence(); }
+__device__ __forceinline__ int gpsat_popc(unsigned m) { return __popc(m); }
+__device__ __forceinline__ int gpsat_ffs(unsigned m) { return __ffs((int)m); }
+typedef int2 gint2;
+// read-only formula index: non-coherent path, stays in L1 across the jobs of an SM
+__device__ __forceinline__ gint2 gpsat_ld2(const gint2 *p) { return __ldg(p); }
+__device__ __forceinline__ int gpsat_ld(const int *p) { return __ldg(p); }
+
+#endif
+
+#define GPSAT_LANEMASK_LT ((1u << lane) - 1u)

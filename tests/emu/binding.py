@@ -1,0 +1,72 @@
+"""TEST-ONLY: builds and binds the lockstep emulator of the kernel source (tests/emu/emu.cpp)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+SO = os.path.join(HERE, "libgpsat_emu.so")
+
+RECORD_DTYPE = np.dtype([
+    ("status", np.int32), ("reserved", np.int32), ("decisions", np.int64), ("implications", np.int64),
+    ("conflicts", np.int64), ("learnt_clauses", np.int64), ("learnt_literals", np.int64), ("restarts", np.int64),
+    ("watchers_visited", np.int64), ("clause_words_read", np.int64), ("learnt_hash", np.int64)])
+
+
+class SolveParams(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("decision", C.c_int32), ("bcp", C.c_int32), ("restart_first", C.c_int32),
+                ("restart_factor", C.c_float), ("max_iterations", C.c_int32), ("stop_on_sat", C.c_int32),
+                ("share_learnts", C.c_int32), ("share_max_len", C.c_int32), ("max_learnts_first", C.c_int32),
+                ("learnt_refs_cap", C.c_int32), ("max_conflicts", C.c_int64), ("arena_words", C.c_int64),
+                ("implied_stride", C.c_int64)]
+
+
+def build(force=False):
+    srcs = [os.path.join(HERE, "emu.cpp"), os.path.join(ROOT, "gpupsat_b200", "csrc", "host_formula.cpp")]
+    deps = srcs + [os.path.join(ROOT, "gpupsat_b200", "csrc", f) for f in
+                   ("cdcl_warp.inl", "warp_lockstep.h", "gpsat_device.h", "host_formula.h")]
+    if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
+        return
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unused-variable", "-fPIC", "-shared", "-o", SO] + srcs)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def run(n_vars, offsets, lits, cube_offsets, cube_lits, *, mode=0, decision=1, restart_first=100, restart_factor=1.3,
+        max_iterations=0, max_conflicts=0, max_learnts_first=None, learnt_refs_cap=16384, arena_words=1 << 19,
+        stop_on_sat=True, share_learnts=0, share_max_len=8, pool=None, pool_cursor=None):
+    build()
+    lib = C.CDLL(SO)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    lits = np.ascontiguousarray(lits, dtype=np.int32)
+    co = np.ascontiguousarray(cube_offsets, dtype=np.int64)
+    cl = np.ascontiguousarray(cube_lits, dtype=np.int32)
+    n_cubes = len(co) - 1
+    m = len(offsets) - 1
+    if max_learnts_first is None:
+        max_learnts_first = max(min(max(m // 3, 300), learnt_refs_cap - n_vars - 2), 1)
+    P = SolveParams(mode, decision, 0, restart_first, restart_factor, max_iterations, 1 if stop_on_sat else 0,
+                    share_learnts, share_max_len, max_learnts_first, learnt_refs_cap, max_conflicts, arena_words,
+                    n_vars)
+    rec = np.zeros(n_cubes, dtype=RECORD_DTYPE)
+    model = np.zeros(max(n_vars, 1), dtype=np.uint8)
+    sat_job = C.c_int32(-1)
+    implied = np.full(max(n_cubes * n_vars, 1), -1, dtype=np.int32)
+    n_implied = np.zeros(n_cubes, dtype=np.int32)
+    confl = np.full(n_cubes, -1, dtype=np.int64)
+    if pool is None:
+        pool = np.zeros(1 << 16, dtype=np.int32)
+        pool_cursor = np.zeros(2, dtype=np.int32)
+    rc = lib.gpsat_emu_run(C.c_int32(n_vars), C.c_int64(m), _p(offsets), _p(lits), C.byref(P), C.c_int32(n_cubes),
+                           _p(co), _p(cl), _p(rec), _p(model), C.byref(sat_job), _p(implied), _p(n_implied), _p(confl),
+                           _p(pool), _p(pool_cursor), C.c_int32(len(pool)))
+    assert rc == 0, rc
+    return {"records": rec, "sat_job": sat_job.value, "model": model[:n_vars],
+            "implied": implied.reshape(n_cubes, n_vars) if n_vars else implied, "n_implied": n_implied,
+            "conflict_clause": confl, "pool": pool, "pool_cursor": pool_cursor}

@@ -1,0 +1,64 @@
+// TEST-ONLY lockstep emulator of the kernel source (gpupsat_b200/csrc/cdcl_warp.inl compiled with
+// GPSAT_WARP_EMU).  It lets the CPU test-suite step the exact warp program the GPU runs and compare it with
+// the oracle when no GPU is present.  Never linked into libgpsat.so; not a fallback of any kind.
+#define GPSAT_WARP_EMU 1
+#include <vector>
+#include <cstring>
+#include "../../gpupsat_b200/csrc/cdcl_warp.inl"
+#include "../../gpupsat_b200/csrc/host_formula.h"
+
+extern "C" int gpsat_emu_run(int32_t n_vars, int64_t n_clauses, const int64_t *offsets, const int32_t *lits,
+                             const gpsat_solve_params *params, int32_t n_cubes, const int64_t *cube_offsets,
+                             const int32_t *cube_lits, gpsat_job_record *records, uint8_t *model, int32_t *sat_job,
+                             int32_t *implied, int32_t *n_implied, int64_t *conflict_clause, int32_t *pool,
+                             int32_t *pool_cursor, int32_t pool_cap_words)
+{
+    gpsat_host::DeviceFormula D;
+    int rc = gpsat_host::build_device_formula(n_vars, n_clauses, offsets, lits, D);
+    if (rc != 0) return rc;
+    gpsat_formula_view F;
+    F.n_vars = D.n_vars;
+    F.n_clauses = (int32_t)D.n_clauses;
+    F.n_lits = (int32_t)D.n_lits;
+    F.wbits_words = (int32_t)D.wbits0.size();
+    F.cstart = D.cstart.data();
+    F.cl2 = D.cl2.data();
+    F.ostart = D.ostart.data();
+    F.occ2 = D.occ2.data();
+    F.wbits0 = D.wbits0.data();
+    F.vsids0 = D.vsids0.data();
+    F.val0 = D.val0.data();
+    gpsat_solve_params P = *params;
+    gpsat_state_layout Ly;
+    gpsat_make_layout(n_vars, D.n_lits, &Ly);
+    std::vector<int32_t> state((size_t)Ly.total_words, 0);
+    std::vector<int32_t> arena((size_t)P.arena_words, 0);
+    int32_t next_job = 0, stop_flag = 0;
+    *sat_job = -1;
+    gpsat_run_buffers B;
+    std::memset(&B, 0, sizeof(B));
+    B.cube_offsets = cube_offsets;
+    B.cube_lits = cube_lits;
+    B.n_cubes = n_cubes;
+    B.next_job = &next_job;
+    B.stop_flag = &stop_flag;
+    B.sat_job = sat_job;
+    B.model = model;
+    B.records = records;
+    B.implied = implied;
+    B.n_implied = n_implied;
+    B.conflict_clause = conflict_clause;
+    B.arena = arena.data();
+    B.pool = pool;
+    B.pool_cursor = pool_cursor;
+    B.pool_cap_words = pool_cap_words;
+    for (int j = 0; j < n_cubes; j++) records[j].status = GPSAT_JOB_NOT_RUN;
+    WarpSolver S;
+    std::memset(&S, 0, sizeof(S));
+    gpsat_bind(S, F, P, Ly, state.data(), arena.data(), B);
+    for (int j = 0; j < n_cubes; j++) {
+        if (stop_flag) break;
+        gpsat_run_and_record(S, j, P, B);
+    }
+    return 0;
+}
