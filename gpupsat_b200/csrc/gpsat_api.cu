@@ -1,0 +1,806 @@
+// C ABI of the device side (include/gpsat.h): handle management, uploads, launches, result gathering.
+// One handle = one GPU = one host thread.  No CPU fallback: without a usable device every entry point fails with
+// GPSAT_E_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gpsat.h"
+#include "gpsat_device.h"
+#include "host_formula.h"
+#include "kernels.h"
+
+namespace {
+
+using gpsat_host::set_error;
+
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                           \
+            return (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? GPSAT_E_NO_DEVICE \
+                                                                                  : GPSAT_E_CUDA;    \
+        }                                                                                            \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { release(); }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    cudaError_t ensure(size_t count)
+    {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    cudaError_t upload(const T *src, size_t count, cudaStream_t s)
+    {
+        cudaError_t e = ensure(count);
+        if (e != cudaSuccess || count == 0) return e;
+        return cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+};
+
+// The per-warp arenas are the one big allocation (GBs).  Keep the last released one per device so that
+// create/destroy cycles (one per solve in the e2e path) do not pay cudaMalloc/cudaFree of it every time.
+struct ArenaCache {
+    int device = -1;
+    int32_t *p = nullptr;
+    size_t words = 0;
+};
+ArenaCache g_arena_cache;
+
+}  // namespace
+
+struct gpsat {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+    gpsat_opts opts{};
+    gpsat_host::DeviceFormula D;
+    std::vector<int32_t> coffsets_h;   // compact CSR offsets (int32) for the evaluation kernel / index lookups
+    // device formula
+    DevBuf<int32_t> cstart, cl2, ostart, occ2, vsids0, coffsets, clits;
+    DevBuf<uint32_t> wbits0;
+    DevBuf<uint8_t> val0;
+    // cubes
+    int32_t n_cubes = 0;
+    bool cubes_set = false;
+    std::vector<int64_t> cube_offsets_h;
+    DevBuf<int64_t> cube_offsets;
+    DevBuf<int32_t> cube_lits;
+    // run buffers
+    DevBuf<int32_t> ctrl;              // [0] next_job [1] stop_flag [2] sat_job
+    DevBuf<unsigned long long> t0;
+    DevBuf<uint8_t> model;
+    DevBuf<gpsat_job_record> records;
+    DevBuf<int32_t> implied, n_implied;
+    DevBuf<int64_t> conflict_clause;
+    DevBuf<int32_t> gstate;
+    DevBuf<int32_t> pool, pool_cursor;
+    int32_t *arena = nullptr;
+    size_t arena_total_words = 0;
+    int64_t pool_export_mark = 0;
+    // geometry
+    gpsat_state_layout Ly{};
+    int blocks = 0, warps_per_block = 0, state_in_smem = 0;
+    size_t smem_bytes = 0;
+    int64_t arena_words = 0;
+    // last run
+    std::vector<gpsat_job_record> records_h;
+    bool solving = false;
+    int32_t run_mode = GPSAT_MODE_SOLVE;
+    double kernel_ms = 0;
+    int kernel_launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+const int64_t kPoolWords = 1 << 22;   // 16 MB shared learnt pool per GPU
+
+gpsat_formula_view make_view(gpsat *h)
+{
+    gpsat_formula_view F;
+    F.n_vars = h->D.n_vars;
+    F.n_clauses = (int32_t)h->D.n_clauses;
+    F.n_lits = (int32_t)h->D.n_lits;
+    F.wbits_words = (int32_t)h->D.wbits0.size();
+    F.cstart = h->cstart.p;
+    F.cl2 = h->cl2.p;
+    F.ostart = h->ostart.p;
+    F.occ2 = h->occ2.p;
+    F.wbits0 = h->wbits0.p;
+    F.vsids0 = h->vsids0.p;
+    F.val0 = h->val0.p;
+    return F;
+}
+
+int32_t default_max_learnts(int64_t n_clauses, int32_t refs_cap, int32_t n_vars)
+{
+    int64_t v = std::max<int64_t>(n_clauses / 3, 300);
+    v = std::min<int64_t>(v, (int64_t)refs_cap - n_vars - 2);
+    return (int32_t)std::max<int64_t>(v, 1);
+}
+
+gpsat_solve_params make_params(gpsat *h, int mode, int64_t implied_stride)
+{
+    gpsat_solve_params P;
+    std::memset(&P, 0, sizeof(P));
+    P.mode = mode;
+    P.decision = h->opts.decision;
+    P.bcp = h->opts.bcp;
+    P.restart_first = h->opts.restart_first;
+    P.restart_factor = h->opts.restart_factor;
+    P.max_iterations = h->opts.max_iterations;
+    P.stop_on_sat = h->opts.stop_on_sat;
+    P.share_learnts = h->opts.share_learnts;
+    P.share_max_len = std::min(h->opts.share_max_len, 32);
+    P.learnt_refs_cap = 16384;
+    if (P.learnt_refs_cap < h->D.n_vars + 64) P.learnt_refs_cap = h->D.n_vars + 64;
+    P.max_learnts_first = default_max_learnts(h->D.n_clauses, P.learnt_refs_cap, h->D.n_vars);
+    P.max_conflicts = h->opts.max_conflicts;
+    P.arena_words = mode == GPSAT_MODE_SOLVE ? h->arena_words : 0;
+    P.implied_stride = implied_stride;
+    return P;
+}
+
+// launch geometry: as many resident warps per SM as shared memory (per-job state) and registers allow
+int plan_geometry(gpsat *h, int mode)
+{
+    gpsat_make_layout(h->D.n_vars, h->D.n_lits, &h->Ly);
+    const size_t bytes_per_warp = (size_t)h->Ly.total_words * 4;
+    const size_t smem_block_max = h->prop.sharedMemPerBlockOptin;                 // 227 KB on B200
+    const size_t smem_sm = h->prop.sharedMemPerMultiprocessor;                    // 228 KB
+    int w = h->opts.warps_per_block;
+    int bps = 1;
+    h->state_in_smem = 1;
+    if (w <= 0) {
+        const int fit_sm = (int)std::min<size_t>(64, (smem_sm - 2048) / std::max<size_t>(bytes_per_warp, 1));
+        if (fit_sm >= 4) {
+            if (fit_sm <= 32) {
+                w = fit_sm;
+            } else {
+                bps = 2;
+                w = std::min(32, fit_sm / 2);
+            }
+        } else {
+            h->state_in_smem = 0;
+            w = 16;
+            bps = 2;
+        }
+    } else if ((size_t)w * bytes_per_warp > smem_block_max) {
+        h->state_in_smem = 0;
+    }
+    if (w > 32) w = 32;
+    h->warps_per_block = w;
+    h->smem_bytes = h->state_in_smem ? (size_t)w * bytes_per_warp : 0;
+    int occ = 0;
+    CU(gpsat_kernels::cdcl_occupancy(w, h->smem_bytes, &occ));
+    if (occ < 1) {
+        set_error("kernel configuration does not fit on an SM");
+        return GPSAT_E_CUDA;
+    }
+    (void)bps;
+    int blocks = h->opts.blocks > 0 ? h->opts.blocks : h->prop.multiProcessorCount * occ;
+    // never launch more warps than cubes (each warp owns an arena / state block)
+    const int64_t need = ((int64_t)std::max(h->n_cubes, 1) + w - 1) / w;
+    if (blocks > need) blocks = (int)need;
+    h->blocks = std::max(blocks, 1);
+    (void)mode;
+    return GPSAT_OK;
+}
+
+int ensure_run_buffers(gpsat *h, int mode)
+{
+    const size_t n_warps = (size_t)h->blocks * h->warps_per_block;
+    CU(h->ctrl.ensure(4));
+    CU(h->t0.ensure(1));
+    CU(h->model.ensure((size_t)std::max(h->D.n_vars, 1)));
+    CU(h->records.ensure((size_t)std::max(h->n_cubes, 1)));
+    if (!h->pool.p) {
+        CU(h->pool.ensure((size_t)kPoolWords));
+        CU(h->pool_cursor.ensure(2));
+        CU(cudaMemsetAsync(h->pool_cursor.p, 0, 2 * sizeof(int32_t), h->stream));
+        CU(cudaMemsetAsync(h->pool.p, 0, (size_t)kPoolWords * sizeof(int32_t), h->stream));
+    }
+    if (!h->state_in_smem) CU(h->gstate.ensure(n_warps * (size_t)h->Ly.total_words));
+    if (mode == GPSAT_MODE_SOLVE) {
+        const size_t want = n_warps * (size_t)h->arena_words;
+        if (h->arena_total_words < want) {
+            if (h->arena) cudaFree(h->arena);
+            h->arena = nullptr;
+            h->arena_total_words = 0;
+            if (g_arena_cache.p && g_arena_cache.device == h->device && g_arena_cache.words >= want) {
+                h->arena = g_arena_cache.p;
+                h->arena_total_words = g_arena_cache.words;
+                g_arena_cache = ArenaCache();
+            } else {
+                if (g_arena_cache.p && g_arena_cache.device == h->device) {
+                    cudaFree(g_arena_cache.p);
+                    g_arena_cache = ArenaCache();
+                }
+                CU(cudaMalloc(&h->arena, want * sizeof(int32_t)));
+                h->arena_total_words = want;
+            }
+        }
+    }
+    return GPSAT_OK;
+}
+
+gpsat_run_buffers make_buffers(gpsat *h, int mode, double budget_ms)
+{
+    gpsat_run_buffers B;
+    std::memset(&B, 0, sizeof(B));
+    B.cube_offsets = h->cube_offsets.p;
+    B.cube_lits = h->cube_lits.p;
+    B.n_cubes = h->n_cubes;
+    B.next_job = h->ctrl.p + 0;
+    B.stop_flag = h->ctrl.p + 1;
+    B.sat_job = h->ctrl.p + 2;
+    B.model = h->model.p;
+    B.records = h->records.p;
+    B.arena = mode == GPSAT_MODE_SOLVE ? h->arena : nullptr;
+    B.gstate = h->gstate.p;
+    B.pool = h->pool.p;
+    B.pool_cursor = h->pool_cursor.p;
+    B.pool_cap_words = (int32_t)kPoolWords;
+    B.state_in_smem = h->state_in_smem;
+    B.t0 = h->t0.p;
+    B.budget_ns = budget_ms > 0 ? (unsigned long long)(budget_ms * 1e6) : 0ull;
+    return B;
+}
+
+int reset_ctrl(gpsat *h)
+{
+    const int32_t init[4] = {0, 0, -1, 0};
+    CU(cudaMemcpyAsync(h->ctrl.p, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+    std::vector<gpsat_job_record> blank((size_t)std::max(h->n_cubes, 1));
+    std::memset(blank.data(), 0, blank.size() * sizeof(gpsat_job_record));
+    for (auto &r : blank) r.status = GPSAT_JOB_NOT_RUN;
+    CU(cudaMemcpyAsync(h->records.p, blank.data(), blank.size() * sizeof(gpsat_job_record), cudaMemcpyHostToDevice,
+                       h->stream));
+    CU(cudaStreamSynchronize(h->stream));   // `blank` is pageable host memory
+    return GPSAT_OK;
+}
+
+int launch_timed(gpsat *h, const gpsat_solve_params &P, const gpsat_run_buffers &B)
+{
+    CU(gpsat_kernels::launch_stamp(h->t0.p, h->stream));
+    CU(cudaEventRecord(h->ev0, h->stream));
+    CU(gpsat_kernels::launch_cdcl(make_view(h), P, h->Ly, B, h->blocks, h->warps_per_block, h->smem_bytes, h->stream));
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->kernel_ms += ms;
+    h->kernel_launches += 1;
+    return GPSAT_OK;
+}
+
+int fetch_records(gpsat *h)
+{
+    h->records_h.resize((size_t)std::max(h->n_cubes, 1));
+    CU(cudaMemcpyAsync(h->records_h.data(), h->records.p, h->records_h.size() * sizeof(gpsat_job_record),
+                       cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return GPSAT_OK;
+}
+
+void fill_stats(gpsat *h, gpsat_stats *s)
+{
+    if (!s) return;
+    std::memset(s, 0, sizeof(*s));
+    s->jobs_total = h->n_cubes;
+    for (int j = 0; j < h->n_cubes; j++) {
+        const gpsat_job_record &r = h->records_h[(size_t)j];
+        if (r.status == GPSAT_JOB_NOT_RUN) continue;
+        if (r.status == GPSAT_SAT) s->jobs_sat++;
+        else if (r.status == GPSAT_UNSAT) s->jobs_unsat++;
+        else s->jobs_undef++;
+        if (r.status != GPSAT_JOB_ABORTED) s->jobs_done++;
+        s->decisions += r.decisions;
+        s->implications += r.implications;
+        s->conflicts += r.conflicts;
+        s->learnt_clauses += r.learnt_clauses;
+        s->learnt_literals += r.learnt_literals;
+        s->restarts += r.restarts;
+        s->watchers_visited += r.watchers_visited;
+        s->clause_words_read += r.clause_words_read;
+    }
+    int32_t cur[2] = {0, 0};
+    if (h->pool_cursor.p) cudaMemcpy(cur, h->pool_cursor.p, sizeof(cur), cudaMemcpyDeviceToHost);
+    s->pool_clauses = cur[1];
+    s->kernel_ms = h->kernel_ms;
+    s->kernel_launches = h->kernel_launches;
+    s->blocks = h->blocks;
+    s->warps_per_block = h->warps_per_block;
+    s->smem_bytes_per_block = (int32_t)h->smem_bytes;
+    s->state_in_smem = h->state_in_smem;
+}
+
+// verdict of the whole run from the per-job records (≙ Results::get_status after parallel_kernel_retrieve_results)
+int32_t run_verdict(gpsat *h, bool *all_done)
+{
+    bool any_sat = false, any_open = false, any_undef = false;
+    for (int j = 0; j < h->n_cubes; j++) {
+        const int st = h->records_h[(size_t)j].status;
+        if (st == GPSAT_SAT) any_sat = true;
+        else if (st == GPSAT_UNSAT) continue;
+        else if (st == GPSAT_JOB_NOT_RUN || st == GPSAT_JOB_ABORTED) any_open = true;
+        else any_undef = true;   // UNDEF (cap) or OOM
+    }
+    if (all_done) *all_done = !any_open;
+    if (any_sat) return GPSAT_SAT;
+    if (any_open || any_undef) return GPSAT_UNDEF;
+    return GPSAT_UNSAT;
+}
+
+}  // namespace
+
+extern "C" {
+
+void gpsat_opts_default(gpsat_opts *o)
+{
+    if (!o) return;
+    std::memset(o, 0, sizeof(*o));
+    o->struct_size = (int32_t)sizeof(gpsat_opts);
+    o->device = -1;
+    o->decision = GPSAT_DECIDE_VSIDS;
+    o->bcp = GPSAT_BCP_WATCHED;
+    o->restart_first = 100;
+    o->restart_factor = 1.3f;
+    o->max_iterations = 0;
+    o->stop_on_sat = 1;
+    o->max_conflicts = 0;
+    o->share_learnts = 0;
+    o->share_max_len = 8;
+    o->warps_per_block = 0;
+    o->blocks = 0;
+    o->arena_words = 0;
+}
+
+int gpsat_create(gpsat_t **out, int32_t n_vars, int64_t n_clauses, const int64_t *offsets, const int32_t *lits,
+                 const gpsat_opts *opts)
+{
+    if (!out) {
+        set_error("null handle pointer");
+        return GPSAT_E_ARG;
+    }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error(std::string("no usable CUDA device (") + cudaGetErrorString(e) +
+                  "); gpupsat_b200 has no CPU fallback");
+        return GPSAT_E_NO_DEVICE;
+    }
+    gpsat *h = new gpsat();
+    if (opts) {
+        if (opts->struct_size != (int32_t)sizeof(gpsat_opts)) {
+            delete h;
+            set_error("gpsat_opts.struct_size mismatch: initialise with gpsat_opts_default");
+            return GPSAT_E_ARG;
+        }
+        h->opts = *opts;
+    } else {
+        gpsat_opts_default(&h->opts);
+    }
+    int rc = gpsat_host::build_device_formula(n_vars, n_clauses, offsets, lits, h->D);
+    if (rc != GPSAT_OK) {
+        delete h;
+        return rc;
+    }
+    auto fail = [&](int code) {
+        gpsat_destroy(h);
+        return code;
+    };
+#define CUH(call)                                                              \
+    do {                                                                       \
+        cudaError_t e_ = (call);                                               \
+        if (e_ != cudaSuccess) {                                               \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(e_));     \
+            return fail(GPSAT_E_CUDA);                                         \
+        }                                                                      \
+    } while (0)
+    if (h->opts.device >= 0) {
+        CUH(cudaSetDevice(h->opts.device));
+        h->device = h->opts.device;
+    } else {
+        CUH(cudaGetDevice(&h->device));
+    }
+    CUH(cudaGetDeviceProperties(&h->prop, h->device));
+    CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUH(cudaEventCreate(&h->ev0));
+    CUH(cudaEventCreate(&h->ev1));
+
+    // compact CSR with int32 offsets (clause evaluation kernel)
+    h->coffsets_h.resize((size_t)n_clauses + 1);
+    const int64_t base = n_clauses ? offsets[0] : 0;
+    for (int64_t c = 0; c <= n_clauses; c++) h->coffsets_h[(size_t)c] = (int32_t)((n_clauses ? offsets[c] : 0) - base);
+
+    CUH(h->cstart.upload(h->D.cstart.data(), h->D.cstart.size(), h->stream));
+    CUH(h->cl2.upload(h->D.cl2.data(), h->D.cl2.size(), h->stream));
+    CUH(h->ostart.upload(h->D.ostart.data(), h->D.ostart.size(), h->stream));
+    CUH(h->occ2.upload(h->D.occ2.data(), h->D.occ2.size(), h->stream));
+    CUH(h->wbits0.upload(h->D.wbits0.data(), h->D.wbits0.size(), h->stream));
+    CUH(h->vsids0.upload(h->D.vsids0.data(), h->D.vsids0.size(), h->stream));
+    CUH(h->val0.upload(h->D.val0.data(), h->D.val0.size(), h->stream));
+    CUH(h->coffsets.upload(h->coffsets_h.data(), h->coffsets_h.size(), h->stream));
+    CUH(h->clits.upload(lits + base, (size_t)h->D.n_lits, h->stream));
+    CUH(cudaStreamSynchronize(h->stream));
+#undef CUH
+
+    // per-warp learnt arena: header (watch-vector heads, histogram, clause list) + room for clauses and watches
+    const int64_t header = 6 * (int64_t)n_vars + 64 + std::max<int64_t>(16384, n_vars + 64);
+    h->arena_words = h->opts.arena_words > 0 ? h->opts.arena_words : std::max<int64_t>((int64_t)1 << 19, 4 * header);
+    if (h->arena_words < header + 1024) h->arena_words = header + 1024;
+    if (h->arena_words >= ((int64_t)1 << 31)) h->arena_words = ((int64_t)1 << 31) - 1;
+
+    // default: the single empty cube (sequential mode)
+    h->n_cubes = 1;
+    h->cube_offsets_h.assign(2, 0);
+    h->cubes_set = false;
+    *out = h;
+    return GPSAT_OK;
+}
+
+void gpsat_destroy(gpsat_t *h)
+{
+    if (!h) return;
+    if (h->arena) {
+        if (g_arena_cache.p) cudaFree(g_arena_cache.p);
+        g_arena_cache.p = h->arena;
+        g_arena_cache.words = h->arena_total_words;
+        g_arena_cache.device = h->device;
+        h->arena = nullptr;
+    }
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int gpsat_set_cubes(gpsat_t *h, int32_t n_cubes, const int64_t *cube_offsets, const int32_t *cube_lits)
+{
+    if (!h || n_cubes < 0 || (n_cubes > 0 && !cube_offsets)) {
+        set_error("bad arguments");
+        return GPSAT_E_ARG;
+    }
+    if (n_cubes == 0) {
+        h->n_cubes = 1;
+        h->cube_offsets_h.assign(2, 0);
+    } else {
+        h->n_cubes = n_cubes;
+        h->cube_offsets_h.assign(cube_offsets, cube_offsets + n_cubes + 1);
+        const int64_t base = cube_offsets[0];
+        for (auto &o : h->cube_offsets_h) o -= base;
+        const int64_t total = h->cube_offsets_h.back();
+        for (int32_t j = 0; j < n_cubes; j++)
+            if (h->cube_offsets_h[(size_t)j + 1] < h->cube_offsets_h[(size_t)j]) {
+                set_error("cube offsets not monotone");
+                return GPSAT_E_ARG;
+            }
+        if (total > 0 && !cube_lits) {
+            set_error("null cube literals");
+            return GPSAT_E_ARG;
+        }
+        for (int64_t i = 0; i < total; i++) {
+            const int32_t x = cube_lits[base + i];
+            if (x < 0 || (x >> 1) >= h->D.n_vars) {
+                set_error("cube literal out of range");
+                return GPSAT_E_ARG;
+            }
+        }
+        CU(h->cube_lits.upload(cube_lits + base, (size_t)total, h->stream));
+    }
+    CU(h->cube_offsets.upload(h->cube_offsets_h.data(), h->cube_offsets_h.size(), h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->cubes_set = true;
+    return GPSAT_OK;
+}
+
+static int ensure_cubes(gpsat_t *h)
+{
+    if (h->cubes_set) return GPSAT_OK;
+    return gpsat_set_cubes(h, 0, nullptr, nullptr);
+}
+
+int gpsat_propagate_all(gpsat_t *h, int32_t *status, int32_t *n_implied, int32_t *implied, int64_t implied_stride,
+                        int64_t *conflict_clause, gpsat_job_record *records)
+{
+    if (!h || implied_stride < 0) {
+        set_error("bad arguments");
+        return GPSAT_E_ARG;
+    }
+    int rc = ensure_cubes(h);
+    if (rc != GPSAT_OK) return rc;
+    rc = plan_geometry(h, GPSAT_MODE_PROPAGATE);
+    if (rc != GPSAT_OK) return rc;
+    rc = ensure_run_buffers(h, GPSAT_MODE_PROPAGATE);
+    if (rc != GPSAT_OK) return rc;
+    const size_t nc = (size_t)h->n_cubes;
+    if (implied) CU(h->implied.ensure(nc * (size_t)implied_stride));
+    CU(h->n_implied.ensure(nc));
+    CU(h->conflict_clause.ensure(nc));
+    rc = reset_ctrl(h);
+    if (rc != GPSAT_OK) return rc;
+    gpsat_solve_params P = make_params(h, GPSAT_MODE_PROPAGATE, implied ? implied_stride : 0);
+    gpsat_run_buffers B = make_buffers(h, GPSAT_MODE_PROPAGATE, 0);
+    B.implied = implied ? h->implied.p : nullptr;
+    B.n_implied = h->n_implied.p;
+    B.conflict_clause = h->conflict_clause.p;
+    h->kernel_ms = 0;
+    h->kernel_launches = 0;
+    h->run_mode = GPSAT_MODE_PROPAGATE;
+    rc = launch_timed(h, P, B);
+    if (rc != GPSAT_OK) return rc;
+    rc = fetch_records(h);
+    if (rc != GPSAT_OK) return rc;
+    if (status)
+        for (size_t j = 0; j < nc; j++) status[j] = h->records_h[j].status;
+    if (records) std::memcpy(records, h->records_h.data(), nc * sizeof(gpsat_job_record));
+    if (n_implied) CU(cudaMemcpy(n_implied, h->n_implied.p, nc * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (conflict_clause)
+        CU(cudaMemcpy(conflict_clause, h->conflict_clause.p, nc * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (implied && implied_stride > 0)
+        CU(cudaMemcpy(implied, h->implied.p, nc * (size_t)implied_stride * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return GPSAT_OK;
+}
+
+int gpsat_propagate(gpsat_t *h, int32_t cube, int32_t *status, int32_t *implied, int32_t *n_implied,
+                    int64_t *conflict_clause)
+{
+    if (!h) {
+        set_error("null handle");
+        return GPSAT_E_ARG;
+    }
+    int rc = ensure_cubes(h);
+    if (rc != GPSAT_OK) return rc;
+    if (cube < 0 || cube >= h->n_cubes) {
+        set_error("cube index out of range");
+        return GPSAT_E_ARG;
+    }
+    // run just this cube: temporarily narrow the job list to [cube, cube+1)
+    const int32_t saved_n = h->n_cubes;
+    int64_t *saved_off = h->cube_offsets.p;
+    h->cube_offsets.p = saved_off + cube;
+    h->n_cubes = 1;
+    std::vector<int32_t> imp((size_t)std::max(h->D.n_vars, 1));
+    int32_t st = GPSAT_UNDEF, n = 0;
+    int64_t cc = -1;
+    rc = gpsat_propagate_all(h, &st, &n, implied ? imp.data() : nullptr, h->D.n_vars, &cc, nullptr);
+    h->cube_offsets.p = saved_off;
+    h->n_cubes = saved_n;
+    if (rc != GPSAT_OK) return rc;
+    if (status) *status = st;
+    if (n_implied) *n_implied = n;
+    if (conflict_clause) *conflict_clause = cc;
+    if (implied) std::memcpy(implied, imp.data(), (size_t)std::min(n, h->D.n_vars) * sizeof(int32_t));
+    return GPSAT_OK;
+}
+
+int gpsat_eval_clauses(gpsat_t *h, int32_t n_assignments, const uint8_t *assignment, int32_t *status_per_clause,
+                       int32_t *unit_lit)
+{
+    if (!h || n_assignments < 0 || (n_assignments > 0 && (!assignment || !status_per_clause))) {
+        set_error("bad arguments");
+        return GPSAT_E_ARG;
+    }
+    const size_t na = (size_t)n_assignments, nv = (size_t)h->D.n_vars, nc = (size_t)h->D.n_clauses;
+    if (na == 0 || nc == 0) return GPSAT_OK;
+    DevBuf<uint8_t> d_as;
+    DevBuf<int32_t> d_st, d_un;
+    CU(d_as.upload(assignment, na * nv, h->stream));
+    CU(d_st.ensure(na * nc));
+    if (unit_lit) CU(d_un.ensure(na * nc));
+    CU(gpsat_kernels::launch_eval_clauses(h->D.n_vars, (int32_t)h->D.n_clauses, h->coffsets.p, h->clits.p, n_assignments,
+                                          d_as.p, d_st.p, unit_lit ? d_un.p : nullptr, h->stream));
+    CU(cudaMemcpyAsync(status_per_clause, d_st.p, na * nc * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (unit_lit) CU(cudaMemcpyAsync(unit_lit, d_un.p, na * nc * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return GPSAT_OK;
+}
+
+int gpsat_solve_begin(gpsat_t *h)
+{
+    if (!h) {
+        set_error("null handle");
+        return GPSAT_E_ARG;
+    }
+    int rc = ensure_cubes(h);
+    if (rc != GPSAT_OK) return rc;
+    rc = plan_geometry(h, GPSAT_MODE_SOLVE);
+    if (rc != GPSAT_OK) return rc;
+    rc = ensure_run_buffers(h, GPSAT_MODE_SOLVE);
+    if (rc != GPSAT_OK) return rc;
+    rc = reset_ctrl(h);
+    if (rc != GPSAT_OK) return rc;
+    h->kernel_ms = 0;
+    h->kernel_launches = 0;
+    h->run_mode = GPSAT_MODE_SOLVE;
+    h->solving = true;
+    return GPSAT_OK;
+}
+
+int gpsat_solve_step(gpsat_t *h, double budget_ms, int32_t *done, int32_t *verdict)
+{
+    if (!h || !h->solving) {
+        set_error("gpsat_solve_step without gpsat_solve_begin");
+        return GPSAT_E_STATE;
+    }
+    gpsat_solve_params P = make_params(h, GPSAT_MODE_SOLVE, 0);
+    gpsat_run_buffers B = make_buffers(h, GPSAT_MODE_SOLVE, budget_ms);
+    int rc = launch_timed(h, P, B);
+    if (rc != GPSAT_OK) return rc;
+    rc = fetch_records(h);
+    if (rc != GPSAT_OK) return rc;
+    bool all_done = false;
+    const int32_t v = run_verdict(h, &all_done);
+    int32_t ctrl[3] = {0, 0, -1};
+    CU(cudaMemcpy(ctrl, h->ctrl.p, sizeof(ctrl), cudaMemcpyDeviceToHost));
+    const bool stopped = ctrl[1] != 0;
+    if (done) *done = (all_done || stopped || (v == GPSAT_SAT && h->opts.stop_on_sat)) ? 1 : 0;
+    if (verdict) *verdict = v;
+    return GPSAT_OK;
+}
+
+int gpsat_solve_end(gpsat_t *h, int32_t *verdict, uint8_t *model, gpsat_stats *stats)
+{
+    if (!h || !h->solving) {
+        set_error("gpsat_solve_end without gpsat_solve_begin");
+        return GPSAT_E_STATE;
+    }
+    h->solving = false;
+    if (h->records_h.size() < (size_t)h->n_cubes) {
+        int rc = fetch_records(h);
+        if (rc != GPSAT_OK) return rc;
+    }
+    const int32_t v = run_verdict(h, nullptr);
+    if (verdict) *verdict = v;
+    if (v == GPSAT_SAT && model)
+        CU(cudaMemcpy(model, h->model.p, (size_t)h->D.n_vars, cudaMemcpyDeviceToHost));
+    fill_stats(h, stats);
+    return GPSAT_OK;
+}
+
+int gpsat_solve(gpsat_t *h, int32_t *verdict, uint8_t *model, gpsat_stats *stats)
+{
+    int rc = gpsat_solve_begin(h);
+    if (rc != GPSAT_OK) return rc;
+    int32_t done = 0, v = GPSAT_UNDEF;
+    rc = gpsat_solve_step(h, 0.0, &done, &v);
+    if (rc != GPSAT_OK) {
+        h->solving = false;
+        return rc;
+    }
+    return gpsat_solve_end(h, verdict, model, stats);
+}
+
+int gpsat_request_stop(gpsat_t *h)
+{
+    if (!h || !h->ctrl.p) {
+        set_error("no run in progress");
+        return GPSAT_E_STATE;
+    }
+    const int32_t two = 2;
+    CU(cudaMemcpy(h->ctrl.p + 1, &two, sizeof(two), cudaMemcpyHostToDevice));
+    return GPSAT_OK;
+}
+
+int gpsat_job_records(gpsat_t *h, gpsat_job_record *records, int32_t cap)
+{
+    if (!h || !records) {
+        set_error("bad arguments");
+        return GPSAT_E_ARG;
+    }
+    if (cap < h->n_cubes || h->records_h.size() < (size_t)h->n_cubes) {
+        set_error("record buffer too small or no run yet");
+        return GPSAT_E_CAPACITY;
+    }
+    std::memcpy(records, h->records_h.data(), (size_t)h->n_cubes * sizeof(gpsat_job_record));
+    return GPSAT_OK;
+}
+
+int gpsat_pool_export(gpsat_t *h, int32_t *buf, int64_t cap_words, int64_t *n_words)
+{
+    if (!h || !n_words || (cap_words > 0 && !buf)) {
+        set_error("bad arguments");
+        return GPSAT_E_ARG;
+    }
+    *n_words = 0;
+    if (!h->pool.p) return GPSAT_OK;
+    int32_t cur[2] = {0, 0};
+    CU(cudaMemcpy(cur, h->pool_cursor.p, sizeof(cur), cudaMemcpyDeviceToHost));
+    int64_t used = std::min<int64_t>(cur[0], kPoolWords);
+    int64_t fresh = used - h->pool_export_mark;
+    if (fresh <= 0) return GPSAT_OK;
+    if (fresh > cap_words) {
+        // hand out whole records only: walk headers on the host
+        std::vector<int32_t> tmp((size_t)fresh);
+        CU(cudaMemcpy(tmp.data(), h->pool.p + h->pool_export_mark, (size_t)fresh * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        int64_t at = 0;
+        while (at < fresh && tmp[(size_t)at] > 0 && at + 1 + tmp[(size_t)at] <= cap_words) at += 1 + tmp[(size_t)at];
+        std::memcpy(buf, tmp.data(), (size_t)at * sizeof(int32_t));
+        *n_words = at;
+        h->pool_export_mark += at;
+        return GPSAT_OK;
+    }
+    CU(cudaMemcpy(buf, h->pool.p + h->pool_export_mark, (size_t)fresh * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    // a record whose header is still 0 was reserved but dropped (pool overflow); stop there
+    int64_t at = 0;
+    while (at < fresh && buf[at] > 0 && at + 1 + buf[at] <= fresh) at += 1 + buf[at];
+    *n_words = at;
+    h->pool_export_mark += (at == fresh) ? fresh : at;
+    return GPSAT_OK;
+}
+
+int gpsat_pool_import(gpsat_t *h, const int32_t *buf, int64_t n_words)
+{
+    if (!h || n_words < 0 || (n_words > 0 && !buf)) {
+        set_error("bad arguments");
+        return GPSAT_E_ARG;
+    }
+    if (n_words == 0) return GPSAT_OK;
+    if (!h->pool.p) {
+        CU(h->pool.ensure((size_t)kPoolWords));
+        CU(h->pool_cursor.ensure(2));
+        CU(cudaMemset(h->pool_cursor.p, 0, 2 * sizeof(int32_t)));
+        CU(cudaMemset(h->pool.p, 0, (size_t)kPoolWords * sizeof(int32_t)));
+    }
+    int64_t at = 0, n_rec = 0;
+    while (at < n_words) {
+        const int32_t len = buf[at];
+        if (len <= 0 || at + 1 + len > n_words) {
+            set_error("malformed pool records");
+            return GPSAT_E_ARG;
+        }
+        for (int32_t i = 0; i < len; i++)
+            if (buf[at + 1 + i] < 0 || (buf[at + 1 + i] >> 1) >= h->D.n_vars) {
+                set_error("pool literal out of range");
+                return GPSAT_E_ARG;
+            }
+        at += 1 + len;
+        n_rec++;
+    }
+    int32_t cur[2] = {0, 0};
+    CU(cudaMemcpy(cur, h->pool_cursor.p, sizeof(cur), cudaMemcpyDeviceToHost));
+    const int64_t used = std::min<int64_t>(cur[0], kPoolWords);
+    if (used + n_words > kPoolWords) return GPSAT_OK;   // pool full: foreign clauses are optional knowledge
+    CU(cudaMemcpy(h->pool.p + used, buf, (size_t)n_words * sizeof(int32_t), cudaMemcpyHostToDevice));
+    cur[0] = (int32_t)(used + n_words);
+    cur[1] += (int32_t)n_rec;
+    CU(cudaMemcpy(h->pool_cursor.p, cur, sizeof(cur), cudaMemcpyHostToDevice));
+    // imported records are not re-exported
+    if (h->pool_export_mark == used) h->pool_export_mark = used + n_words;
+    return GPSAT_OK;
+}
+
+int gpsat_device_ptrs(gpsat_t *h, void **pool_words, void **pool_cursor, void **stop_flag, void **stream)
+{
+    if (!h) {
+        set_error("null handle");
+        return GPSAT_E_ARG;
+    }
+    if (pool_words) *pool_words = h->pool.p;
+    if (pool_cursor) *pool_cursor = h->pool_cursor.p;
+    if (stop_flag) *stop_flag = h->ctrl.p ? (void *)(h->ctrl.p + 1) : nullptr;
+    if (stream) *stream = (void *)h->stream;
+    return GPSAT_OK;
+}
+
+}  // extern "C"

@@ -80,7 +80,8 @@ struct gpsat_run_buffers {
     int32_t *pool_cursor;          // [0] words used, [1] clauses
     int32_t pool_cap_words;
     int32_t state_in_smem;
-    unsigned long long deadline_ns;   // globaltimer deadline for pulling new jobs, 0 = none
+    const unsigned long long *t0;     // globaltimer stamp taken right before the launch
+    unsigned long long budget_ns;     // warps stop pulling new cubes once now > *t0 + budget_ns (0 = no limit)
 };
 
 // per-warp state block: word offsets of each array (every array starts on a 16-byte boundary)

@@ -1,0 +1,142 @@
+// sm_100a kernels of gpupsat_b200.
+//
+//   gpsat_cdcl_kernel   persistent, one warp per cube (≙ parallel_kernel, SATSolver/Parallelizer.cu:180-228, and
+//                       run_sequential :230-278): each warp pulls the next cube from an atomic cursor
+//                       (≙ JobsQueue::next_job, SATSolver/JobsQueue.cu:10-32), runs the whole CDCL search for it
+//                       (cdcl_warp.inl), writes its record, and polls the early-termination flag inside the loop
+//                       rather than at kernel boundaries (SATSolver/main.cu:259-269).
+//   gpsat_eval_kernel   clause evaluation (≙ VariablesStateHandler::clause_status, SATSolver/VariablesStateHandler.cu:180-206)
+//
+// Tensor cores are not used anywhere: this path is integer gather / scan work (BASELINE.json north_star).
+#include "kernels.h"
+#include "cdcl_warp.inl"
+
+namespace {
+
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void gpsat_stamp_kernel(unsigned long long *t0) { *t0 = globaltimer_ns(); }
+
+__global__ void __launch_bounds__(1024, 1)
+gpsat_cdcl_kernel(const gpsat_formula_view F, const gpsat_solve_params P, const gpsat_state_layout Ly,
+                  const gpsat_run_buffers B)
+{
+    extern __shared__ __align__(16) int gpsat_smem[];
+    const int lane = (int)(threadIdx.x & 31u);
+    const int warp_in_block = (int)(threadIdx.x >> 5);
+    const int warps_per_block = (int)(blockDim.x >> 5);
+    const long long gwarp = (long long)blockIdx.x * warps_per_block + warp_in_block;
+
+    int *state = B.state_in_smem ? gpsat_smem + (size_t)warp_in_block * Ly.total_words
+                                 : B.gstate + (size_t)gwarp * Ly.total_words;
+    int *arena = B.arena ? B.arena + (size_t)gwarp * (size_t)P.arena_words : nullptr;
+
+    WarpSolver S;
+    gpsat_bind(S, F, P, Ly, state, arena, B);
+
+    while (true) {
+        int job = 0;
+        int go = 1;
+        if (lane == 0) {
+            if (*(volatile int *)B.stop_flag) go = 0;
+            if (go && B.budget_ns && globaltimer_ns() > *B.t0 + B.budget_ns) go = 0;
+            if (go) job = atomicAdd(B.next_job, 1);
+        }
+        go = __shfl_sync(0xffffffffu, go, 0);
+        job = __shfl_sync(0xffffffffu, job, 0);
+        if (!go || job >= B.n_cubes) break;
+        gpsat_run_and_record(S, job, P, B);
+    }
+}
+
+// One thread per (assignment, clause).  Clause literals are read from the compact CSR (4 B per literal, coalesced
+// across the warp for fixed-width clauses); variable values are byte gathers served by L1/L2.
+__global__ void __launch_bounds__(256)
+gpsat_eval_kernel(int32_t n_vars, int32_t n_clauses, const int32_t *__restrict__ coffsets,
+                  const int32_t *__restrict__ clits, const uint8_t *__restrict__ assignment,
+                  int32_t *__restrict__ status, int32_t *__restrict__ unit)
+{
+    const int a = (int)blockIdx.y;
+    const uint8_t *__restrict__ as = assignment + (size_t)a * (size_t)n_vars;
+    for (int c = (int)(blockIdx.x * blockDim.x + threadIdx.x); c < n_clauses; c += (int)(gridDim.x * blockDim.x)) {
+        const int b = __ldg(coffsets + c), e = __ldg(coffsets + c + 1);
+        int n_false = 0, last_undef = -1, st = -1;
+        for (int i = b; i < e; ++i) {
+            const int x = __ldg(clits + i);
+            const int sv = as[x >> 1];   // reference sat_status: 0 true, 1 false, 2 unassigned
+            if (sv == 2) {
+                last_undef = x;
+            } else if ((sv == 0) == ((x & 1) == 1)) {
+                st = GPSAT_SAT;
+                break;
+            } else {
+                n_false++;
+            }
+        }
+        int u = -1;
+        if (st != GPSAT_SAT) {
+            st = (n_false == e - b) ? GPSAT_UNSAT : GPSAT_UNDEF;
+            if (n_false == e - b - 1) u = last_undef;
+        }
+        const size_t o = (size_t)a * (size_t)n_clauses + (size_t)c;
+        status[o] = st;
+        if (unit) unit[o] = u;
+    }
+}
+
+}  // namespace
+
+namespace gpsat_kernels {
+
+cudaError_t launch_cdcl(const gpsat_formula_view &F, const gpsat_solve_params &P, const gpsat_state_layout &Ly,
+                        const gpsat_run_buffers &B, int blocks, int warps_per_block, size_t smem_bytes,
+                        cudaStream_t stream)
+{
+    cudaError_t e = cudaFuncSetAttribute(gpsat_cdcl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    gpsat_cdcl_kernel<<<blocks, warps_per_block * 32, smem_bytes, stream>>>(F, P, Ly, B);
+    return cudaGetLastError();
+}
+
+cudaError_t cdcl_occupancy(int warps_per_block, size_t smem_bytes, int *blocks_per_sm)
+{
+    cudaError_t e = cudaFuncSetAttribute(gpsat_cdcl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, gpsat_cdcl_kernel, warps_per_block * 32, smem_bytes);
+}
+
+cudaError_t cdcl_attributes(int *regs_per_thread, size_t *local_bytes)
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, gpsat_cdcl_kernel);
+    if (e != cudaSuccess) return e;
+    *regs_per_thread = a.numRegs;
+    *local_bytes = a.localSizeBytes;
+    return cudaSuccess;
+}
+
+cudaError_t launch_stamp(unsigned long long *t0, cudaStream_t stream)
+{
+    gpsat_stamp_kernel<<<1, 1, 0, stream>>>(t0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_eval_clauses(int32_t n_vars, int32_t n_clauses, const int32_t *coffsets, const int32_t *clits,
+                                int32_t n_assignments, const uint8_t *assignment, int32_t *status, int32_t *unit,
+                                cudaStream_t stream)
+{
+    if (n_clauses <= 0 || n_assignments <= 0) return cudaSuccess;
+    int bx = (n_clauses + 255) / 256;
+    const int cap = 148 * 16;
+    if (bx > cap) bx = cap;
+    dim3 grid((unsigned)bx, (unsigned)n_assignments);
+    gpsat_eval_kernel<<<grid, 256, 0, stream>>>(n_vars, n_clauses, coffsets, clits, assignment, status, unit);
+    return cudaGetLastError();
+}
+
+}  // namespace gpsat_kernels

@@ -1,0 +1,25 @@
+// Launchers of the sm_100a kernels (kernels.cu), called by the C-ABI layer (gpsat_api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "gpsat_device.h"
+
+namespace gpsat_kernels {
+
+// Persistent warp-per-cube CDCL / BCP kernel.  grid = blocks, block = warps_per_block*32 threads,
+// smem_bytes = warps_per_block * layout.total_words * 4 when the per-job state lives in shared memory, else 0.
+cudaError_t launch_cdcl(const gpsat_formula_view &F, const gpsat_solve_params &P, const gpsat_state_layout &Ly,
+                        const gpsat_run_buffers &B, int blocks, int warps_per_block, size_t smem_bytes,
+                        cudaStream_t stream);
+// resident blocks per SM for that configuration (cudaOccupancyMaxActiveBlocksPerMultiprocessor)
+cudaError_t cdcl_occupancy(int warps_per_block, size_t smem_bytes, int *blocks_per_sm);
+cudaError_t cdcl_attributes(int *regs_per_thread, size_t *local_bytes);
+
+// stamps *t0 with the GPU's globaltimer (deadline base for budgeted steps)
+cudaError_t launch_stamp(unsigned long long *t0, cudaStream_t stream);
+
+// clause evaluation: one thread per (assignment, clause)
+cudaError_t launch_eval_clauses(int32_t n_vars, int32_t n_clauses, const int32_t *coffsets, const int32_t *clits,
+                                int32_t n_assignments, const uint8_t *assignment, int32_t *status, int32_t *unit,
+                                cudaStream_t stream);
+
+}  // namespace gpsat_kernels

@@ -189,6 +189,8 @@ int gpsat_solve_begin(gpsat_t *h);
  * *done = 1 when nothing is left to do on this GPU. *verdict as gpsat_solve (UNDEF while cubes remain). */
 int gpsat_solve_step(gpsat_t *h, double budget_ms, int32_t *done, int32_t *verdict);
 int gpsat_solve_end(gpsat_t *h, int32_t *verdict, uint8_t *model, gpsat_stats *stats);
+/* raises the early-termination flag (another GPU found a model): running cubes abort, no new cube starts */
+int gpsat_request_stop(gpsat_t *h);
 /* learnt-clause pool exchange: records are [len, lit0, ..., lit(len-1)] packed back to back.
  * export returns clauses appended to this GPU's pool since the previous export; import appends foreign clauses. */
 int gpsat_pool_export(gpsat_t *h, int32_t *buf, int64_t cap_words, int64_t *n_words);

@@ -1,0 +1,109 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle on the same inputs — bit-exact."""
+import numpy as np
+import pytest
+
+import gpupsat_b200 as g
+from gpupsat_b200.instances import check_model, pigeonhole, random_ksat
+from oracle.binding import Oracle
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = [f for f in g.RECORD_DTYPE.names if f != "reserved"]
+
+
+def _cmp_records(a, b, what):
+    for f in FIELDS:
+        bad = np.nonzero(a[f] != b[f])[0]
+        assert len(bad) == 0, f"{what}: field {f} differs at jobs {bad[:8]}: gpu {a[f][bad[:8]]} oracle {b[f][bad[:8]]}"
+
+
+def _prep(offs, lits):
+    cnf = g.Cnf.from_arrays(offs, lits)
+    pre = cnf.preprocess()
+    assert pre.status == g.UNDEF
+    return cnf, pre
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_propagate_all_cubes_c2(seed):
+    """config 2: n=250 m=1065, 4096 cubes: status, implied literal LISTS and conflict clause, all cubes."""
+    offs, lits = random_ksat(250, 1065, seed)
+    cnf, pre = _prep(offs, lits)
+    cubes = pre.choose_cubes(8, 32)
+    assert cubes.shape == (4096, 12)
+    with g.Solver(cnf.n_vars, pre.offsets, pre.lits) as s:
+        s.set_cubes(cubes)
+        got = s.propagate_all()
+    o = Oracle(cnf.n_vars, pre.offsets, pre.lits)
+    co = np.arange(0, cubes.size + 1, 12, dtype=np.int64)
+    want = o.run(co, cubes.reshape(-1), mode=1)
+    assert np.array_equal(got["status"], want["records"]["status"])
+    assert np.array_equal(got["n_implied"], want["n_implied"])
+    assert np.array_equal(got["conflict_clause"], want["conflict_clause"])
+    assert np.array_equal(got["implied"], want["implied"])
+    _cmp_records(got["records"], want["records"], "propagate")
+
+
+@pytest.mark.parametrize("n,m,seed,decision", [(20, 91, 0, 1), (20, 91, 1, 0), (50, 218, 0, 1), (50, 218, 1, 1),
+                                               (50, 218, 2, 0), (100, 426, 0, 1), (150, 639, 0, 1)])
+def test_sequential_solve_bit_exact(n, m, seed, decision):
+    """config 1 style (-b 1 -t 1): one empty cube; every counter and the learnt-clause checksum equal the oracle's."""
+    offs, lits = random_ksat(n, m, seed)
+    cnf, pre = _prep(offs, lits)
+    with g.Solver(cnf.n_vars, pre.offsets, pre.lits, decision=decision) as s:
+        s.set_cubes(None)
+        verdict, model, stats = s.solve()
+        rec = s.job_records()
+    o = Oracle(cnf.n_vars, pre.offsets, pre.lits)
+    want = o.run(np.array([0, 0]), np.zeros(0), decision=decision)
+    _cmp_records(rec, want["records"], "solve")
+    assert verdict == want["records"]["status"][0]
+    if verdict == g.SAT:
+        assert np.array_equal(model, want["model"])
+        assert check_model(pre.offsets, pre.lits, model)
+
+
+def test_cube_solve_bit_exact_and_verdict():
+    """cube-and-conquer on a uf100 instance with 2^7 cubes, no early stop: per-cube records equal the oracle's."""
+    offs, lits = random_ksat(100, 426, 3)
+    cnf, pre = _prep(offs, lits)
+    cubes = pre.choose_cubes(1, 8)          # 80 jobs wanted -> k = 7, 128 cubes
+    with g.Solver(cnf.n_vars, pre.offsets, pre.lits, stop_on_sat=0) as s:
+        s.set_cubes(cubes)
+        verdict, model, stats = s.solve()
+        rec = s.job_records()
+    o = Oracle(cnf.n_vars, pre.offsets, pre.lits)
+    k = cubes.shape[1]
+    want = o.run(np.arange(0, cubes.size + 1, k, dtype=np.int64), cubes.reshape(-1), stop_on_sat=False)
+    _cmp_records(rec, want["records"], "cube solve")
+    any_sat = (want["records"]["status"] == 0).any()
+    assert verdict == (g.SAT if any_sat else g.UNSAT)
+    if verdict == g.SAT:
+        assert check_model(pre.offsets, pre.lits, model)
+    assert stats["jobs_done"] == len(cubes)
+
+
+def test_pigeonhole_unsat():
+    offs, lits = pigeonhole(7, 6)
+    cnf, pre = _prep(offs, lits)
+    with g.Solver(cnf.n_vars, pre.offsets, pre.lits) as s:
+        s.set_cubes(None)
+        verdict, _, _ = s.solve()
+        rec = s.job_records()
+    o = Oracle(cnf.n_vars, pre.offsets, pre.lits)
+    want = o.run(np.array([0, 0]), np.zeros(0))
+    assert verdict == g.UNSAT
+    _cmp_records(rec, want["records"], "php(7,6)")
+
+
+def test_eval_clauses():
+    offs, lits = random_ksat(250, 1065, 5)
+    rng = np.random.default_rng(0)
+    assignment = rng.integers(0, 3, size=(7, 250)).astype(np.uint8)
+    assignment[0, :] = 2
+    with g.Solver(250, offs, lits) as s:
+        st, unit = s.eval_clauses(assignment)
+    o = Oracle(250, offs, lits)
+    st2, unit2 = o.eval_clauses(assignment)
+    assert np.array_equal(st, st2)
+    assert np.array_equal(unit, unit2)
