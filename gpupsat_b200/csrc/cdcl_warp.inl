@@ -873,7 +873,7 @@ struct WarpSolver {
                 c_restarts++;
                 cancel_until(k < dlevel ? k : dlevel);
             }
-            if (n_learnts >= max_learnts || (watch_bot - arena_top) < (arena_words - clause_base) / 4) {
+            if (use_learnts && (n_learnts >= max_learnts || (watch_bot - arena_top) < (arena_words - clause_base) / 4)) {
                 reduce_db();
                 if (oom) return GPSAT_JOB_OOM;
             }

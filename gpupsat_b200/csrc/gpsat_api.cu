@@ -534,7 +534,10 @@ int gpsat_propagate_all(gpsat_t *h, int32_t *status, int32_t *n_implied, int32_t
     rc = ensure_run_buffers(h, GPSAT_MODE_PROPAGATE);
     if (rc != GPSAT_OK) return rc;
     const size_t nc = (size_t)h->n_cubes;
-    if (implied) CU(h->implied.ensure(nc * (size_t)implied_stride));
+    if (implied) {
+        CU(h->implied.ensure(nc * (size_t)implied_stride));
+        CU(cudaMemsetAsync(h->implied.p, 0xFF, nc * (size_t)implied_stride * sizeof(int32_t), h->stream));   // -1 padding
+    }
     CU(h->n_implied.ensure(nc));
     CU(h->conflict_clause.ensure(nc));
     rc = reset_ctrl(h);

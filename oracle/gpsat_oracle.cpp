@@ -430,7 +430,8 @@ struct Oracle {
                 R.restarts++;
                 cancel_until(std::min(k, dlevel));
             }
-            if ((int)learnt_order.size() >= max_learnts || (watch_bot - arena_top) < (P.arena_words - clause_base) / 4) {
+            if (P.mode == MODE_SOLVE &&
+                ((int)learnt_order.size() >= max_learnts || (watch_bot - arena_top) < (P.arena_words - clause_base) / 4)) {
                 reduce_db();
                 if (oom) return JOB_OOM;
             }
