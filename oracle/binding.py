@@ -21,6 +21,25 @@ RECORD_DTYPE = np.dtype([
     ("watchers_visited", np.int64), ("clause_words_read", np.int64), ("learnt_hash", np.int64)])
 
 
+class Quiet:
+    """Silences the C-level stdout of the reference host build (its library code printf()s)."""
+
+    def __enter__(self):
+        import sys
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+        return self
+
+    def __exit__(self, *a):
+        import sys
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        os.close(self.null)
+
+
 def build(force: bool = False) -> None:
     """Compile the oracle (always possible) and the reference host build (only where /root/reference exists)."""
     so = os.path.join(REF_DIR, "libgpsat_oracle.so")

@@ -47,21 +47,7 @@ def reference_available():
     return os.path.exists(os.path.join(binding.REF_DIR, "libgpsat_ref.so")) or os.path.isdir("/root/reference/src")
 
 
-class Quiet:
-    """Silences the C-level stdout of the reference host build (it printf()s from library code)."""
-
-    def __enter__(self):
-        sys.stdout.flush()
-        self.saved = os.dup(1)
-        self.null = os.open(os.devnull, os.O_WRONLY)
-        os.dup2(self.null, 1)
-        return self
-
-    def __exit__(self, *a):
-        sys.stdout.flush()
-        os.dup2(self.saved, 1)
-        os.close(self.saved)
-        os.close(self.null)
+from oracle.binding import Quiet  # noqa: E402
 
 
 @pytest.fixture
