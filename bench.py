@@ -273,8 +273,8 @@ def run_ours(args):
             e2e_imp += st2["implications"]
         L, m, n = len(lits), len(offs) - 1, cnf.n_vars
         h2d = 4 * ((m + 1) + 2 * (L + m) + (2 * n + 1) + 2 * L + (L + 31) // 32 + 2 * n + (m + 1) + L) + n \
-            + 8 * (len(mine) + 1) + 4 * mine.size + 16 + 88 * len(mine)
-        d2h = 88 * len(mine) + n + 12 + 8
+            + 8 * (len(mine) + 1) + 4 * mine.size + 16 + 80 * len(mine)
+        d2h = 80 * len(mine) + n + 12 + 8
 
     steps = args.steps
     tot_ms = sum(kernel_ms)

@@ -884,7 +884,11 @@ struct WarpSolver {
                 if (v == 1) {
                     new_level();
                 } else if (v == 0) {
-                    return GPSAT_UNSAT;   // the cube contradicts what propagation already fixed
+                    // the cube contradicts what propagation already fixed: the clause that implied ~x is falsified
+                    // once the whole cube is assigned (the reference assigns it up front: SATSolver.cu:231-246)
+                    const int why = reason[x >> 1];
+                    if (why != GPSAT_REASON_NONE) conflict_out = why;
+                    return GPSAT_UNSAT;
                 } else {
                     next = x;
                     break;

@@ -440,7 +440,10 @@ struct Oracle {
                 const int x = cube[dlevel];
                 const int v = lit_value(x);
                 if (v == 1) new_level();
-                else if (v == 0) return UNSAT;
+                else if (v == 0) {   /* cube literal already false: its reason clause is falsified under the full cube */
+                    if (reason[x >> 1] != -1) conflict_out = reason[x >> 1];
+                    return UNSAT;
+                }
                 else { next = x; break; }
             }
             if (next < 0) {
