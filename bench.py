@@ -216,7 +216,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    solver = g.Solver(cnf.n_vars, offs, lits, device=local_rank)
+    extra = {}
+    if os.environ.get("GPSAT_WARPS_PER_BLOCK"):
+        extra["warps_per_block"] = int(os.environ["GPSAT_WARPS_PER_BLOCK"])
+    if os.environ.get("GPSAT_DYNAMIC_SPLIT"):
+        extra["dynamic_split"] = int(os.environ["GPSAT_DYNAMIC_SPLIT"])
+    if os.environ.get("GPSAT_SHARE_LEARNTS"):
+        extra["share_learnts"] = int(os.environ["GPSAT_SHARE_LEARNTS"])
+    solver = g.Solver(cnf.n_vars, offs, lits, device=local_rank, **extra)
     solver.set_cubes(mine)
 
     def one_solve():
@@ -264,7 +271,7 @@ def run_ours(args):
         for i in range(max(args.steps, 1)):
             barrier()
             t0 = time.perf_counter()
-            s2 = g.Solver(cnf.n_vars, offs, lits, device=local_rank)
+            s2 = g.Solver(cnf.n_vars, offs, lits, device=local_rank, **extra)
             s2.set_cubes(mine)
             v2, m2, st2 = s2.solve()
             s2.close()

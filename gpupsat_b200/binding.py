@@ -26,7 +26,7 @@ class GpsatOpts(C.Structure):
                 ("restart_first", C.c_int32), ("restart_factor", C.c_float), ("max_iterations", C.c_int32),
                 ("stop_on_sat", C.c_int32), ("max_conflicts", C.c_int64), ("share_learnts", C.c_int32),
                 ("share_max_len", C.c_int32), ("warps_per_block", C.c_int32), ("blocks", C.c_int32),
-                ("arena_words", C.c_int64), ("reserved", C.c_int32 * 8)]
+                ("arena_words", C.c_int64), ("dynamic_split", C.c_int32), ("reserved", C.c_int32 * 7)]
 
 
 class GpsatStats(C.Structure):

@@ -44,6 +44,7 @@ struct WarpSolver {
     int *vs;
     int *lbuf;
     int lbuf_words;
+    int *cube_buf;        // this job's cube when it may grow by splitting (GPSAT_DQ_MAXK literals)
     // ---- this warp's learnt arena (global): [lw_ptr | lw_size | lw_cap | hist | refs | clauses ->   <- watch vectors]
     int *arena;
     int arena_words;
@@ -62,6 +63,11 @@ struct WarpSolver {
     int decision_mode, restart_first, max_iterations, share_learnts, share_max_len;
     float restart_factor;
     long long max_conflicts;
+    // dynamic splitting
+    int dynamic_split, split_force, root;
+    int *dq_lits, *dq_meta, *dq_ctrl, *root_pending, *dq_hand;
+    int hand_words;
+    long long c_splits;
     // shared pool
     int *pool;
     int *pool_cursor;
@@ -760,6 +766,7 @@ struct WarpSolver {
         oom = 0;
         c_decisions = c_implications = c_conflicts = c_learnt_clauses = c_learnt_literals = c_restarts = 0;
         c_hash = 0;
+        c_splits = 0;
         c_lwatchers = c_lwords = 0;
         SYNCWARP();
     }
@@ -769,13 +776,19 @@ struct WarpSolver {
     // refute the formula).  Only records whose header is already published are read.
     GPSAT_DEV int pool_import()
     {
-        GPSAT_LANE_DECL
         if (!share_learnts || pool == nullptr) return GPSAT_UNDEF;
-        int used = ((volatile int *)pool_cursor)[0];
+        int used = gpsat_ld_volatile(pool_cursor);
         if (used > pool_cap_words) used = pool_cap_words;
+        return import_records(pool, used);
+    }
+
+    // records = [len, lit0 .. lit(len-1)] back to back in pool[0..used)
+    GPSAT_DEV int import_records(const int *pool, int used)
+    {
+        GPSAT_LANE_DECL
         int at = 0;
         while (at < used) {
-            const int len = ((volatile int *)pool)[at];
+            const int len = gpsat_ld_volatile(pool + at);
             if (len <= 0 || at + 1 + len > used) break;
             if (len == 1) {
                 const int u = pool[at + 1];
@@ -830,10 +843,132 @@ struct WarpSolver {
     // Runs one cube.  mode SOLVE: full CDCL; mode PROPAGATE: stop once every cube literal is placed.
     // returns GPSAT_SAT / GPSAT_UNSAT / GPSAT_UNDEF / GPSAT_JOB_ABORTED / GPSAT_JOB_OOM; conflict_out = falsified
     // clause of the last conflict (cref) or NO_CONFLICT
-    GPSAT_DEV int run_job(const int *cube, int k, int mode, volatile const int *stop_flag, int &conflict_out)
+    // What a child inherits from the cube it was split off: the VSIDS counters, the level-0 facts and the newest
+    // learnt clauses that fit (all of them are implied by the formula alone, cube literals being decisions).
+    // Block layout: [n_record_words][vs: 2*n_vars][records ...]
+    GPSAT_DEV void write_handoff(int slot)
     {
+        GPSAT_LANE_DECL
+        if (dq_hand == nullptr) return;
+        int *h = dq_hand + (long long)slot * hand_words;
+        int *rec = h + 1 + 2 * n_vars;
+        const int cap = hand_words - 1 - 2 * n_vars;
+        LANES
+        {
+            for (int x = lane; x < 2 * n_vars; x += 32) h[1 + x] = vs[x];
+        }
+        // level-0 facts as unit records
+        const int n0 = dlevel > 0 ? trail_lim[0] : trail_size;
+        int used = 0;
+        const int n_units = (2 * n0 <= cap) ? n0 : cap / 2;
+        LANES
+        {
+            for (int i = lane; i < n_units; i += 32) {
+                rec[2 * i] = 1;
+                rec[2 * i + 1] = trail[i];
+            }
+        }
+        used = 2 * n_units;
+        // newest learnt clauses: the arena tail [refs[first] .. arena_top) that fits
+        int first = n_learnts;
+        for (int base = 0; base < n_learnts && first == n_learnts; base += 32) {
+            const unsigned m = BALLOT((base + lane < n_learnts) && (arena_top - refs[base + lane] <= cap - used));
+            if (m) first = base + gpsat_ffs(m) - 1;
+        }
+        if (first < n_learnts) {
+            const int from = refs[first];
+            const int nw = arena_top - from;
+            LANES
+            {
+                for (int i = lane; i < nw; i += 32) rec[used + i] = arena[from + i];
+            }
+            used += nw;
+        }
+        LANE0 { h[0] = used; }
+        SYNCWARP();
+    }
+
+    // Hand half of the remaining search space to another warp: queue cube + ~p, keep cube + p.
+    // Called at a restart, with exactly the k cube literals decided and propagated.  Returns the new k.
+    GPSAT_DEV int try_split(int k)
+    {
+        GPSAT_LANE_DECL
+        if (k + 1 >= GPSAT_DQ_MAXK) return k;
+        // dq_ctrl[3] = demand = idle warps - queued children - splits in flight; claim one unit of it
+        LANEVAR(int, claim_v);
+        LANES { LV(claim_v) = 0; }
+        LANE0
+        {
+            int ok = split_force;
+            if (!ok && gpsat_ld_volatile(dq_ctrl + 3) > 0) {
+                if (gpsat_atomic_add(dq_ctrl + 3, -1) > 0) ok = 1;
+                else gpsat_atomic_add(dq_ctrl + 3, 1);
+            }
+            LV(claim_v) = ok;
+        }
+        if (!SHFL(claim_v, 0)) return k;
+        const int p = pick_branch();
+        LANEVAR(int, slot_v);
+        LANES { LV(slot_v) = GPSAT_DQ_CAP; }
+        if (p >= 0) {
+            LANE0 { LV(slot_v) = gpsat_atomic_add(dq_ctrl + 0, 1); }
+        }
+        const int slot = SHFL(slot_v, 0);
+        if (slot >= GPSAT_DQ_CAP) {   // nothing to branch on, or the queue is full: give the claim back
+            LANE0
+            {
+                if (p >= 0) gpsat_atomic_add(dq_ctrl + 0, -1);
+                if (!split_force) gpsat_atomic_add(dq_ctrl + 3, 1);
+            }
+            return k;
+        }
+        LANES
+        {
+            for (int i = lane; i < k; i += 32) dq_lits[(long long)slot * GPSAT_DQ_MAXK + i] = cube_buf[i];
+        }
+        LANE0
+        {
+            dq_lits[(long long)slot * GPSAT_DQ_MAXK + k] = p ^ 1;
+            dq_meta[2 * slot] = root;
+            gpsat_atomic_add(root_pending + root, 1);
+            gpsat_atomic_add(dq_ctrl + 2, 1);
+            cube_buf[k] = p;
+        }
+        SYNCWARP();
+        write_handoff(slot);
+        gpsat_threadfence();
+        LANE0 { ((volatile int *)dq_meta)[2 * slot + 1] = k + 1; }   // publish
+        SYNCWARP();
+        c_splits++;
+        return k + 1;
+    }
+
+    GPSAT_DEV int run_job(const int *cube, int k, int mode, volatile const int *stop_flag, int &conflict_out,
+                          const int *hand)
+    {
+        GPSAT_LANE_DECL
         conflict_out = GPSAT_NO_CONFLICT;
         reset_job();
+        if (hand != nullptr) {   // a child of a split cube: inherit the parent's counters, facts and newest clauses
+            LANES
+            {
+                for (int x = lane; x < 2 * n_vars; x += 32) vs[x] = hand[1 + x];
+            }
+            SYNCWARP();
+            const int st = import_records(hand + 1 + 2 * n_vars, hand[0]);
+            if (st != GPSAT_UNDEF) return st;
+        }
+        const bool may_split = mode == GPSAT_MODE_SOLVE && dynamic_split && k + 1 < GPSAT_DQ_MAXK;
+        int want_split = 0;
+        long long last_split_at = 0;
+        if (may_split) {
+            LANES
+            {
+                for (int i = lane; i < k; i += 32) cube_buf[i] = cube[i];
+            }
+            SYNCWARP();
+            cube = cube_buf;
+        }
         if (mode == GPSAT_MODE_SOLVE) {
             const int st = pool_import();
             if (st != GPSAT_UNDEF) return st;
@@ -864,6 +999,9 @@ struct WarpSolver {
                 pool_publish(n_out);
                 if (max_conflicts && c_conflicts >= max_conflicts) return GPSAT_UNDEF;
                 if ((c_conflicts & 31) == 0 && stop_flag && *stop_flag) return GPSAT_JOB_ABORTED;
+                if (may_split && (c_conflicts & 7) == 0 && c_conflicts - last_split_at >= 32 &&
+                    gpsat_ld_volatile(dq_ctrl + 3) > 0)
+                    want_split = 1;
                 continue;
             }
             if (mode == GPSAT_MODE_PROPAGATE && dlevel >= k) return GPSAT_UNDEF;
@@ -872,6 +1010,16 @@ struct WarpSolver {
                 restart_limit = (int)((float)restart_limit * restart_factor);
                 c_restarts++;
                 cancel_until(k < dlevel ? k : dlevel);
+                if (split_force) want_split = 1;
+            }
+            if (want_split) {   // an idle warp is waiting: go back to the cube and give it half of what is left
+                want_split = 0;
+                if (dlevel >= k) {
+                    cancel_until(k);
+                    const int k2 = try_split(k);
+                    if (k2 != k) last_split_at = c_conflicts;
+                    k = k2;
+                }
             }
             if (use_learnts && (n_learnts >= max_learnts || (watch_bot - arena_top) < (arena_words - clause_base) / 4)) {
                 reduce_db();
@@ -933,6 +1081,16 @@ GPSAT_DEV void gpsat_bind(WarpSolver &S, const gpsat_formula_view &F, const gpsa
     S.vs = state + Ly.vs;
     S.lbuf = state + Ly.lbuf;
     S.lbuf_words = Ly.lbuf_words;
+    S.cube_buf = state + Ly.cube;
+    S.dynamic_split = P.dynamic_split;
+    S.split_force = P.split_force;
+    S.root = 0;
+    S.dq_lits = B.dq_lits;
+    S.dq_meta = B.dq_meta;
+    S.dq_ctrl = B.dq_ctrl;
+    S.root_pending = B.root_pending;
+    S.dq_hand = B.dq_hand;
+    S.hand_words = B.hand_words;
     S.use_learnts = (P.mode == GPSAT_MODE_SOLVE) ? 1 : 0;
     S.arena = arena;
     S.arena_words = (int)P.arena_words;
@@ -956,33 +1114,38 @@ GPSAT_DEV void gpsat_bind(WarpSolver &S, const gpsat_formula_view &F, const gpsa
     S.pool_cap_words = B.pool_cap_words;
 }
 
-GPSAT_DEV void gpsat_run_and_record(WarpSolver &S, int job, const gpsat_solve_params &P, const gpsat_run_buffers &B)
+// Runs one job (an original cube, or a child produced by a split) and folds its outcome into the record of the
+// original cube it descends from.
+GPSAT_DEV void gpsat_run_and_record(WarpSolver &S, int root, const int *cube, int k, const int *hand,
+                                    const gpsat_solve_params &P, const gpsat_run_buffers &B)
 {
     GPSAT_LANE_DECL
-    const long long c0 = B.cube_offsets[job], c1 = B.cube_offsets[job + 1];
-    const int *cube = B.cube_lits + c0;
-    const int k = (int)(c1 - c0);
     int confl;
     S.max_learnts = P.max_learnts_first;
-    const int status = S.run_job(cube, k, P.mode, B.stop_flag, confl);
+    S.root = root;
+    const int job = root;
+    const int status = S.run_job(cube, k, P.mode, B.stop_flag, confl, hand);
 
     const long long watchers = LANE_SUM_I64(S.l_watchers) + S.c_lwatchers;
     const long long words = LANE_SUM_I64(S.l_words) + S.c_lwords;
     LANE0
     {
-        gpsat_job_record r;
-        r.status = status;
-        r.reserved = 0;
-        r.decisions = S.c_decisions;
-        r.implications = S.c_implications;
-        r.conflicts = S.c_conflicts;
-        r.learnt_clauses = S.c_learnt_clauses;
-        r.learnt_literals = S.c_learnt_literals;
-        r.restarts = S.c_restarts;
-        r.watchers_visited = watchers;
-        r.clause_words_read = words;
-        r.learnt_hash = (long long)S.c_hash;
-        B.records[job] = r;
+        gpsat_job_record *r = B.records + job;
+        gpsat_atomic_add_ll((long long *)&r->decisions, S.c_decisions);
+        gpsat_atomic_add_ll((long long *)&r->implications, S.c_implications);
+        gpsat_atomic_add_ll((long long *)&r->conflicts, S.c_conflicts);
+        gpsat_atomic_add_ll((long long *)&r->learnt_clauses, S.c_learnt_clauses);
+        gpsat_atomic_add_ll((long long *)&r->learnt_literals, S.c_learnt_literals);
+        gpsat_atomic_add_ll((long long *)&r->restarts, S.c_restarts);
+        gpsat_atomic_add_ll((long long *)&r->watchers_visited, watchers);
+        gpsat_atomic_add_ll((long long *)&r->clause_words_read, words);
+        gpsat_atomic_add_ll((long long *)&r->learnt_hash, (long long)S.c_hash);
+        gpsat_atomic_add(&r->reserved, (int)S.c_splits);
+        const int flag = status == GPSAT_SAT ? GPSAT_FLAG_SAT
+                       : status == GPSAT_UNSAT ? GPSAT_FLAG_UNSAT
+                       : status == GPSAT_UNDEF ? GPSAT_FLAG_UNDEF
+                       : status == GPSAT_JOB_OOM ? GPSAT_FLAG_OOM : GPSAT_FLAG_ABORTED;
+        gpsat_atomic_max(B.root_flag + job, flag);
     }
     if (P.mode == GPSAT_MODE_PROPAGATE) {
         if (B.conflict_clause) {
@@ -1031,9 +1194,7 @@ GPSAT_DEV void gpsat_run_and_record(WarpSolver &S, int job, const gpsat_solve_pa
             LANE0 { B.n_implied[job] = n_imp; }
         }
         SYNCWARP();
-        return;
-    }
-    if (status == GPSAT_SAT) {
+    } else if (status == GPSAT_SAT) {
         LANEVAR(int, won);
         LANES { LV(won) = 0; }
         LANE0 { LV(won) = (gpsat_atomic_cas(B.sat_job, -1, job) == -1) ? 1 : 0; }
@@ -1048,5 +1209,89 @@ GPSAT_DEV void gpsat_run_and_record(WarpSolver &S, int job, const gpsat_solve_pa
                 LANE0 { gpsat_atomic_cas(B.stop_flag, 0, 1); }
             }
         }
+    }
+    // this job is closed: one fewer open descendant of the original cube, one fewer outstanding job
+    gpsat_threadfence();
+    LANE0
+    {
+        gpsat_atomic_add(B.root_pending + job, -1);
+        gpsat_atomic_add(B.dq_ctrl + 2, -1);
+    }
+    SYNCWARP();
+}
+
+// The warp's main loop: original cubes from the atomic cursor (≙ JobsQueue::next_job, SATSolver/JobsQueue.cu:10-32),
+// then children of split cubes from the dynamic queue; a warp with nothing to do advertises itself as idle (so that
+// long-running cubes split) and leaves when no job is outstanding, the stop flag is up, or the step budget is spent.
+GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const gpsat_run_buffers &B)
+{
+    GPSAT_LANE_DECL
+    int is_idle = 0;
+    while (true) {
+        LANEVAR(int, kind_v);   // 0 exit, 1 original cube, 2 queued child, 3 wait
+        LANEVAR(int, idx_v);
+        LANES
+        {
+            LV(kind_v) = 0;
+            LV(idx_v) = 0;
+        }
+        LANE0
+        {
+            int kind = 3, idx = 0;
+            if (gpsat_ld_volatile(B.stop_flag)) {
+                kind = 0;
+            } else if (B.budget_ns && gpsat_now_ns() > *B.t0 + B.budget_ns) {
+                kind = 0;
+            } else {
+                if (gpsat_ld_volatile(B.next_job) < B.n_cubes) {
+                    idx = gpsat_atomic_add(B.next_job, 1);
+                    if (idx < B.n_cubes) kind = 1;
+                }
+                if (kind == 3 && P.mode == GPSAT_MODE_SOLVE && P.dynamic_split) {
+                    const int head = gpsat_ld_volatile(B.dq_ctrl + 1);
+                    int tail = gpsat_ld_volatile(B.dq_ctrl + 0);
+                    if (tail > GPSAT_DQ_CAP) tail = GPSAT_DQ_CAP;
+                    if (head < tail && gpsat_atomic_cas(B.dq_ctrl + 1, head, head + 1) == head) {
+                        idx = head;
+                        kind = 2;
+                    }
+                }
+                if (kind == 3 && gpsat_ld_volatile(B.dq_ctrl + 2) <= 0) kind = 0;   // nothing outstanding anywhere
+            }
+            LV(kind_v) = kind;
+            LV(idx_v) = idx;
+        }
+        const int kind = SHFL(kind_v, 0);
+        const int idx = SHFL(idx_v, 0);
+        if (kind == 0) break;
+        if (kind == 3) {
+            if (!is_idle && P.dynamic_split) {
+                is_idle = 1;
+                LANE0 { gpsat_atomic_add(B.dq_ctrl + 3, 1); }   // demand +1
+            }
+            gpsat_nanosleep(1000);
+            continue;
+        }
+        if (is_idle) {
+            is_idle = 0;
+            // popping a queued child consumes the unit of demand its split claimed; any other exit returns ours
+            if (kind != 2) {
+                LANE0 { gpsat_atomic_add(B.dq_ctrl + 3, -1); }
+            }
+        }
+        if (kind == 1) {
+            const long long c0 = B.cube_offsets[idx], c1 = B.cube_offsets[idx + 1];
+            gpsat_run_and_record(S, idx, B.cube_lits + c0, (int)(c1 - c0), nullptr, P, B);
+        } else {
+            int len = 0;
+            while ((len = gpsat_ld_volatile(B.dq_meta + 2 * idx + 1)) == 0) gpsat_nanosleep(200);   // being published
+            gpsat_threadfence();
+            const int root = B.dq_meta[2 * idx];
+            const int *hand = B.dq_hand ? B.dq_hand + (long long)idx * B.hand_words : nullptr;
+            gpsat_run_and_record(S, root, B.dq_lits + (long long)idx * GPSAT_DQ_MAXK, len, hand, P, B);
+        }
+    }
+    if (is_idle) {
+        LANE0 { gpsat_atomic_add(B.dq_ctrl + 3, -1); }
     }
 }

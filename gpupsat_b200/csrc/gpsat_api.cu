@@ -92,6 +92,8 @@ struct gpsat {
     DevBuf<int64_t> conflict_clause;
     DevBuf<int32_t> gstate;
     DevBuf<int32_t> pool, pool_cursor;
+    DevBuf<int32_t> dq_lits, dq_meta, dq_ctrl, root_pending, root_flag, dq_hand;
+    std::vector<int32_t> root_pending_h, root_flag_h;
     int32_t *arena = nullptr;
     size_t arena_total_words = 0;
     int64_t pool_export_mark = 0;
@@ -156,6 +158,8 @@ gpsat_solve_params make_params(gpsat *h, int mode, int64_t implied_stride)
     P.max_conflicts = h->opts.max_conflicts;
     P.arena_words = mode == GPSAT_MODE_SOLVE ? h->arena_words : 0;
     P.implied_stride = implied_stride;
+    P.dynamic_split = (mode == GPSAT_MODE_SOLVE && h->opts.dynamic_split) ? 1 : 0;
+    P.split_force = 0;
     return P;
 }
 
@@ -218,6 +222,14 @@ int ensure_run_buffers(gpsat *h, int mode)
         CU(cudaMemsetAsync(h->pool_cursor.p, 0, 2 * sizeof(int32_t), h->stream));
         CU(cudaMemsetAsync(h->pool.p, 0, (size_t)kPoolWords * sizeof(int32_t), h->stream));
     }
+    CU(h->dq_ctrl.ensure(4));
+    CU(h->root_pending.ensure((size_t)std::max(h->n_cubes, 1)));
+    CU(h->root_flag.ensure((size_t)std::max(h->n_cubes, 1)));
+    if (mode == GPSAT_MODE_SOLVE && h->opts.dynamic_split) {
+        CU(h->dq_lits.ensure((size_t)GPSAT_DQ_CAP * GPSAT_DQ_MAXK));
+        CU(h->dq_meta.ensure((size_t)GPSAT_DQ_CAP * 2));
+        CU(h->dq_hand.ensure((size_t)GPSAT_DQ_CAP * (size_t)(1 + 2 * h->D.n_vars + GPSAT_HAND_CLAUSE_WORDS)));
+    }
     if (!h->state_in_smem) CU(h->gstate.ensure(n_warps * (size_t)h->Ly.total_words));
     if (mode == GPSAT_MODE_SOLVE) {
         const size_t want = n_warps * (size_t)h->arena_words;
@@ -260,6 +272,13 @@ gpsat_run_buffers make_buffers(gpsat *h, int mode, double budget_ms)
     B.pool_cursor = h->pool_cursor.p;
     B.pool_cap_words = (int32_t)kPoolWords;
     B.state_in_smem = h->state_in_smem;
+    B.dq_lits = h->dq_lits.p;
+    B.dq_meta = h->dq_meta.p;
+    B.dq_ctrl = h->dq_ctrl.p;
+    B.root_pending = h->root_pending.p;
+    B.dq_hand = h->dq_hand.p;
+    B.hand_words = 1 + 2 * h->D.n_vars + GPSAT_HAND_CLAUSE_WORDS;
+    B.root_flag = h->root_flag.p;
     B.t0 = h->t0.p;
     B.budget_ns = budget_ms > 0 ? (unsigned long long)(budget_ms * 1e6) : 0ull;
     return B;
@@ -267,14 +286,17 @@ gpsat_run_buffers make_buffers(gpsat *h, int mode, double budget_ms)
 
 int reset_ctrl(gpsat *h)
 {
+    const size_t nc = (size_t)std::max(h->n_cubes, 1);
     const int32_t init[4] = {0, 0, -1, 0};
+    const int32_t dq_init[4] = {0, 0, h->n_cubes, 0};   // tail, head, outstanding jobs, idle warps
     CU(cudaMemcpyAsync(h->ctrl.p, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
-    std::vector<gpsat_job_record> blank((size_t)std::max(h->n_cubes, 1));
-    std::memset(blank.data(), 0, blank.size() * sizeof(gpsat_job_record));
-    for (auto &r : blank) r.status = GPSAT_JOB_NOT_RUN;
-    CU(cudaMemcpyAsync(h->records.p, blank.data(), blank.size() * sizeof(gpsat_job_record), cudaMemcpyHostToDevice,
-                       h->stream));
-    CU(cudaStreamSynchronize(h->stream));   // `blank` is pageable host memory
+    CU(cudaMemcpyAsync(h->dq_ctrl.p, dq_init, sizeof(dq_init), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(h->records.p, 0, nc * sizeof(gpsat_job_record), h->stream));
+    CU(cudaMemsetAsync(h->root_flag.p, 0, nc * sizeof(int32_t), h->stream));
+    std::vector<int32_t> ones(nc, 1);
+    CU(cudaMemcpyAsync(h->root_pending.p, ones.data(), nc * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    if (h->dq_meta.p) CU(cudaMemsetAsync(h->dq_meta.p, 0, (size_t)GPSAT_DQ_CAP * 2 * sizeof(int32_t), h->stream));
+    CU(cudaStreamSynchronize(h->stream));   // `ones` is pageable host memory
     return GPSAT_OK;
 }
 
@@ -294,10 +316,16 @@ int launch_timed(gpsat *h, const gpsat_solve_params &P, const gpsat_run_buffers 
 
 int fetch_records(gpsat *h)
 {
-    h->records_h.resize((size_t)std::max(h->n_cubes, 1));
-    CU(cudaMemcpyAsync(h->records_h.data(), h->records.p, h->records_h.size() * sizeof(gpsat_job_record),
-                       cudaMemcpyDeviceToHost, h->stream));
+    const size_t nc = (size_t)std::max(h->n_cubes, 1);
+    h->records_h.resize(nc);
+    h->root_pending_h.resize(nc);
+    h->root_flag_h.resize(nc);
+    CU(cudaMemcpyAsync(h->records_h.data(), h->records.p, nc * sizeof(gpsat_job_record), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->root_pending_h.data(), h->root_pending.p, nc * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->root_flag_h.data(), h->root_flag.p, nc * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    // the status of an original cube is decided by all jobs that descend from it (dynamic splitting)
+    for (size_t j = 0; j < nc; j++) h->records_h[j].status = gpsat_root_status(h->root_flag_h[j], h->root_pending_h[j]);
     return GPSAT_OK;
 }
 
@@ -372,6 +400,7 @@ void gpsat_opts_default(gpsat_opts *o)
     o->warps_per_block = 0;
     o->blocks = 0;
     o->arena_words = 0;
+    o->dynamic_split = 1;
 }
 
 int gpsat_create(gpsat_t **out, int32_t n_vars, int64_t n_clauses, const int64_t *offsets, const int32_t *lits,

@@ -24,6 +24,17 @@
 #define GPSAT_JOB_ABORTED (-2)   // stopped by the early-termination flag
 #define GPSAT_JOB_OOM (-3)       // learnt arena exhausted even after reduction
 
+// dynamic cube queue (children of split cubes)
+#define GPSAT_DQ_MAXK 64         // literals per queued cube
+#define GPSAT_DQ_CAP 16384       // queued cubes per run
+#define GPSAT_HAND_CLAUSE_WORDS 4096   // learnt-clause words a child inherits from the cube it was split off
+// per-root outcome flags, combined with atomicMax (higher wins)
+#define GPSAT_FLAG_UNSAT 1
+#define GPSAT_FLAG_ABORTED 2
+#define GPSAT_FLAG_UNDEF 3
+#define GPSAT_FLAG_OOM 4
+#define GPSAT_FLAG_SAT 5
+
 struct gpsat_formula_view {
     int32_t n_vars;
     int32_t n_clauses;
@@ -53,11 +64,13 @@ struct gpsat_solve_params {
     int64_t max_conflicts;
     int64_t arena_words;         // per warp
     int64_t implied_stride;      // propagate mode: words reserved per cube in `implied`
+    int32_t dynamic_split;       // 1: a long-running cube hands half of its search space to an idle warp at restarts
+    int32_t split_force;         // test hook: split at every restart even when no warp is idle
 };
 
 // word offsets (int32 units) of the per-warp state arrays inside one warp's state block
 struct gpsat_state_layout {
-    int32_t val, seen, level, reason, trail, trail_lim, wbits, vs, lbuf;
+    int32_t val, seen, level, reason, trail, trail_lim, wbits, vs, lbuf, cube;
     int32_t total_words;
     int32_t lbuf_words;
 };
@@ -80,6 +93,14 @@ struct gpsat_run_buffers {
     int32_t *pool_cursor;          // [0] words used, [1] clauses
     int32_t pool_cap_words;
     int32_t state_in_smem;
+    // dynamic splitting: children of split cubes are queued here and popped by idle warps
+    int32_t *dq_lits;              // GPSAT_DQ_CAP * GPSAT_DQ_MAXK
+    int32_t *dq_meta;              // GPSAT_DQ_CAP * 2 : (root cube, length); length written last (0 = not published)
+    int32_t *dq_ctrl;              // [0] tail (pushed) [1] head (popped) [2] outstanding jobs [3] demand = idle warps - queued children - splits in flight
+    int32_t *dq_hand;              // GPSAT_DQ_CAP * hand_words : per queued child [n][vs 2n][records] (may be null)
+    int32_t hand_words;
+    int32_t *root_pending;         // n_cubes: open jobs descending from each original cube
+    int32_t *root_flag;            // n_cubes: GPSAT_FLAG_* (atomicMax)
     const unsigned long long *t0;     // globaltimer stamp taken right before the launch
     unsigned long long budget_ns;     // warps stop pulling new cubes once now > *t0 + budget_ns (0 = no limit)
 };
@@ -104,6 +125,18 @@ static inline void gpsat_make_layout(int32_t n_vars, int64_t n_lits, gpsat_state
     GPSAT_TAKE(vs, 2 * n);
     ly->lbuf_words = (n + 1) > 64 ? (n + 1) : 64;
     GPSAT_TAKE(lbuf, ly->lbuf_words);
+    GPSAT_TAKE(cube, GPSAT_DQ_MAXK);
 #undef GPSAT_TAKE
     ly->total_words = at;
+}
+
+// outcome of an original cube from the flags of all jobs that descend from it
+static inline int32_t gpsat_root_status(int32_t flag, int32_t pending)
+{
+    if (flag == GPSAT_FLAG_SAT) return GPSAT_SAT;
+    if (flag == GPSAT_FLAG_OOM) return GPSAT_JOB_OOM;
+    if (flag == GPSAT_FLAG_UNDEF) return GPSAT_UNDEF;
+    if (flag == GPSAT_FLAG_ABORTED) return GPSAT_JOB_ABORTED;
+    if (flag == GPSAT_FLAG_UNSAT && pending == 0) return GPSAT_UNSAT;
+    return GPSAT_JOB_NOT_RUN;   // not started, or descendants still open
 }

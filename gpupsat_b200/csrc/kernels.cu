@@ -27,7 +27,6 @@ gpsat_cdcl_kernel(const gpsat_formula_view F, const gpsat_solve_params P, const 
                   const gpsat_run_buffers B)
 {
     extern __shared__ __align__(16) int gpsat_smem[];
-    const int lane = (int)(threadIdx.x & 31u);
     const int warp_in_block = (int)(threadIdx.x >> 5);
     const int warps_per_block = (int)(blockDim.x >> 5);
     const long long gwarp = (long long)blockIdx.x * warps_per_block + warp_in_block;
@@ -39,19 +38,7 @@ gpsat_cdcl_kernel(const gpsat_formula_view F, const gpsat_solve_params P, const 
     WarpSolver S;
     gpsat_bind(S, F, P, Ly, state, arena, B);
 
-    while (true) {
-        int job = 0;
-        int go = 1;
-        if (lane == 0) {
-            if (*(volatile int *)B.stop_flag) go = 0;
-            if (go && B.budget_ns && globaltimer_ns() > *B.t0 + B.budget_ns) go = 0;
-            if (go) job = atomicAdd(B.next_job, 1);
-        }
-        go = __shfl_sync(0xffffffffu, go, 0);
-        job = __shfl_sync(0xffffffffu, job, 0);
-        if (!go || job >= B.n_cubes) break;
-        gpsat_run_and_record(S, job, P, B);
-    }
+    gpsat_warp_loop(S, P, B);
 }
 
 // One thread per (assignment, clause).  Clause literals are read from the compact CSR (4 B per literal, coalesced

@@ -58,6 +58,11 @@ static inline void gpsat_atomic_and(uint32_t *p, uint32_t v) { *p &= v; }
 static inline int gpsat_atomic_add(int *p, int v) { int o = *p; *p += v; return o; }
 static inline int gpsat_atomic_cas(int *p, int cmp, int v) { int o = *p; if (o == cmp) *p = v; return o; }
 static inline void gpsat_threadfence() {}
+static inline int gpsat_atomic_max(int *p, int v) { int o = *p; if (v > o) *p = v; return o; }
+static inline void gpsat_atomic_add_ll(long long *p, long long v) { *p += v; }
+static inline int gpsat_ld_volatile(const int *p) { return *(const volatile int *)p; }
+static inline void gpsat_nanosleep(unsigned) {}
+static inline unsigned long long gpsat_now_ns() { return 0; }
 static inline int gpsat_popc(unsigned m) { return __builtin_popcount(m); }
 static inline int gpsat_ffs(unsigned m) { return __builtin_ffs((int)m); }
 struct gpsat_int2 { int x, y; };
@@ -109,6 +114,19 @@ __device__ __forceinline__ void gpsat_atomic_and(uint32_t *p, uint32_t v) { atom
 __device__ __forceinline__ int gpsat_atomic_add(int *p, int v) { return atomicAdd(p, v); }
 __device__ __forceinline__ int gpsat_atomic_cas(int *p, int cmp, int v) { return atomicCAS(p, cmp, v); }
 __device__ __forceinline__ void gpsat_threadfence() { __threadfence(); }
+__device__ __forceinline__ int gpsat_atomic_max(int *p, int v) { return atomicMax(p, v); }
+__device__ __forceinline__ void gpsat_atomic_add_ll(long long *p, long long v)
+{
+    atomicAdd((unsigned long long *)p, (unsigned long long)v);
+}
+__device__ __forceinline__ int gpsat_ld_volatile(const int *p) { return *(const volatile int *)p; }
+__device__ __forceinline__ void gpsat_nanosleep(unsigned ns) { __nanosleep(ns); }
+__device__ __forceinline__ unsigned long long gpsat_now_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ int gpsat_popc(unsigned m) { return __popc(m); }
 __device__ __forceinline__ int gpsat_ffs(unsigned m) { return __ffs((int)m); }
 typedef int2 gint2;

@@ -109,7 +109,11 @@ typedef struct gpsat_opts {
     int32_t warps_per_block;      /* 0 = auto */
     int32_t blocks;               /* 0 = auto (SM count x resident blocks) */
     int64_t arena_words;          /* per-warp learnt-clause arena (int32 words); 0 = auto */
-    int32_t reserved[8];
+    int32_t dynamic_split;        /* 1 (default): at a restart a long-running cube hands half of its remaining search
+                                     space to an idle warp (the reference's wave-synchronous loop waits for the slowest
+                                     job instead: SATSolver/main.cu:259-269).  Verdicts are unaffected; per-cube counters
+                                     then depend on timing, so parity runs set 0. */
+    int32_t reserved[7];
 } gpsat_opts;
 
 void gpsat_opts_default(gpsat_opts *o);
@@ -118,7 +122,7 @@ void gpsat_opts_default(gpsat_opts *o);
  * share_learnts = 0, a pure function of (formula, cube, opts) — the parity tests compare them with the oracle. */
 typedef struct gpsat_job_record {
     int32_t status;               /* GPSAT_SAT / UNSAT / UNDEF; -1 = not run (run ended early) */
-    int32_t reserved;
+    int32_t reserved;             /* number of times this cube was split (dynamic_split) */
     int64_t decisions;
     int64_t implications;         /* literals assigned by unit propagation (≙ VariablesStateHandler::new_implication) */
     int64_t conflicts;

@@ -22,7 +22,7 @@ class SolveParams(C.Structure):
                 ("restart_factor", C.c_float), ("max_iterations", C.c_int32), ("stop_on_sat", C.c_int32),
                 ("share_learnts", C.c_int32), ("share_max_len", C.c_int32), ("max_learnts_first", C.c_int32),
                 ("learnt_refs_cap", C.c_int32), ("max_conflicts", C.c_int64), ("arena_words", C.c_int64),
-                ("implied_stride", C.c_int64)]
+                ("implied_stride", C.c_int64), ("dynamic_split", C.c_int32), ("split_force", C.c_int32)]
 
 
 def build(force=False):
@@ -40,7 +40,8 @@ def _p(a):
 
 def run(n_vars, offsets, lits, cube_offsets, cube_lits, *, mode=0, decision=1, restart_first=100, restart_factor=1.3,
         max_iterations=0, max_conflicts=0, max_learnts_first=None, learnt_refs_cap=16384, arena_words=1 << 19,
-        stop_on_sat=True, share_learnts=0, share_max_len=8, pool=None, pool_cursor=None):
+        stop_on_sat=True, share_learnts=0, share_max_len=8, pool=None, pool_cursor=None, dynamic_split=0,
+        split_force=0):
     build()
     lib = C.CDLL(SO)
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
@@ -53,7 +54,7 @@ def run(n_vars, offsets, lits, cube_offsets, cube_lits, *, mode=0, decision=1, r
         max_learnts_first = max(min(max(m // 3, 300), learnt_refs_cap - n_vars - 2), 1)
     P = SolveParams(mode, decision, 0, restart_first, restart_factor, max_iterations, 1 if stop_on_sat else 0,
                     share_learnts, share_max_len, max_learnts_first, learnt_refs_cap, max_conflicts, arena_words,
-                    n_vars)
+                    n_vars, dynamic_split, split_force)
     rec = np.zeros(n_cubes, dtype=RECORD_DTYPE)
     model = np.zeros(max(n_vars, 1), dtype=np.uint8)
     sat_job = C.c_int32(-1)

@@ -52,13 +52,22 @@ extern "C" int gpsat_emu_run(int32_t n_vars, int64_t n_clauses, const int64_t *o
     B.pool = pool;
     B.pool_cursor = pool_cursor;
     B.pool_cap_words = pool_cap_words;
-    for (int j = 0; j < n_cubes; j++) records[j].status = GPSAT_JOB_NOT_RUN;
+    std::memset(records, 0, sizeof(gpsat_job_record) * (size_t)n_cubes);
+    std::vector<int32_t> dq_lits((size_t)GPSAT_DQ_CAP * GPSAT_DQ_MAXK, 0), dq_meta((size_t)GPSAT_DQ_CAP * 2, 0);
+    std::vector<int32_t> root_pending((size_t)n_cubes, 1), root_flag((size_t)n_cubes, 0);
+    int32_t dq_ctrl[4] = {0, 0, n_cubes, 0};
+    B.dq_lits = dq_lits.data();
+    B.dq_meta = dq_meta.data();
+    B.dq_ctrl = dq_ctrl;
+    B.root_pending = root_pending.data();
+    B.hand_words = 1 + 2 * n_vars + GPSAT_HAND_CLAUSE_WORDS;
+    std::vector<int32_t> dq_hand(P.dynamic_split ? (size_t)GPSAT_DQ_CAP * B.hand_words : 1, 0);
+    B.dq_hand = P.dynamic_split ? dq_hand.data() : nullptr;
+    B.root_flag = root_flag.data();
     WarpSolver S;
     std::memset(&S, 0, sizeof(S));
     gpsat_bind(S, F, P, Ly, state.data(), arena.data(), B);
-    for (int j = 0; j < n_cubes; j++) {
-        if (stop_flag) break;
-        gpsat_run_and_record(S, j, P, B);
-    }
+    gpsat_warp_loop(S, P, B);
+    for (int j = 0; j < n_cubes; j++) records[j].status = gpsat_root_status(root_flag[j], root_pending[j]);
     return 0;
 }

@@ -122,3 +122,23 @@ def test_pool_import_and_publish():
                     pool=first["pool"], pool_cursor=first["pool_cursor"])
     assert np.array_equal(base["records"]["status"], again["records"]["status"])
     assert again["records"]["conflicts"].sum() <= base["records"]["conflicts"].sum()
+
+
+def test_dynamic_split_keeps_verdicts():
+    """forced splitting at every restart (test hook): children are queued and solved; every original cube gets the
+    same status as without splitting, SAT models verify, and all queued children are closed."""
+    for n, m, seed, bt in ((100, 426, 0, (1, 1)), (100, 426, 3, (1, 8)), (120, 511, 1, (1, 2))):
+        offs, lits = random_ksat(n, m, seed)
+        pre = g.Cnf.from_arrays(offs, lits).preprocess()
+        cubes = pre.choose_cubes(*bt)
+        co, cl = cube_csr(cubes)
+        base = emu.run(n, pre.offsets, pre.lits, co, cl, stop_on_sat=False)
+        split = emu.run(n, pre.offsets, pre.lits, co, cl, stop_on_sat=False, dynamic_split=1, split_force=1)
+        assert np.array_equal(base["records"]["status"], split["records"]["status"])
+        if bt == (1, 1):
+            assert split["records"]["reserved"].sum() > 0      # cubes long enough to reach a restart were split
+        if split["sat_job"] >= 0:
+            assert check_model(pre.offsets, pre.lits, split["model"])
+        # without the hook (nobody is ever idle in the one-warp emulator) the run is identical to no splitting
+        quiet_split = emu.run(n, pre.offsets, pre.lits, co, cl, stop_on_sat=False, dynamic_split=1)
+        assert same(base["records"], quiet_split["records"]) == []

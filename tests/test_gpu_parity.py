@@ -50,7 +50,7 @@ def test_sequential_solve_bit_exact(n, m, seed, decision):
     """config 1 style (-b 1 -t 1): one empty cube; every counter and the learnt-clause checksum equal the oracle's."""
     offs, lits = random_ksat(n, m, seed)
     cnf, pre = _prep(offs, lits)
-    with g.Solver(cnf.n_vars, pre.offsets, pre.lits, decision=decision) as s:
+    with g.Solver(cnf.n_vars, pre.offsets, pre.lits, decision=decision, dynamic_split=0) as s:
         s.set_cubes(None)
         verdict, model, stats = s.solve()
         rec = s.job_records()
@@ -68,7 +68,7 @@ def test_cube_solve_bit_exact_and_verdict():
     offs, lits = random_ksat(100, 426, 3)
     cnf, pre = _prep(offs, lits)
     cubes = pre.choose_cubes(1, 8)          # 80 jobs wanted -> k = 7, 128 cubes
-    with g.Solver(cnf.n_vars, pre.offsets, pre.lits, stop_on_sat=0) as s:
+    with g.Solver(cnf.n_vars, pre.offsets, pre.lits, stop_on_sat=0, dynamic_split=0) as s:
         s.set_cubes(cubes)
         verdict, model, stats = s.solve()
         rec = s.job_records()
@@ -86,7 +86,7 @@ def test_cube_solve_bit_exact_and_verdict():
 def test_pigeonhole_unsat():
     offs, lits = pigeonhole(7, 6)
     cnf, pre = _prep(offs, lits)
-    with g.Solver(cnf.n_vars, pre.offsets, pre.lits) as s:
+    with g.Solver(cnf.n_vars, pre.offsets, pre.lits, dynamic_split=0) as s:
         s.set_cubes(None)
         verdict, _, _ = s.solve()
         rec = s.job_records()
@@ -107,3 +107,22 @@ def test_eval_clauses():
     st2, unit2 = o.eval_clauses(assignment)
     assert np.array_equal(st, st2)
     assert np.array_equal(unit, unit2)
+
+
+def test_dynamic_split_same_verdicts():
+    """default options (dynamic splitting on): per-cube statuses equal the oracle's, every cube is closed, models verify"""
+    for seed in (3, 6):
+        offs, lits = random_ksat(120, 511, seed)
+        cnf, pre = _prep(offs, lits)
+        cubes = pre.choose_cubes(1, 2)          # few, long cubes: idle warps exist from the start -> splits happen
+        with g.Solver(cnf.n_vars, pre.offsets, pre.lits, stop_on_sat=0) as s:
+            s.set_cubes(cubes)
+            verdict, model, stats = s.solve()
+            rec = s.job_records()
+        o = Oracle(cnf.n_vars, pre.offsets, pre.lits)
+        k = cubes.shape[1]
+        want = o.run(np.arange(0, cubes.size + 1, k, dtype=np.int64), cubes.reshape(-1), stop_on_sat=False)
+        assert np.array_equal(rec["status"], want["records"]["status"])
+        assert stats["jobs_done"] == len(cubes)
+        if verdict == g.SAT:
+            assert check_model(pre.offsets, pre.lits, model)
