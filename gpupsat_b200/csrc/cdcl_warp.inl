@@ -1269,7 +1269,7 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
                 is_idle = 1;
                 LANE0 { gpsat_atomic_add(B.dq_ctrl + 3, 1); }   // demand +1
             }
-            gpsat_nanosleep(1000);
+            gpsat_nanosleep(4000);   // idle warps must not steal issue slots from the busy ones
             continue;
         }
         if (is_idle) {

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -99,7 +100,7 @@ struct gpsat {
     int64_t pool_export_mark = 0;
     // geometry
     gpsat_state_layout Ly{};
-    int blocks = 0, warps_per_block = 0, state_in_smem = 0;
+    int blocks = 0, warps_per_block = 0, state_in_smem = 0, formula_in_smem = 0, formula_smem_words = 0;
     size_t smem_bytes = 0;
     int64_t arena_words = 0;
     // last run
@@ -171,35 +172,49 @@ int plan_geometry(gpsat *h, int mode)
     const size_t smem_block_max = h->prop.sharedMemPerBlockOptin;                 // 227 KB on B200
     const size_t smem_sm = h->prop.sharedMemPerMultiprocessor;                    // 228 KB
     int w = h->opts.warps_per_block;
-    int bps = 1;
+    const int w_max = gpsat_kernels::cdcl_max_warps_per_block();
+    const size_t smem_max = std::min(smem_block_max, smem_sm - 1024);
+    // read-only formula index staged once per block when it leaves room for at least 8 warps of state
+    const size_t f_words = (size_t)((2 * (h->D.n_lits + h->D.n_clauses) + 3) & ~(int64_t)3) +
+                           (size_t)((2 * h->D.n_lits + 3) & ~(int64_t)3) + (size_t)((2 * (int64_t)h->D.n_vars + 1 + 3) & ~(int64_t)3);
     h->state_in_smem = 1;
+    h->formula_in_smem = 0;
+    h->formula_smem_words = 0;
+    const bool allow_formula = std::getenv("GPSAT_NO_SMEM_FORMULA") == nullptr;
+    if (allow_formula && mode == GPSAT_MODE_SOLVE && f_words * 4 + 8 * bytes_per_warp <= smem_max) {
+        h->formula_in_smem = 1;
+        h->formula_smem_words = (int)f_words;
+    }
+    const size_t room = smem_max - (size_t)h->formula_smem_words * 4;
     if (w <= 0) {
-        const int fit_sm = (int)std::min<size_t>(64, (smem_sm - 2048) / std::max<size_t>(bytes_per_warp, 1));
-        if (fit_sm >= 4) {
-            if (fit_sm <= 32) {
-                w = fit_sm;
-            } else {
-                bps = 2;
-                w = std::min(32, fit_sm / 2);
-            }
+        const int fit = (int)std::min<size_t>((size_t)w_max, room / std::max<size_t>(bytes_per_warp, 1));
+        if (fit >= 4) {
+            w = fit;
         } else {
             h->state_in_smem = 0;
             w = 16;
-            bps = 2;
         }
-    } else if ((size_t)w * bytes_per_warp > smem_block_max) {
-        h->state_in_smem = 0;
+    } else if ((size_t)w * bytes_per_warp > room) {
+        if ((size_t)w * bytes_per_warp <= smem_max) {
+            h->formula_in_smem = 0;
+            h->formula_smem_words = 0;
+        } else {
+            h->state_in_smem = 0;
+        }
     }
-    if (w > 32) w = 32;
+    if (!h->state_in_smem) {
+        h->formula_in_smem = 0;
+        h->formula_smem_words = 0;
+    }
+    if (w > w_max) w = w_max;
     h->warps_per_block = w;
-    h->smem_bytes = h->state_in_smem ? (size_t)w * bytes_per_warp : 0;
+    h->smem_bytes = h->state_in_smem ? (size_t)w * bytes_per_warp + (size_t)h->formula_smem_words * 4 : 0;
     int occ = 0;
-    CU(gpsat_kernels::cdcl_occupancy(w, h->smem_bytes, &occ));
+    CU(gpsat_kernels::cdcl_occupancy(w, h->smem_bytes, h->state_in_smem != 0, h->formula_in_smem != 0, &occ));
     if (occ < 1) {
         set_error("kernel configuration does not fit on an SM");
         return GPSAT_E_CUDA;
     }
-    (void)bps;
     int blocks = h->opts.blocks > 0 ? h->opts.blocks : h->prop.multiProcessorCount * occ;
     // never launch more warps than cubes (each warp owns an arena / state block)
     const int64_t need = ((int64_t)std::max(h->n_cubes, 1) + w - 1) / w;
@@ -272,6 +287,8 @@ gpsat_run_buffers make_buffers(gpsat *h, int mode, double budget_ms)
     B.pool_cursor = h->pool_cursor.p;
     B.pool_cap_words = (int32_t)kPoolWords;
     B.state_in_smem = h->state_in_smem;
+    B.formula_in_smem = h->formula_in_smem;
+    B.formula_smem_words = h->formula_smem_words;
     B.dq_lits = h->dq_lits.p;
     B.dq_meta = h->dq_meta.p;
     B.dq_ctrl = h->dq_ctrl.p;

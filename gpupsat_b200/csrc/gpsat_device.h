@@ -93,6 +93,8 @@ struct gpsat_run_buffers {
     int32_t *pool_cursor;          // [0] words used, [1] clauses
     int32_t pool_cap_words;
     int32_t state_in_smem;
+    int32_t formula_in_smem;       // cl2 / occ2 / ostart staged once per block in front of the warps' state blocks
+    int32_t formula_smem_words;    // size of that staging area (multiple of 4 words)
     // dynamic splitting: children of split cubes are queued here and popped by idle warps
     int32_t *dq_lits;              // GPSAT_DQ_CAP * GPSAT_DQ_MAXK
     int32_t *dq_meta;              // GPSAT_DQ_CAP * 2 : (root cube, length); length written last (0 = not published)

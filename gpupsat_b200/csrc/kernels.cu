@@ -11,6 +11,8 @@
 #include "kernels.h"
 #include "cdcl_warp.inl"
 
+#define GPSAT_MAX_THREADS 768   // 24 warps per block: up to 85 registers per thread
+
 namespace {
 
 __device__ __forceinline__ unsigned long long globaltimer_ns()
@@ -22,7 +24,13 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 
 __global__ void gpsat_stamp_kernel(unsigned long long *t0) { *t0 = globaltimer_ns(); }
 
-__global__ void __launch_bounds__(1024, 1)
+// kSmemState:   the per-job state blocks live in dynamic shared memory.
+// kSmemFormula: the read-only formula index (cl2, occ2, ostart) is staged once per block in shared memory, in front
+//               of the state blocks, and every warp of the block reads it from there.
+// Both are template parameters (not run-time selects) so that the pointers provably derive from the shared window
+// and compile to LDS/STS/ATOMS instead of generic loads.
+template <bool kSmemState, bool kSmemFormula>
+__global__ void __launch_bounds__(GPSAT_MAX_THREADS, 1)
 gpsat_cdcl_kernel(const gpsat_formula_view F, const gpsat_solve_params P, const gpsat_state_layout Ly,
                   const gpsat_run_buffers B)
 {
@@ -31,14 +39,41 @@ gpsat_cdcl_kernel(const gpsat_formula_view F, const gpsat_solve_params P, const 
     const int warps_per_block = (int)(blockDim.x >> 5);
     const long long gwarp = (long long)blockIdx.x * warps_per_block + warp_in_block;
 
-    int *state = B.state_in_smem ? gpsat_smem + (size_t)warp_in_block * Ly.total_words
-                                 : B.gstate + (size_t)gwarp * Ly.total_words;
+    gpsat_formula_view Fv = F;
+    int *state_base = gpsat_smem;
+    if (kSmemFormula) {
+        // layout: cl2 | occ2 | ostart, each rounded up to 4 words
+        const int n_cl2 = 2 * (F.n_lits + F.n_clauses), n_occ2 = 2 * F.n_lits, n_os = 2 * F.n_vars + 1;
+        int *s_cl2 = gpsat_smem;
+        int *s_occ2 = s_cl2 + ((n_cl2 + 3) & ~3);
+        int *s_os = s_occ2 + ((n_occ2 + 3) & ~3);
+        const int *g_cl2 = (const int *)F.cl2, *g_occ2 = (const int *)F.occ2;
+        for (int i = (int)threadIdx.x; i < n_cl2; i += (int)blockDim.x) s_cl2[i] = g_cl2[i];
+        for (int i = (int)threadIdx.x; i < n_occ2; i += (int)blockDim.x) s_occ2[i] = g_occ2[i];
+        for (int i = (int)threadIdx.x; i < n_os; i += (int)blockDim.x) s_os[i] = F.ostart[i];
+        __syncthreads();
+        Fv.cl2 = s_cl2;
+        Fv.occ2 = s_occ2;
+        Fv.ostart = s_os;
+        state_base = gpsat_smem + B.formula_smem_words;
+    }
+    int *state;
+    if (kSmemState) state = state_base + (size_t)warp_in_block * Ly.total_words;
+    else state = B.gstate + (size_t)gwarp * Ly.total_words;
     int *arena = B.arena ? B.arena + (size_t)gwarp * (size_t)P.arena_words : nullptr;
 
     WarpSolver S;
-    gpsat_bind(S, F, P, Ly, state, arena, B);
-
+    gpsat_bind(S, Fv, P, Ly, state, arena, B);
     gpsat_warp_loop(S, P, B);
+}
+
+typedef void (*cdcl_kernel_t)(const gpsat_formula_view, const gpsat_solve_params, const gpsat_state_layout,
+                              const gpsat_run_buffers);
+cdcl_kernel_t pick_kernel(bool smem_state, bool smem_formula)
+{
+    if (smem_state && smem_formula) return gpsat_cdcl_kernel<true, true>;
+    if (smem_state) return gpsat_cdcl_kernel<true, false>;
+    return gpsat_cdcl_kernel<false, false>;
 }
 
 // One thread per (assignment, clause).  Clause literals are read from the compact CSR (4 B per literal, coalesced
@@ -84,23 +119,33 @@ cudaError_t launch_cdcl(const gpsat_formula_view &F, const gpsat_solve_params &P
                         const gpsat_run_buffers &B, int blocks, int warps_per_block, size_t smem_bytes,
                         cudaStream_t stream)
 {
-    cudaError_t e = cudaFuncSetAttribute(gpsat_cdcl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess) return e;
-    gpsat_cdcl_kernel<<<blocks, warps_per_block * 32, smem_bytes, stream>>>(F, P, Ly, B);
+    if (warps_per_block * 32 > GPSAT_MAX_THREADS) return cudaErrorInvalidConfiguration;
+    cdcl_kernel_t k = pick_kernel(B.state_in_smem != 0, B.formula_in_smem != 0);
+    if (smem_bytes > 0) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) return e;
+    }
+    k<<<blocks, warps_per_block * 32, smem_bytes, stream>>>(F, P, Ly, B);
     return cudaGetLastError();
 }
 
-cudaError_t cdcl_occupancy(int warps_per_block, size_t smem_bytes, int *blocks_per_sm)
+cudaError_t cdcl_occupancy(int warps_per_block, size_t smem_bytes, bool smem_state, bool smem_formula,
+                           int *blocks_per_sm)
 {
-    cudaError_t e = cudaFuncSetAttribute(gpsat_cdcl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, gpsat_cdcl_kernel, warps_per_block * 32, smem_bytes);
+    cdcl_kernel_t k = pick_kernel(smem_state, smem_formula);
+    if (smem_bytes > 0) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, warps_per_block * 32, smem_bytes);
 }
+
+int cdcl_max_warps_per_block() { return GPSAT_MAX_THREADS / 32; }
 
 cudaError_t cdcl_attributes(int *regs_per_thread, size_t *local_bytes)
 {
     cudaFuncAttributes a;
-    cudaError_t e = cudaFuncGetAttributes(&a, gpsat_cdcl_kernel);
+    cudaError_t e = cudaFuncGetAttributes(&a, gpsat_cdcl_kernel<true, true>);
     if (e != cudaSuccess) return e;
     *regs_per_thread = a.numRegs;
     *local_bytes = a.localSizeBytes;

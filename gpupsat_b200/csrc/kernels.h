@@ -11,8 +11,10 @@ cudaError_t launch_cdcl(const gpsat_formula_view &F, const gpsat_solve_params &P
                         const gpsat_run_buffers &B, int blocks, int warps_per_block, size_t smem_bytes,
                         cudaStream_t stream);
 // resident blocks per SM for that configuration (cudaOccupancyMaxActiveBlocksPerMultiprocessor)
-cudaError_t cdcl_occupancy(int warps_per_block, size_t smem_bytes, int *blocks_per_sm);
+cudaError_t cdcl_occupancy(int warps_per_block, size_t smem_bytes, bool smem_state, bool smem_formula,
+                           int *blocks_per_sm);
 cudaError_t cdcl_attributes(int *regs_per_thread, size_t *local_bytes);
+int cdcl_max_warps_per_block();
 
 // stamps *t0 with the GPU's globaltimer (deadline base for budgeted steps)
 cudaError_t launch_stamp(unsigned long long *t0, cudaStream_t stream);

@@ -130,9 +130,10 @@ __device__ __forceinline__ unsigned long long gpsat_now_ns()
 __device__ __forceinline__ int gpsat_popc(unsigned m) { return __popc(m); }
 __device__ __forceinline__ int gpsat_ffs(unsigned m) { return __ffs((int)m); }
 typedef int2 gint2;
-// read-only formula index: non-coherent path, stays in L1 across the jobs of an SM
-__device__ __forceinline__ gint2 gpsat_ld2(const gint2 *p) { return __ldg(p); }
-__device__ __forceinline__ int gpsat_ld(const int *p) { return __ldg(p); }
+// read-only formula index: plain loads, so the same code reads it from shared memory (staged once per block when it
+// fits) or from global memory through L1/L2
+__device__ __forceinline__ gint2 gpsat_ld2(const gint2 *p) { return *p; }
+__device__ __forceinline__ int gpsat_ld(const int *p) { return *p; }
 
 #endif
 
