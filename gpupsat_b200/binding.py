@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(HERE, "libgpsat.so")
 
 SAT, UNSAT, UNDEF = 0, 1, 2
 DECIDE_REFERENCE, DECIDE_VSIDS = 0, 1
+BCP_WATCHED, BCP_OCCURRENCE = 0, 1
 STRATEGY_DISTRIBUTED, STRATEGY_UNIFORM = 0, 1
 E_NO_DEVICE = -2
 
@@ -83,6 +84,8 @@ def lib():
     L.gpsat_eval_clauses.argtypes = [vp, i32, vp, vp, vp]
     L.gpsat_solve.argtypes = [vp, C.POINTER(i32), vp, C.POINTER(GpsatStats)]
     L.gpsat_job_records.argtypes = [vp, vp, i32]
+    L.gpsat_last_kernel_ms.argtypes = [vp]
+    L.gpsat_last_kernel_ms.restype = C.c_double
     L.gpsat_solve_begin.argtypes = [vp]
     L.gpsat_solve_step.argtypes = [vp, C.c_double, C.POINTER(i32), C.POINTER(i32)]
     L.gpsat_solve_end.argtypes = [vp, C.POINTER(i32), vp, C.POINTER(GpsatStats)]
@@ -266,6 +269,9 @@ class Solver:
         st = GpsatStats()
         _check(lib().gpsat_solve(self.h, C.byref(verdict), _p(model), C.byref(st)))
         return verdict.value, model[: self.n_vars], st.as_dict()
+
+    def last_kernel_ms(self):
+        return float(lib().gpsat_last_kernel_ms(self.h))
 
     def job_records(self):
         rec = np.zeros(self.n_cubes, dtype=RECORD_DTYPE)

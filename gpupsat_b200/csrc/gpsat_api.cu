@@ -78,6 +78,11 @@ struct gpsat {
     DevBuf<int32_t> cstart, cl2, ostart, occ2, vsids0, coffsets, clits;
     DevBuf<uint32_t> wbits0;
     DevBuf<uint8_t> val0;
+    // occurrence-mode BCP (opts.bcp == GPSAT_BCP_OCCURRENCE)
+    DevBuf<int32_t> occ_clause, occ_pair;
+    DevBuf<uint32_t> valbits;
+    DevBuf<int64_t> sweep_counters;
+    int uniform3 = 0;
     // cubes
     int32_t n_cubes = 0;
     bool cubes_set = false;
@@ -395,6 +400,94 @@ int32_t run_verdict(gpsat *h, bool *all_done)
     return GPSAT_UNSAT;
 }
 
+// occurrence-list BCP for large clause databases: gpsat_bcp_sweep_kernel, one warp per cube, all state in HBM
+int propagate_all_occurrence(gpsat *h, int32_t *status, int32_t *n_implied, int32_t *implied, int64_t implied_stride,
+                             int64_t *conflict_clause, gpsat_job_record *records)
+{
+    const size_t nc = (size_t)h->n_cubes;
+    if (implied_stride <= 0) implied_stride = h->D.n_vars;       // the implied block doubles as the trail
+    int wpb = h->opts.warps_per_block > 0 ? std::min(h->opts.warps_per_block, 32) : 32;
+    int blocks = h->opts.blocks > 0 ? h->opts.blocks : h->prop.multiProcessorCount;   // 1024 threads: 1 block per SM
+    const int64_t need = ((int64_t)nc + wpb - 1) / wpb;
+    if (blocks > need) blocks = (int)std::max<int64_t>(need, 1);
+    const size_t n_warps = (size_t)blocks * wpb;
+    const int32_t val_words = (h->D.n_vars + 15) / 16;
+    CU(h->ctrl.ensure(4));
+    if (h->valbits.n < n_warps * (size_t)val_words) {
+        CU(h->valbits.ensure(n_warps * (size_t)val_words));
+        CU(cudaMemsetAsync(h->valbits.p, 0, n_warps * (size_t)val_words * sizeof(uint32_t), h->stream));
+    }
+    CU(h->implied.ensure(nc * (size_t)implied_stride));
+    CU(h->n_implied.ensure(nc));
+    CU(h->conflict_clause.ensure(nc));
+    CU(h->records.ensure(nc));           // reused as int32 status scratch below
+    CU(h->sweep_counters.ensure(2 * nc));
+    DevBuf<int32_t> d_status;
+    CU(d_status.ensure(nc));
+    CU(cudaMemsetAsync(h->ctrl.p, 0, 4 * sizeof(int32_t), h->stream));
+    gpsat_kernels::SweepLaunch L;
+    L.n_vars = h->D.n_vars;
+    L.n_clauses = (int32_t)h->D.n_clauses;
+    L.n_cubes = h->n_cubes;
+    L.uniform3 = h->uniform3;
+    L.ostart = h->ostart.p;
+    L.occ_clause = h->occ_clause.p;
+    L.occ_pair = h->occ_pair.p;
+    L.coffsets = h->coffsets.p;
+    L.clits = h->clits.p;
+    L.cube_offsets = h->cube_offsets.p;
+    L.cube_lits = h->cube_lits.p;
+    L.valbits = h->valbits.p;
+    L.val_words = val_words;
+    L.implied = h->implied.p;
+    L.stride = implied_stride;
+    L.n_implied = h->n_implied.p;
+    L.status = d_status.p;
+    L.conflict_clause = h->conflict_clause.p;
+    L.counters = h->sweep_counters.p;
+    L.next_job = h->ctrl.p;
+    L.blocks = blocks;
+    L.warps_per_block = wpb;
+    h->kernel_ms = 0;
+    h->kernel_launches = 0;
+    h->blocks = blocks;
+    h->warps_per_block = wpb;
+    h->smem_bytes = 512;
+    h->state_in_smem = 0;
+    CU(cudaEventRecord(h->ev0, h->stream));
+    CU(gpsat_kernels::launch_bcp_sweep(L, h->stream));
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->kernel_ms = ms;
+    h->kernel_launches = 1;
+    std::vector<int32_t> st(nc), ni(nc);
+    std::vector<int64_t> cnt(2 * nc);
+    CU(cudaMemcpy(st.data(), d_status.p, nc * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(ni.data(), h->n_implied.p, nc * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(cnt.data(), h->sweep_counters.p, 2 * nc * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    h->records_h.assign(nc, gpsat_job_record());
+    for (size_t j = 0; j < nc; j++) {
+        gpsat_job_record &r = h->records_h[j];
+        std::memset(&r, 0, sizeof(r));
+        r.status = st[j];
+        r.implications = ni[j];
+        r.conflicts = st[j] == GPSAT_UNSAT ? 1 : 0;
+        r.watchers_visited = cnt[2 * j];
+        r.clause_words_read = cnt[2 * j + 1];
+    }
+    h->run_mode = GPSAT_MODE_PROPAGATE;
+    if (status) std::memcpy(status, st.data(), nc * sizeof(int32_t));
+    if (n_implied) std::memcpy(n_implied, ni.data(), nc * sizeof(int32_t));
+    if (records) std::memcpy(records, h->records_h.data(), nc * sizeof(gpsat_job_record));
+    if (conflict_clause)
+        CU(cudaMemcpy(conflict_clause, h->conflict_clause.p, nc * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (implied)
+        CU(cudaMemcpy(implied, h->implied.p, nc * (size_t)implied_stride * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return GPSAT_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -488,6 +581,28 @@ int gpsat_create(gpsat_t **out, int32_t n_vars, int64_t n_clauses, const int64_t
     CUH(h->val0.upload(h->D.val0.data(), h->D.val0.size(), h->stream));
     CUH(h->coffsets.upload(h->coffsets_h.data(), h->coffsets_h.size(), h->stream));
     CUH(h->clits.upload(lits + base, (size_t)h->D.n_lits, h->stream));
+    if (h->opts.bcp == GPSAT_BCP_OCCURRENCE) {
+        // occurrence slot -> clause index, and for pure 3-SAT the two other literals of that clause (no clause
+        // dereference on the hot path)
+        const size_t L = (size_t)h->D.n_lits;
+        std::vector<int32_t> oc(L), op;
+        h->uniform3 = (h->D.n_clauses > 0 && h->D.n_lits == 3 * h->D.n_clauses && h->D.max_clause_len == 3) ? 1 : 0;
+        if (h->uniform3) op.resize(2 * L);
+        for (size_t k = 0; k < L; k++) {
+            const int32_t s0 = h->D.occ2[2 * k], len = h->D.occ2[2 * k + 1];
+            oc[k] = h->D.cl2[2 * (size_t)(s0 - 1) + 1];
+            if (h->uniform3) {
+                int w = 0;
+                for (int i = 0; i < len; i++) {
+                    if (h->D.cl2[2 * (size_t)(s0 + i) + 1] == (int32_t)k) continue;
+                    op[2 * k + (w++)] = h->D.cl2[2 * (size_t)(s0 + i)];
+                }
+            }
+        }
+        CUH(h->occ_clause.upload(oc.data(), oc.size(), h->stream));
+        if (h->uniform3) CUH(h->occ_pair.upload(op.data(), op.size(), h->stream));
+        CUH(cudaStreamSynchronize(h->stream));
+    }
     CUH(cudaStreamSynchronize(h->stream));
 #undef CUH
 
@@ -575,6 +690,8 @@ int gpsat_propagate_all(gpsat_t *h, int32_t *status, int32_t *n_implied, int32_t
     }
     int rc = ensure_cubes(h);
     if (rc != GPSAT_OK) return rc;
+    if (h->opts.bcp == GPSAT_BCP_OCCURRENCE)
+        return propagate_all_occurrence(h, status, n_implied, implied, implied_stride, conflict_clause, records);
     rc = plan_geometry(h, GPSAT_MODE_PROPAGATE);
     if (rc != GPSAT_OK) return rc;
     rc = ensure_run_buffers(h, GPSAT_MODE_PROPAGATE);
@@ -750,6 +867,8 @@ int gpsat_request_stop(gpsat_t *h)
     CU(cudaMemcpy(h->ctrl.p + 1, &two, sizeof(two), cudaMemcpyHostToDevice));
     return GPSAT_OK;
 }
+
+double gpsat_last_kernel_ms(gpsat_t *h) { return h ? h->kernel_ms : 0.0; }
 
 int gpsat_job_records(gpsat_t *h, gpsat_job_record *records, int32_t cap)
 {

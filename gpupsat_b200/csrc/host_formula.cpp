@@ -469,10 +469,26 @@ int build_device_formula(int32_t n_vars, int64_t n_clauses, const int64_t *offse
         }
     }
 
-    for (int64_t c = 0; c < n_clauses; c++) {
-        for (int64_t i = offsets[c]; i < offsets[c + 1]; i++) out.vsids0[(size_t)lits[i]]++;
-        if ((c + 1) % 50 == 0)
-            for (auto &s : out.vsids0) s /= 2;
+    // "+1 per occurrence, halve every counter every 50 clauses", with the halvings applied lazily per literal
+    // (c >>= missed epochs): identical integers, O(n_lits) instead of O(n_clauses/50 * n_vars)
+    {
+        std::vector<int32_t> epoch_of((size_t)(2 * (int64_t)n_vars), 0);
+        int32_t epoch = 0;
+        auto settle = [&](size_t x) {
+            const int32_t d = epoch - epoch_of[x];
+            if (d > 0) {
+                out.vsids0[x] = d >= 31 ? 0 : (out.vsids0[x] >> d);
+                epoch_of[x] = epoch;
+            }
+        };
+        for (int64_t c = 0; c < n_clauses; c++) {
+            for (int64_t i = offsets[c]; i < offsets[c + 1]; i++) {
+                settle((size_t)lits[i]);
+                out.vsids0[(size_t)lits[i]]++;
+            }
+            if ((c + 1) % 50 == 0) epoch++;
+        }
+        for (size_t x = 0; x < out.vsids0.size(); x++) settle(x);
     }
     return GPSAT_OK;
 }

@@ -172,3 +172,205 @@ cudaError_t launch_eval_clauses(int32_t n_vars, int32_t n_clauses, const int32_t
 }
 
 }  // namespace gpsat_kernels
+
+// ---------------------------------------------------------------------------------------------------------------
+// gpsat_bcp_sweep_kernel — BCP by clause evaluation over occurrence lists for LARGE clause databases (config 4:
+// n = 1e6, m = 4e6), where neither watch state nor assignments of a job fit in shared memory.
+//   ≙ ConflictAnalyzer::propagate_all_clauses + VariablesStateHandler::clause_status
+//     (ConflictAnalysis/ConflictAnalyzer.cu:173-245, SATSolver/VariablesStateHandler.cu:180-206) made incremental:
+//     only clauses containing a literal that just became false are evaluated.
+// One warp per job (cube).  The job's assignment is a 2-bit-per-variable bitmap in HBM (bit1 = assigned, bit0 =
+// value); its trail is the cube followed by the implied literals, which are written straight into the caller's
+// `implied` block.  Each lane owns one trail literal of the current batch of 32 and walks that literal's occurrence
+// list, so a warp keeps ~32 x (entries + 2 gathers) independent loads in flight; all cube literals are assigned
+// before propagation starts, as the reference does (VariablesStateHandler::set_assumptions, SATSolver.cu:231-246).
+// Unit propagation is confluent: status and, without conflict, the implied SET do not depend on the visiting order.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct SweepArgs {
+    int32_t n_vars, n_clauses, n_cubes;
+    int32_t uniform3;                 // every clause has exactly 3 literals: use the (other, other) pair entries
+    const int32_t *ostart;            // 2n+1
+    const int32_t *occ_clause;        // n_lits : clause index per occurrence slot
+    const int2 *occ_pair;             // n_lits : the two other literals of that clause (uniform3 only)
+    const int32_t *coffsets;          // n_clauses+1 (general path)
+    const int32_t *clits;             // compact literals
+    const int64_t *cube_offsets;
+    const int32_t *cube_lits;
+    uint32_t *valbits;                // n_warps * val_words, zero on entry and on exit
+    int32_t val_words;                // ceil(n/16)
+    int32_t *implied;                 // n_cubes * stride
+    int64_t stride;
+    int32_t *n_implied, *status;
+    int64_t *conflict_clause;
+    int64_t *counters;                // per cube: [0] occurrence entries visited [1] clause literals read
+    int32_t *next_job;
+};
+
+__device__ __forceinline__ int sw_value(const uint32_t *vb, int x)
+{
+    const uint32_t w = vb[x >> 5];                 // var = x>>1, 16 vars per word -> word (x>>1)>>4
+    const uint32_t f = (w >> (((x >> 1) & 15) * 2)) & 3u;
+    return (f & 2u) ? (int)((f & 1u) == (uint32_t)(x & 1)) : 2;   // 1 true, 0 false, 2 unassigned
+}
+
+// assign literal x; returns previous field (0 = was unassigned)
+__device__ __forceinline__ uint32_t sw_assign(uint32_t *vb, int x)
+{
+    const int sh = ((x >> 1) & 15) * 2;
+    const uint32_t prev = atomicOr(vb + (x >> 5), (2u | (uint32_t)(x & 1)) << sh);
+    return (prev >> sh) & 3u;
+}
+
+__global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_kernel(const SweepArgs A)
+{
+    __shared__ int s_count[32];        // implied literals appended so far, per warp
+    __shared__ int s_conflict[32];     // 0 none, 1 conflict seen
+    __shared__ long long s_clause[32];
+    const int lane = (int)(threadIdx.x & 31u), wib = (int)(threadIdx.x >> 5);
+    const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+    uint32_t *vb = A.valbits + (size_t)gwarp * (size_t)A.val_words;
+
+    while (true) {
+        int job = 0;
+        if (lane == 0) job = atomicAdd(A.next_job, 1);
+        job = __shfl_sync(0xffffffffu, job, 0);
+        if (job >= A.n_cubes) break;
+        const long long c0 = A.cube_offsets[job], c1 = A.cube_offsets[job + 1];
+        const int k = (int)(c1 - c0);
+        const int32_t *cube = A.cube_lits + c0;
+        int32_t *imp = A.implied + (long long)job * A.stride;
+        if (lane == 0) {
+            s_count[wib] = 0;
+            s_conflict[wib] = 0;
+            s_clause[wib] = -1;
+        }
+        __syncwarp();
+        // phase 0: the whole cube is assigned up front
+        for (int i = lane; i < k; i += 32) {
+            const int x = cube[i];
+            const uint32_t prev = sw_assign(vb, x);
+            if ((prev & 2u) && (prev & 1u) != (uint32_t)(x & 1)) s_conflict[wib] = 1;   // x and ~x in one cube
+        }
+        __syncwarp();
+        long long visited = 0, words = 0;
+        // phase 1: trail = cube ++ implied; 32 trail literals per batch, one per lane
+        int qhead = 0;
+        while (!s_conflict[wib]) {
+            const int total = k + min(s_count[wib], (int)A.stride);
+            if (qhead >= total) break;
+            const int t = qhead + lane;
+            if (t < total) {
+                const int p = t < k ? cube[t] : imp[t - k];
+                const int f = p ^ 1;
+                const int os = __ldg(A.ostart + f), oe = __ldg(A.ostart + f + 1);
+                for (int e = os; e < oe; ++e) {
+                    int a, b, c = -1, unit = -1, n_false = 0, n_undef = 0;
+                    bool sat = false;
+                    if (A.uniform3) {
+                        const int2 pr = __ldg(A.occ_pair + e);
+                        a = pr.x;
+                        b = pr.y;
+                        const int va = sw_value(vb, a), vb2 = sw_value(vb, b);
+                        sat = (va == 1) || (vb2 == 1);
+                        n_false = (va == 0) + (vb2 == 0);
+                        n_undef = (va == 2) + (vb2 == 2);
+                        unit = (va == 2) ? a : b;
+                        words += 2;
+                    } else {
+                        c = __ldg(A.occ_clause + e);
+                        const int lb = __ldg(A.coffsets + c), le = __ldg(A.coffsets + c + 1);
+                        for (int i = lb; i < le && !sat; ++i) {
+                            const int x = __ldg(A.clits + i);
+                            words++;
+                            if (x == f) continue;
+                            const int v = sw_value(vb, x);
+                            if (v == 1) sat = true;
+                            else if (v == 0) n_false++;
+                            else { n_undef++; unit = x; }
+                        }
+                    }
+                    visited++;
+                    if (sat || n_undef > 1) continue;
+                    if (n_undef == 0) {                               // every other literal false: conflict
+                        if (c < 0) c = __ldg(A.occ_clause + e);
+                        s_conflict[wib] = 1;
+                        s_clause[wib] = c;
+                        break;
+                    }
+                    const uint32_t prev = sw_assign(vb, unit);        // exactly one unassigned literal: imply it
+                    if (prev == 0) {
+                        const int pos = atomicAdd(&s_count[wib], 1);
+                        if (pos < A.stride) imp[pos] = unit;
+                    } else if ((prev & 1u) != (uint32_t)(unit & 1)) {  // lost a race against the opposite literal
+                        if (c < 0) c = __ldg(A.occ_clause + e);
+                        s_conflict[wib] = 1;
+                        s_clause[wib] = c;
+                        break;
+                    }
+                }
+            }
+            __syncwarp();
+            qhead += 32;
+        }
+        __syncwarp();
+        const int n_imp = s_count[wib];
+        const int conflict = s_conflict[wib];
+        // restore the bitmap to all-unassigned for the next job of this warp (only the words we touched)
+        for (int i = lane; i < k; i += 32) atomicAnd(vb + (cube[i] >> 5), ~(3u << (((cube[i] >> 1) & 15) * 2)));
+        const int n_written = min(n_imp, (int)A.stride);
+        for (int i = lane; i < n_written; i += 32) atomicAnd(vb + (imp[i] >> 5), ~(3u << (((imp[i] >> 1) & 15) * 2)));
+        if (n_imp > n_written)   // implied block too small: some assigned variables are not listed, clear everything
+            for (int i = lane; i < A.val_words; i += 32) vb[i] = 0u;
+        __syncwarp();
+        for (int o = 16; o > 0; o >>= 1) {
+            visited += __shfl_xor_sync(0xffffffffu, visited, o);
+            words += __shfl_xor_sync(0xffffffffu, words, o);
+        }
+        if (lane == 0) {
+            // truncated trail (implied block too small) without a conflict: no verdict for this cube
+            A.status[job] = conflict ? GPSAT_UNSAT : (n_imp > n_written ? GPSAT_JOB_OOM : GPSAT_UNDEF);
+            A.n_implied[job] = n_imp;
+            A.conflict_clause[job] = conflict ? s_clause[wib] : -1;
+            if (A.counters) {
+                A.counters[2 * job] = visited;
+                A.counters[2 * job + 1] = words;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+namespace gpsat_kernels {
+
+cudaError_t launch_bcp_sweep(const SweepLaunch &L, cudaStream_t stream)
+{
+    SweepArgs A;
+    A.n_vars = L.n_vars;
+    A.n_clauses = L.n_clauses;
+    A.n_cubes = L.n_cubes;
+    A.uniform3 = L.uniform3;
+    A.ostart = L.ostart;
+    A.occ_clause = L.occ_clause;
+    A.occ_pair = (const int2 *)L.occ_pair;
+    A.coffsets = L.coffsets;
+    A.clits = L.clits;
+    A.cube_offsets = L.cube_offsets;
+    A.cube_lits = L.cube_lits;
+    A.valbits = L.valbits;
+    A.val_words = L.val_words;
+    A.implied = L.implied;
+    A.stride = L.stride;
+    A.n_implied = L.n_implied;
+    A.status = L.status;
+    A.conflict_clause = L.conflict_clause;
+    A.counters = L.counters;
+    A.next_job = L.next_job;
+    gpsat_bcp_sweep_kernel<<<L.blocks, L.warps_per_block * 32, 0, stream>>>(A);
+    return cudaGetLastError();
+}
+
+}  // namespace gpsat_kernels

@@ -24,4 +24,22 @@ cudaError_t launch_eval_clauses(int32_t n_vars, int32_t n_clauses, const int32_t
                                 int32_t n_assignments, const uint8_t *assignment, int32_t *status, int32_t *unit,
                                 cudaStream_t stream);
 
+// BCP by clause evaluation over occurrence lists for large clause databases (warp per job, state in HBM)
+struct SweepLaunch {
+    int32_t n_vars, n_clauses, n_cubes, uniform3;
+    const int32_t *ostart, *occ_clause, *occ_pair, *coffsets, *clits;
+    const int64_t *cube_offsets;
+    const int32_t *cube_lits;
+    uint32_t *valbits;
+    int32_t val_words;
+    int32_t *implied;
+    int64_t stride;
+    int32_t *n_implied, *status;
+    int64_t *conflict_clause;
+    int64_t *counters;
+    int32_t *next_job;
+    int blocks, warps_per_block;
+};
+cudaError_t launch_bcp_sweep(const SweepLaunch &L, cudaStream_t stream);
+
 }  // namespace gpsat_kernels

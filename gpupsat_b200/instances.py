@@ -153,3 +153,43 @@ def check_model(offsets, lits, model) -> bool:
     if (lens == 0).any():
         return False
     return bool((sat > 0).all())
+
+
+def planted_3sat_large(n: int, m: int, seed: int):
+    """random_3sat_large with a planted solution: the hidden assignment is drawn from the same stream and every
+    clause it would falsify (1 in 8) gets one sign flipped, so the formula is satisfiable and any subset of the
+    planted assignment propagates without conflict (config 4: an under-constrained instance whose BCP throughput
+    can be swept with trails of any length).  Returns (offsets, lits, planted[n] in {0,1})."""
+    offsets, lits = random_3sat_large(n, m, seed)
+    planted = (_splitmix_vec(seed ^ 0x5EED5EED, n) & np.uint64(1)).astype(np.int32)
+    l3 = lits.reshape(m, 3)
+    true3 = planted[l3 >> 1] == (l3 & 1)
+    dead = ~true3.any(axis=1)
+    which = (_splitmix_vec(seed ^ 0xF11BF11B, m) % np.uint64(3)).astype(np.int64)
+    rows = np.nonzero(dead)[0]
+    l3[rows, which[rows]] ^= 1
+    return offsets, l3.reshape(-1).astype(np.int32), planted
+
+
+def sweep_trails(n: int, n_jobs: int, length: int, seed: int, planted=None):
+    """Trails for the large-database BCP sweep (config 4): job j assigns `length` literals over DISTINCT variables,
+    v_i = (a_j * i + b_j) mod n with a_j coprime to n (an affine permutation seeded by splitmix64(seed ^ j)); signs
+    follow `planted` when given (conflict-free trails), else come from the same stream.
+    Returns CSR (offsets int64[n_jobs+1], lits int32[n_jobs*length])."""
+    import math
+    lits = np.empty((n_jobs, length), dtype=np.int32)
+    i = np.arange(length, dtype=np.int64)
+    for j in range(n_jobs):
+        rng = SplitMix64(seed ^ (j * 0x9E3779B1 + 1))
+        a = int(rng.next() % n) | 1
+        while math.gcd(a, n) != 1:
+            a = (a + 2) % n
+        b = int(rng.next() % n)
+        v = (a * i + b) % n
+        if planted is not None:
+            sg = planted[v].astype(np.int64)
+        else:
+            sg = (_splitmix_vec(rng.next(), length) & np.uint64(1)).astype(np.int64)
+        lits[j] = (2 * v + sg).astype(np.int32)
+    offsets = np.arange(0, n_jobs * length + 1, length, dtype=np.int64)
+    return offsets, lits.reshape(-1)

@@ -183,6 +183,9 @@ int gpsat_eval_clauses(gpsat_t *h, int32_t n_assignments, const uint8_t *assignm
  * refuted, GPSAT_UNDEF if a cap (max_iterations / max_conflicts) stopped some job and none was SAT. */
 int gpsat_solve(gpsat_t *h, int32_t *verdict, uint8_t *model, gpsat_stats *stats);
 
+/* CUDA-event time (ms) of the kernels of the last gpsat_solve / gpsat_propagate_all on this handle */
+double gpsat_last_kernel_ms(gpsat_t *h);
+
 /* per-job records of the last gpsat_solve / gpsat_propagate_all (n_cubes entries) */
 int gpsat_job_records(gpsat_t *h, gpsat_job_record *records, int32_t cap);
 

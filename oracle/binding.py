@@ -99,7 +99,7 @@ class Oracle:
         sat_job = C.c_int32(-1)
         stride = self.n_vars if implied_stride is None else implied_stride
         implied = n_implied = confl = None
-        if mode == 1:
+        if mode != 0:
             implied = np.full(max(n_cubes * stride, 1), -1, dtype=np.int32)
             n_implied = np.zeros(n_cubes, dtype=np.int32)
             confl = np.full(n_cubes, -1, dtype=np.int64)
@@ -107,7 +107,7 @@ class Oracle:
                             _p(cl), _p(rec), _p(model), C.byref(sat_job), 1 if stop_on_sat else 0, _p(implied), stride,
                             _p(n_implied), _p(confl))
         out = {"records": rec, "sat_job": sat_job.value, "model": model[: self.n_vars]}
-        if mode == 1:
+        if mode != 0:
             out.update(implied=implied.reshape(n_cubes, stride) if stride else implied, n_implied=n_implied,
                        conflict_clause=confl)
         return out

@@ -36,7 +36,7 @@ namespace {
 enum { SAT = 0, UNSAT = 1, UNDEF = 2 };
 enum { V_FALSE = 0, V_TRUE = 1, V_UNDEF = 2, V_ABSENT = 4 };
 enum { DECIDE_REFERENCE = 0, DECIDE_VSIDS = 1 };
-enum { MODE_SOLVE = 0, MODE_PROPAGATE = 1 };
+enum { MODE_SOLVE = 0, MODE_PROPAGATE = 1, MODE_PROPAGATE_BATCH = 2 };
 const int JOB_OOM = -3;
 
 struct Params {
@@ -398,6 +398,19 @@ struct Oracle {
         const int NOC = INT32_MIN;
         conflict_out = NOC;
         reset_job();
+        if (P.mode == MODE_PROPAGATE_BATCH) {
+            /* the reference's own order: the whole cube is assigned first (VariablesStateHandler::set_assumptions,
+             * SATSolver.cu:231-246), then BCP runs to fixpoint or first conflict */
+            new_level();
+            for (int i = 0; i < k; i++) {
+                const int v = lit_value(cube[i]);
+                if (v == 0) return UNSAT;
+                if (v == 2) enqueue(cube[i], -1);
+            }
+            const int confl = propagate();
+            if (confl != NOC) { conflict_out = confl; R.conflicts++; return UNSAT; }
+            return UNDEF;
+        }
         while (true) {
             const int confl = propagate();
             if (oom) return JOB_OOM;
@@ -475,16 +488,34 @@ void *oracle_open(int32_t n_vars, int64_t n_clauses, const int64_t *offsets, con
     o->occ.assign((size_t)2 * n_vars, std::vector<Occ>());
     o->val0.assign((size_t)n_vars, V_ABSENT);
     o->vsids0.assign((size_t)2 * n_vars, 0);
+    /* VSIDS::handle_clause over the formula (DecisionMaker.cu:3-16) with VSIDS::decay every 50 clauses (VSIDS.cu:84-89).
+     * Small formulas: literally that.  Large ones: each counter is halved lazily for the decays it missed, which
+     * yields the same integers (repeated floor-halving == right shift). */
+    const bool literal_decay = n_clauses <= 20000;
+    std::vector<int32_t> seen_epoch((size_t)2 * n_vars, 0);
+    int32_t epoch = 0;
     for (int c = 0; c < (int)n_clauses; c++) {
         for (int64_t i = o->off[c]; i < o->off[c + 1]; i++) {
             const int x = o->lits[i];
             o->occ[x].push_back(Occ{c, (int32_t)(i - o->off[c])});
             o->val0[x >> 1] = V_UNDEF;
-            o->vsids0[x]++;                                  /* VSIDS::handle_clause over the formula, DecisionMaker.cu:3-16 */
+            if (!literal_decay && epoch > seen_epoch[x]) {
+                const int d = epoch - seen_epoch[x];
+                o->vsids0[x] = d >= 31 ? 0 : (o->vsids0[x] >> d);
+                seen_epoch[x] = epoch;
+            }
+            o->vsids0[x]++;
         }
-        if ((c + 1) % 50 == 0)
-            for (auto &s : o->vsids0) s /= 2;               /* VSIDS::decay every 50 clauses, VSIDS.cu:84-89 */
+        if ((c + 1) % 50 == 0) {
+            if (literal_decay) for (auto &s : o->vsids0) s /= 2;
+            else epoch++;
+        }
     }
+    if (!literal_decay)
+        for (size_t x = 0; x < o->vsids0.size(); x++) {
+            const int d = epoch - seen_epoch[x];
+            if (d > 0) o->vsids0[x] = d >= 31 ? 0 : (o->vsids0[x] >> d);
+        }
     return o;
 }
 void oracle_close(void *h) { delete (Oracle *)h; }
@@ -517,7 +548,7 @@ int oracle_run(void *h, const int32_t *iparams, float restart_factor, int64_t ma
         const int st = o->run_job(cube, k, confl);
         o->R.status = st;
         rec[j] = o->R;
-        if (o->P.mode == MODE_PROPAGATE) {
+        if (o->P.mode != MODE_SOLVE) {
             if (conflict_clause) conflict_clause[j] = (st == UNSAT && confl != INT32_MIN && confl >= 0) ? confl : -1;
             std::vector<uint8_t> in_cube((size_t)o->n_vars, 0);
             for (int i = 0; i < k; i++) in_cube[cube[i] >> 1] = 1;

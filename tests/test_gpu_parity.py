@@ -126,3 +126,72 @@ def test_dynamic_split_same_verdicts():
         assert stats["jobs_done"] == len(cubes)
         if verdict == g.SAT:
             assert check_model(pre.offsets, pre.lits, model)
+
+
+def test_occurrence_bcp_small_with_conflicts():
+    """GPSAT_BCP_OCCURRENCE (clause evaluation over occurrence lists, whole cube assigned first): status and implied
+    SETS equal the oracle's batch propagation; a reported conflict clause is falsified under cube + implied."""
+    from gpupsat_b200.instances import sweep_trails
+    offs, lits = random_ksat(250, 1065, 7)
+    cnf, pre = _prep(offs, lits)
+    cubes = pre.choose_cubes(8, 32)
+    co = np.arange(0, cubes.size + 1, 12, dtype=np.int64)
+    with g.Solver(cnf.n_vars, pre.offsets, pre.lits, bcp=g.binding.BCP_OCCURRENCE) as s:
+        s.set_cubes(cubes)
+        got = s.propagate_all()
+    want = Oracle(cnf.n_vars, pre.offsets, pre.lits).run(co, cubes.reshape(-1), mode=2)
+    assert np.array_equal(got["status"], want["records"]["status"])
+    for j in range(len(cubes)):
+        mine = set(got["implied"][j, : got["n_implied"][j]].tolist())
+        if got["status"][j] == g.UNDEF:
+            assert mine == set(want["implied"][j, : want["n_implied"][j]].tolist())
+        else:
+            c = got["conflict_clause"][j]
+            assert c >= 0
+            trail = set(cubes[j].tolist()) | mine
+            assert all((x ^ 1) in trail for x in pre.lits[pre.offsets[c]: pre.offsets[c + 1]])
+
+
+def test_occurrence_bcp_mixed_clause_lengths():
+    rng = np.random.default_rng(11)
+    n = 400
+    cl = []
+    for _ in range(1500):
+        ln = int(rng.choice([2, 3, 3, 4, 7]))
+        vs = rng.choice(n, size=ln, replace=False)
+        cl.append([int(2 * v + rng.integers(0, 2)) for v in vs])
+    offs = np.cumsum([0] + [len(c) for c in cl]).astype(np.int64)
+    lits = np.array([x for c in cl for x in c], dtype=np.int32)
+    cubes = rng.integers(0, 2, size=(64, 10)).astype(np.int32) + 2 * rng.permuted(np.tile(np.arange(n), (64, 1)), axis=1)[:, :10].astype(np.int32)
+    co = np.arange(0, cubes.size + 1, 10, dtype=np.int64)
+    with g.Solver(n, offs, lits, bcp=g.binding.BCP_OCCURRENCE) as s:
+        s.set_cubes(cubes)
+        got = s.propagate_all()
+    want = Oracle(n, offs, lits).run(co, cubes.reshape(-1), mode=2)
+    assert np.array_equal(got["status"], want["records"]["status"])
+    for j in np.nonzero(got["status"] == g.UNDEF)[0]:
+        assert set(got["implied"][j, : got["n_implied"][j]].tolist()) == set(want["implied"][j, : want["n_implied"][j]].tolist())
+
+
+def test_config4_large_database_sample():
+    """config 4 at full size: n = 1e6, m = 4e6 planted 3-SAT, 32 jobs x 100k-literal trails; sample of jobs against
+    the oracle (implied sets), all jobs conflict-free, implied literals agree with the planted assignment."""
+    from gpupsat_b200.instances import planted_3sat_large, sweep_trails
+    n, m, L, J = 1_000_000, 4_000_000, 100_000, 32
+    offs, lits, planted = planted_3sat_large(n, m, 4)
+    co, cl = sweep_trails(n, J, L, 4, planted)
+    stride = 200_000
+    with g.Solver(n, offs, lits, bcp=g.binding.BCP_OCCURRENCE) as s:
+        s.set_cubes(cube_offsets=co, cube_lits=cl)
+        got = s.propagate_all(implied_stride=stride)
+    assert (got["status"] == g.UNDEF).all()
+    assert (got["n_implied"] > 1000).all() and (got["n_implied"] < stride).all()
+    for j in range(J):
+        imp = got["implied"][j, : got["n_implied"][j]]
+        assert np.array_equal(planted[imp >> 1], imp & 1)
+        assert len(np.unique(imp >> 1)) == len(imp)
+    o = Oracle(n, offs, lits)
+    for j in (0, 17):
+        want = o.run(co[j: j + 2] - co[j], cl[co[j]: co[j + 1]], mode=2, implied_stride=stride)
+        assert want["records"]["status"][0] == g.UNDEF
+        assert set(got["implied"][j, : got["n_implied"][j]].tolist()) == set(want["implied"][0, : want["n_implied"][0]].tolist())
