@@ -173,18 +173,18 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(walls),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": workload_config(args.gpus, cubes), "cpu_baseline": base,
+            "config": workload_config(args.gpus, cubes, 1 if args.gpus > 1 else 0), "cpu_baseline": base,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus, cubes):
+def workload_config(n_gpus, cubes, share=0):
     return {"workload": f"uniform random 3-SAT n={N_VARS} m={N_CLAUSES} r=4.26 splitmix64 seed {SEED} (UNSAT), "
                         f"{len(cubes)} JobChooser cubes of {cubes.shape[1]} literals "
                         f"({len(cubes) // n_gpus} per GPU), full CDCL solve of every cube",
             "cubes": int(len(cubes)), "cube_literals": int(cubes.shape[1]), "parallelism": f"cubes x{n_gpus}",
-            "l2": "flushed between timed steps (256 MiB write)", "decision": "vsids", "share_learnts": 0}
+            "l2": "flushed between timed steps (256 MiB write)", "decision": "vsids", "share_learnts": share}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -208,7 +208,6 @@ def run_ours(args):
     mine = cubes[rank::n_gpus]
     offs, lits = pre.offsets, pre.lits
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    flag = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def barrier():
         torch.cuda.synchronize()
@@ -221,29 +220,30 @@ def run_ours(args):
         extra["warps_per_block"] = int(os.environ["GPSAT_WARPS_PER_BLOCK"])
     if os.environ.get("GPSAT_DYNAMIC_SPLIT"):
         extra["dynamic_split"] = int(os.environ["GPSAT_DYNAMIC_SPLIT"])
-    if os.environ.get("GPSAT_SHARE_LEARNTS"):
-        extra["share_learnts"] = int(os.environ["GPSAT_SHARE_LEARNTS"])
+    for env_name, opt in (("GPSAT_SHARE_LEARNTS", "share_learnts"), ("GPSAT_SPLIT_GAP", "split_gap"),
+                          ("GPSAT_SPLIT_BURST", "split_burst")):
+        if os.environ.get(env_name):
+            extra[opt] = int(os.environ[env_name])
+    if n_gpus > 1:
+        extra.setdefault("share_learnts", 1)        # short learnt clauses ride the per-epoch all-gather
     solver = g.Solver(cnf.n_vars, offs, lits, device=local_rank, **extra)
     solver.set_cubes(mine)
+
+    xinfo = {"epochs": 0, "imported_clauses": 0, "exchange_bytes_per_epoch": 0}
 
     def one_solve():
         """device-resident step; returns (kernel_ms, stats, verdict)"""
         if dist is None:
             verdict, model, st = solver.solve()
             return st["kernel_ms"], st, verdict
-        solver.solve_begin()
-        while True:
-            done, verdict = solver.solve_step(budget_ms=20.0)
-            flag.fill_(1 if verdict == g.SAT else 0)
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX)          # early-termination flag over NVLink
-            if int(flag.item()) == 1 and verdict != g.SAT:
-                solver.request_stop()
-                done = True
-            fin = torch.tensor([1 if done else 0], dtype=torch.int32, device=dev)
-            dist.all_reduce(fin, op=dist.ReduceOp.MIN)
-            if int(fin.item()) == 1:
-                break
-        verdict, model, st = solver.solve_end()
+        # N > 1: epoch loop of gpupsat_b200.multi_gpu — budgeted persistent-kernel steps, ONE NCCL all-gather per epoch
+        # carrying the early-termination flag, the done flags and the short learnt clauses of every rank
+        from gpupsat_b200 import multi_gpu as mg
+        verdict, model, st, info = mg.solve_sharded(solver, dist, rank, n_gpus, dev, budget_ms=args.epoch_ms,
+                                                    max_clauses_per_epoch=1024)
+        for k2 in ("epochs", "imported_clauses"):
+            xinfo[k2] += info[k2]
+        xinfo["exchange_bytes_per_epoch"] = info["exchange_bytes_per_epoch"]
         return st["kernel_ms"], st, verdict
 
     kernel_ms, stats_acc, launches = [], None, 0
@@ -259,7 +259,8 @@ def run_ours(args):
             kernel_ms.append(ms)
             launches += 2 * st["kernel_launches"]                # stamp kernel + solve kernel per launch
             summed = ("jobs_done", "decisions", "implications", "conflicts", "learnt_clauses", "learnt_literals",
-                      "restarts", "watchers_visited", "clause_words_read", "kernel_launches")
+                      "restarts", "watchers_visited", "clause_words_read", "kernel_launches", "splits",
+                      "warp_busy_frac")
             stats_acc = dict(st) if stats_acc is None else {k: (stats_acc[k] + st[k]) if k in summed else st[k] for k in st}
             flush.fill_(i & 0xFF)                                 # L2 flush between timed steps (outside the event time)
         barrier()
@@ -316,7 +317,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": imp_all / (tot_ms_max * 1e-3), "unit": UNIT, "n_gpus": n_gpus, "steps": steps,
             "warmup": args.warmup, "ms_per_step": tot_ms_max / steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": workload_config(n_gpus, cubes),
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": workload_config(n_gpus, cubes, extra.get("share_learnts", 0)),
             "time_to_solve_ms": tot_ms_max / steps, "verdict": {0: "SAT", 1: "UNSAT", 2: "UNDEF"}[verdict],
             "solved_jobs_per_sec": jobs_all / (tot_ms_max * 1e-3), "conflicts_per_sec": confl_all / (tot_ms_max * 1e-3),
             "implications_per_step": imp_all / steps, "wall_ms_timed_region": wall_ms,
@@ -329,10 +330,17 @@ def run_ours(args):
                          "note": "13 KB clause database lives in L1/L2: this kernel is latency/issue bound, the HBM "
                                  "fraction is reported because the metric asks for it (DESIGN.md)"},
             "cpu_baseline": cpu_base,
+            "multi_gpu": None if dist is None else {
+                "collective": "one NCCL all-gather per epoch (flag + done + short learnt clauses)",
+                "epoch_ms": args.epoch_ms, "epochs_per_step": xinfo["epochs"] / max(steps + args.warmup, 1),
+                "exchange_bytes_per_epoch": xinfo["exchange_bytes_per_epoch"],
+                "clauses_imported_rank0_per_step": xinfo["imported_clauses"] / max(steps + args.warmup, 1)},
             "clocks": clocks.summary(),
             "launch": {"blocks": stats_acc["blocks"], "warps_per_block": stats_acc["warps_per_block"],
                        "smem_bytes_per_block": stats_acc["smem_bytes_per_block"],
-                       "state_in_smem": stats_acc["state_in_smem"]},
+                       "state_in_smem": stats_acc["state_in_smem"],
+                       "splits_per_step": stats_acc["splits"] / steps,
+                       "warp_busy_frac": stats_acc["warp_busy_frac"] / steps},
         }
         print(json.dumps(line), flush=True)
     solver.close()
@@ -347,6 +355,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--epoch-ms", type=float, default=20.0, help="N > 1: kernel budget per exchange epoch")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

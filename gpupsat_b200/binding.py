@@ -27,7 +27,8 @@ class GpsatOpts(C.Structure):
                 ("restart_first", C.c_int32), ("restart_factor", C.c_float), ("max_iterations", C.c_int32),
                 ("stop_on_sat", C.c_int32), ("max_conflicts", C.c_int64), ("share_learnts", C.c_int32),
                 ("share_max_len", C.c_int32), ("warps_per_block", C.c_int32), ("blocks", C.c_int32),
-                ("arena_words", C.c_int64), ("dynamic_split", C.c_int32), ("reserved", C.c_int32 * 7)]
+                ("arena_words", C.c_int64), ("dynamic_split", C.c_int32), ("split_gap", C.c_int32),
+                ("split_burst", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class GpsatStats(C.Structure):
@@ -37,7 +38,8 @@ class GpsatStats(C.Structure):
                  "clause_words_read", "pool_clauses")] + \
                [("kernel_ms", C.c_double), ("kernel_launches", C.c_int32), ("blocks", C.c_int32),
                 ("warps_per_block", C.c_int32), ("smem_bytes_per_block", C.c_int32), ("state_in_smem", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32), ("splits", C.c_int64), ("warp_busy_frac", C.c_double),
+                ("foreign_clauses", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
@@ -92,6 +94,11 @@ def lib():
     L.gpsat_request_stop.argtypes = [vp]
     L.gpsat_pool_export.argtypes = [vp, vp, i64, C.POINTER(i64)]
     L.gpsat_pool_import.argtypes = [vp, vp, i64]
+    L.gpsat_exchange_block_words.argtypes = [i32]
+    L.gpsat_exchange_block_words.restype = i64
+    L.gpsat_exchange_pack.argtypes = [vp, vp, i64, i32, i32, i32]
+    L.gpsat_exchange_unpack.argtypes = [vp, vp, i32, i32, i64, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32),
+                                        C.POINTER(i64), C.POINTER(i64)]
     L.gpsat_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     _lib = L
     return L
@@ -306,6 +313,19 @@ class Solver:
     def pool_import(self, words):
         words = np.ascontiguousarray(words, dtype=np.int32)
         _check(lib().gpsat_pool_import(self.h, _p(words), len(words)))
+
+    # --- device-side epoch exchange: `block` / `gathered` are DEVICE buffers (anything with .data_ptr(), e.g. torch) ---
+    def exchange_pack(self, block, rank, done, verdict):
+        _check(lib().gpsat_exchange_pack(self.h, C.c_void_p(block.data_ptr()), block.numel(), rank, int(done), verdict))
+
+    def exchange_unpack(self, gathered, n_ranks, rank):
+        sat, done, undef = C.c_int32(-1), C.c_int32(0), C.c_int32(0)
+        imported, jobs = C.c_int64(0), C.c_int64(0)
+        _check(lib().gpsat_exchange_unpack(self.h, C.c_void_p(gathered.data_ptr()), n_ranks, rank,
+                                           gathered.numel() // n_ranks, C.byref(sat), C.byref(done), C.byref(undef),
+                                           C.byref(imported), C.byref(jobs)))
+        return {"sat_rank": sat.value, "all_done": bool(done.value), "any_undef": bool(undef.value),
+                "imported_clauses": imported.value, "jobs_done": jobs.value}
 
 
 def solve_cnf(cnf: Cnf, blocks=32, threads=32, strategy=STRATEGY_DISTRIBUTED, sequential=False, **opts):

@@ -64,14 +64,19 @@ struct WarpSolver {
     float restart_factor;
     long long max_conflicts;
     // dynamic splitting
-    int dynamic_split, split_force, root;
+    int dynamic_split, split_force, split_gap, split_burst, root;
     int *dq_lits, *dq_meta, *dq_ctrl, *root_pending, *dq_hand;
-    int hand_words;
+    int hand_words, dq_cap;
+    int rel_slot, rel_seq;                 // queue slot this job was popped from (released once its content is consumed)
+    const unsigned long long *t0;          // budgeted steps: jobs park themselves once now > *t0 + budget_ns
+    unsigned long long budget_ns;
     long long c_splits;
     // shared pool
-    int *pool;
-    int *pool_cursor;
+    int *pool;            // this GPU's pool: fixed slots of GPSAT_POOL_SLOT_WORDS words, [len, lit0 ...], len written last
+    int *pool_cursor;     // [0] slots reserved [1] clauses published [2] export mark (host / exchange kernels)
     int pool_cap_words;
+    const int *xpool;     // clauses received from the other GPUs (same slot format, filled between launches)
+    const int *xpool_cursor;
     // counters (uniform) + per-lane counters
     long long c_decisions, c_implications, c_conflicts, c_learnt_clauses, c_learnt_literals, c_restarts;
     unsigned long long c_hash;
@@ -511,16 +516,17 @@ struct WarpSolver {
         }
     }
 
-    // append a short learnt clause to the per-GPU pool (atomics on the cursor; header written last)
+    // append a short learnt clause to the per-GPU pool: one atomic on the slot cursor, length written last
     GPSAT_DEV void pool_publish(int n_out)
     {
         GPSAT_LANE_DECL
-        if (!share_learnts || n_out > share_max_len || pool == nullptr) return;
+        if (!share_learnts || n_out > share_max_len || n_out >= GPSAT_POOL_SLOT_WORDS || pool == nullptr) return;
         LANEVAR(int, off);
         LANES { LV(off) = 0; }
-        LANE0 { LV(off) = gpsat_atomic_add(pool_cursor, n_out + 1); }
-        const int at = SHFL(off, 0);
-        if (at + n_out + 1 > pool_cap_words) return;   // pool full: clause stays private
+        LANE0 { LV(off) = gpsat_atomic_add(pool_cursor, 1); }
+        const int slot = SHFL(off, 0);
+        if (slot >= pool_cap_words / GPSAT_POOL_SLOT_WORDS) return;   // pool full: clause stays private
+        const int at = slot * GPSAT_POOL_SLOT_WORDS;
         LANES
         {
             for (int i = lane; i < n_out; i += 32) pool[at + 1 + i] = lbuf[i];
@@ -529,7 +535,7 @@ struct WarpSolver {
         gpsat_threadfence();
         LANE0
         {
-            pool[at] = n_out;
+            ((volatile int *)pool)[at] = n_out;
             gpsat_atomic_add(pool_cursor + 1, 1);
         }
         SYNCWARP();
@@ -776,32 +782,44 @@ struct WarpSolver {
     // refute the formula).  Only records whose header is already published are read.
     GPSAT_DEV int pool_import()
     {
-        if (!share_learnts || pool == nullptr) return GPSAT_UNDEF;
-        int used = gpsat_ld_volatile(pool_cursor);
-        if (used > pool_cap_words) used = pool_cap_words;
-        return import_records(pool, used);
+        if (!share_learnts) return GPSAT_UNDEF;
+        const int cap_slots = pool_cap_words / GPSAT_POOL_SLOT_WORDS;
+        if (pool != nullptr) {
+            int used = gpsat_ld_volatile(pool_cursor);
+            if (used > cap_slots) used = cap_slots;
+            const int st = import_records(pool, used * GPSAT_POOL_SLOT_WORDS, GPSAT_POOL_SLOT_WORDS);
+            if (st != GPSAT_UNDEF) return st;
+        }
+        if (xpool != nullptr) {
+            int used = gpsat_ld_volatile(xpool_cursor);
+            if (used > cap_slots) used = cap_slots;
+            const int st = import_records(xpool, used * GPSAT_POOL_SLOT_WORDS, GPSAT_POOL_SLOT_WORDS);
+            if (st != GPSAT_UNDEF) return st;
+        }
+        return GPSAT_UNDEF;
     }
 
-    // records = [len, lit0 .. lit(len-1)] back to back in pool[0..used)
-    GPSAT_DEV int import_records(const int *pool, int used)
+    // records = [len, lit0 .. lit(len-1)]: packed back to back (stride 0: hand-off blocks) or one per fixed slot of
+    // `stride` words (the pools; a slot whose length is still 0 is being written by another warp and is skipped)
+    GPSAT_DEV int import_records(const int *pool, int used, int stride)
     {
         GPSAT_LANE_DECL
         int at = 0;
         while (at < used) {
             const int len = gpsat_ld_volatile(pool + at);
-            if (len <= 0 || at + 1 + len > used) break;
+            if (stride == 0 && (len <= 0 || at + 1 + len > used)) break;
             if (len == 1) {
                 const int u = pool[at + 1];
                 const int v = lit_value(u);
                 if (v == 0) return GPSAT_UNSAT;
                 if (v == 2) enqueue(u, GPSAT_REASON_NONE);
             }
-            at += len + 1;
+            at += stride ? stride : len + 1;
         }
         const int end_at = at;
         if (propagate() != GPSAT_NO_CONFLICT) return GPSAT_UNSAT;
         for (at = 0; at < end_at;) {
-            const int len = pool[at];
+            const int len = gpsat_ld_volatile(pool + at);
             if (len >= 2 && len <= 32 && len <= lbuf_words) {
                 if ((watch_bot - arena_top) < (arena_words - clause_base) / 2) break;   // keep room for own clauses
                 LANEVAR(int, x);
@@ -834,7 +852,7 @@ struct WarpSolver {
                     }
                 }
             }
-            at += len + 1;
+            at += stride ? stride : len + 1;
         }
         if (propagate() != GPSAT_NO_CONFLICT) return GPSAT_UNSAT;
         return GPSAT_UNDEF;
@@ -888,59 +906,124 @@ struct WarpSolver {
         SYNCWARP();
     }
 
-    // Hand half of the remaining search space to another warp: queue cube + ~p, keep cube + p.
-    // Called at a restart, with exactly the k cube literals decided and propagated.  Returns the new k.
-    GPSAT_DEV int try_split(int k)
+    // ---- dynamic queue: a bounded multi-producer multi-consumer ring (per-slot sequence numbers, dq_meta[4*slot+2]).
+    // dq_ctrl: [0] tail (push tickets) [1] head (pop tickets) [2] outstanding jobs [3] idle warps [4] splits in flight.
+    // demand = idle warps - queued children - splits in flight: how many more children would find a taker right now.
+    GPSAT_DEV int demand_hint() const
+    {
+        return gpsat_ld_volatile(dq_ctrl + 3) - (gpsat_ld_volatile(dq_ctrl + 0) - gpsat_ld_volatile(dq_ctrl + 1)) -
+               gpsat_ld_volatile(dq_ctrl + 4);
+    }
+
+    // reserves a slot for writing; returns it (ticket in `ticket`) or -1 when the ring is full
+    GPSAT_DEV int dq_acquire(int &ticket)
     {
         GPSAT_LANE_DECL
-        if (k + 1 >= GPSAT_DQ_MAXK) return k;
-        // dq_ctrl[3] = demand = idle warps - queued children - splits in flight; claim one unit of it
-        LANEVAR(int, claim_v);
-        LANES { LV(claim_v) = 0; }
+        LANEVAR(int, slot_v);
+        LANEVAR(int, pos_v);
+        LANES
+        {
+            LV(slot_v) = -1;
+            LV(pos_v) = 0;
+        }
         LANE0
         {
-            int ok = split_force;
-            if (!ok && gpsat_ld_volatile(dq_ctrl + 3) > 0) {
-                if (gpsat_atomic_add(dq_ctrl + 3, -1) > 0) ok = 1;
-                else gpsat_atomic_add(dq_ctrl + 3, 1);
+            int pos = gpsat_ld_volatile(dq_ctrl + 0);
+            for (int tries = 0; tries < 64; ++tries) {
+                const int slot = pos & (dq_cap - 1);
+                const int dif = gpsat_ld_volatile(dq_meta + 4 * slot + 2) - pos;
+                if (dif == 0) {
+                    const int old = gpsat_atomic_cas(dq_ctrl + 0, pos, pos + 1);
+                    if (old == pos) {
+                        LV(slot_v) = slot;
+                        LV(pos_v) = pos;
+                        break;
+                    }
+                    pos = old;
+                } else if (dif < 0) {
+                    break;   // full
+                } else {
+                    pos = gpsat_ld_volatile(dq_ctrl + 0);
+                }
             }
-            LV(claim_v) = ok;
         }
-        if (!SHFL(claim_v, 0)) return k;
-        const int p = pick_branch();
-        LANEVAR(int, slot_v);
-        LANES { LV(slot_v) = GPSAT_DQ_CAP; }
-        if (p >= 0) {
-            LANE0 { LV(slot_v) = gpsat_atomic_add(dq_ctrl + 0, 1); }
-        }
-        const int slot = SHFL(slot_v, 0);
-        if (slot >= GPSAT_DQ_CAP) {   // nothing to branch on, or the queue is full: give the claim back
-            LANE0
-            {
-                if (p >= 0) gpsat_atomic_add(dq_ctrl + 0, -1);
-                if (!split_force) gpsat_atomic_add(dq_ctrl + 3, 1);
-            }
-            return k;
-        }
+        ticket = SHFL(pos_v, 0);
+        return SHFL(slot_v, 0);
+    }
+
+    // writes cube[0..k) (+ extra literal when >= 0) and the hand-off block into `slot` and publishes it
+    GPSAT_DEV void dq_fill_and_publish(int slot, int ticket, int k, int extra)
+    {
+        GPSAT_LANE_DECL
         LANES
         {
             for (int i = lane; i < k; i += 32) dq_lits[(long long)slot * GPSAT_DQ_MAXK + i] = cube_buf[i];
         }
         LANE0
         {
-            dq_lits[(long long)slot * GPSAT_DQ_MAXK + k] = p ^ 1;
-            dq_meta[2 * slot] = root;
+            if (extra >= 0) dq_lits[(long long)slot * GPSAT_DQ_MAXK + k] = extra;
+            dq_meta[4 * slot] = root;
+            dq_meta[4 * slot + 1] = extra >= 0 ? k + 1 : k;
             gpsat_atomic_add(root_pending + root, 1);
             gpsat_atomic_add(dq_ctrl + 2, 1);
-            cube_buf[k] = p;
         }
         SYNCWARP();
         write_handoff(slot);
         gpsat_threadfence();
-        LANE0 { ((volatile int *)dq_meta)[2 * slot + 1] = k + 1; }   // publish
+        LANE0 { ((volatile int *)dq_meta)[4 * slot + 2] = ticket + 1; }   // publish
         SYNCWARP();
+    }
+
+    // a job popped from the ring frees its slot as soon as it has copied the cube and imported the hand-off
+    GPSAT_DEV void release_slot()
+    {
+        GPSAT_LANE_DECL
+        if (rel_slot < 0) return;
+        gpsat_threadfence();
+        LANE0 { ((volatile int *)dq_meta)[4 * rel_slot + 2] = rel_seq; }
+        SYNCWARP();
+        rel_slot = -1;
+    }
+
+    // Hand half of the remaining search space to another warp: queue cube + ~p, keep cube + p.
+    // Called with exactly the k cube literals decided and propagated.  Returns the new k.
+    GPSAT_DEV int try_split(int k)
+    {
+        GPSAT_LANE_DECL
+        if (k + 1 >= GPSAT_DQ_MAXK) return k;
+        LANEVAR(int, claim_v);
+        LANES { LV(claim_v) = 0; }
+        LANE0
+        {
+            const int mine = gpsat_atomic_add(dq_ctrl + 4, 1) + 1;   // splits in flight, this one included
+            const int d = gpsat_ld_volatile(dq_ctrl + 3) -
+                          (gpsat_ld_volatile(dq_ctrl + 0) - gpsat_ld_volatile(dq_ctrl + 1)) - mine;
+            LV(claim_v) = (split_force || d >= 0) ? 1 : 0;
+        }
+        int slot = -1, ticket = 0, p = -1;
+        if (SHFL(claim_v, 0)) {
+            p = pick_branch();
+            if (p >= 0) slot = dq_acquire(ticket);
+        }
+        LANE0 { gpsat_atomic_add(dq_ctrl + 4, -1); }   // from here on the child is counted by tail - head
+        if (slot < 0) return k;                        // no demand, nothing to branch on, or the ring is full
+        LANE0 { cube_buf[k] = p; }
+        SYNCWARP();
+        dq_fill_and_publish(slot, ticket, k, p ^ 1);
         c_splits++;
         return k + 1;
+    }
+
+    // Budgeted steps (gpsat_solve_step): park this job in the ring — same cube, VSIDS counters, level-0 facts and the
+    // newest learnt clauses — so that the kernel can end and the host can run the epoch's exchange; a warp of the
+    // next launch picks it up.  Returns false when the ring is full (the job then simply keeps running).
+    GPSAT_DEV bool suspend(int k)
+    {
+        int ticket = 0;
+        const int slot = dq_acquire(ticket);
+        if (slot < 0) return false;
+        dq_fill_and_publish(slot, ticket, k, -1);
+        return true;
     }
 
     GPSAT_DEV int run_job(const int *cube, int k, int mode, volatile const int *stop_flag, int &conflict_out,
@@ -949,25 +1032,27 @@ struct WarpSolver {
         GPSAT_LANE_DECL
         conflict_out = GPSAT_NO_CONFLICT;
         reset_job();
-        if (hand != nullptr) {   // a child of a split cube: inherit the parent's counters, facts and newest clauses
-            LANES
-            {
-                for (int x = lane; x < 2 * n_vars; x += 32) vs[x] = hand[1 + x];
-            }
-            SYNCWARP();
-            const int st = import_records(hand + 1 + 2 * n_vars, hand[0]);
-            if (st != GPSAT_UNDEF) return st;
-        }
-        const bool may_split = mode == GPSAT_MODE_SOLVE && dynamic_split && k + 1 < GPSAT_DQ_MAXK;
-        int want_split = 0;
+        const bool queued_ok = mode == GPSAT_MODE_SOLVE && dynamic_split;
+        const bool may_split = queued_ok && k + 1 < GPSAT_DQ_MAXK;
+        int want_split = 0, burst = 0;
         long long last_split_at = 0;
-        if (may_split) {
+        if (queued_ok) {   // the cube may grow (splits) or be re-queued (budgeted steps): work on a private copy
             LANES
             {
                 for (int i = lane; i < k; i += 32) cube_buf[i] = cube[i];
             }
             SYNCWARP();
             cube = cube_buf;
+        }
+        if (hand != nullptr) {   // popped from the ring: inherit the parent's counters, facts and newest clauses
+            LANES
+            {
+                for (int x = lane; x < 2 * n_vars; x += 32) vs[x] = hand[1 + x];
+            }
+            SYNCWARP();
+            const int st = import_records(hand + 1 + 2 * n_vars, hand[0], 0);
+            release_slot();
+            if (st != GPSAT_UNDEF) return st;
         }
         if (mode == GPSAT_MODE_SOLVE) {
             const int st = pool_import();
@@ -998,10 +1083,19 @@ struct WarpSolver {
                 if (decision_mode == GPSAT_DECIDE_VSIDS) vsids_learnt(n_out);
                 pool_publish(n_out);
                 if (max_conflicts && c_conflicts >= max_conflicts) return GPSAT_UNDEF;
-                if ((c_conflicts & 31) == 0 && stop_flag && *stop_flag) return GPSAT_JOB_ABORTED;
-                if (may_split && (c_conflicts & 7) == 0 && c_conflicts - last_split_at >= 32 &&
-                    gpsat_ld_volatile(dq_ctrl + 3) > 0)
+                if ((c_conflicts & 31) == 0) {
+                    if (stop_flag && *stop_flag) return GPSAT_JOB_ABORTED;
+                    if (budget_ns && queued_ok) {
+                        LANEVAR(int, late_v);
+                        LANES { LV(late_v) = 0; }
+                        LANE0 { LV(late_v) = gpsat_now_ns() > *t0 + budget_ns ? 1 : 0; }
+                        if (SHFL(late_v, 0) && suspend(k)) return GPSAT_JOB_SUSPENDED;
+                    }
+                }
+                if (may_split && !want_split && c_conflicts - last_split_at >= split_gap && demand_hint() > 0) {
                     want_split = 1;
+                    burst = 0;
+                }
                 continue;
             }
             if (mode == GPSAT_MODE_PROPAGATE && dlevel >= k) return GPSAT_UNDEF;
@@ -1017,7 +1111,12 @@ struct WarpSolver {
                 if (dlevel >= k) {
                     cancel_until(k);
                     const int k2 = try_split(k);
-                    if (k2 != k) last_split_at = c_conflicts;
+                    if (k2 != k) {
+                        // while warps are still idle keep peeling children off (cube+~p1, cube+p1+~p2, ...): the
+                        // number of busy warps then grows by split_burst per gap instead of doubling
+                        last_split_at = c_conflicts;
+                        if (++burst < split_burst && demand_hint() > 0) want_split = 1;
+                    }
                     k = k2;
                 }
             }
@@ -1084,6 +1183,8 @@ GPSAT_DEV void gpsat_bind(WarpSolver &S, const gpsat_formula_view &F, const gpsa
     S.cube_buf = state + Ly.cube;
     S.dynamic_split = P.dynamic_split;
     S.split_force = P.split_force;
+    S.split_gap = P.split_gap > 0 ? P.split_gap : 1;
+    S.split_burst = P.split_burst > 0 ? P.split_burst : 1;
     S.root = 0;
     S.dq_lits = B.dq_lits;
     S.dq_meta = B.dq_meta;
@@ -1091,6 +1192,11 @@ GPSAT_DEV void gpsat_bind(WarpSolver &S, const gpsat_formula_view &F, const gpsa
     S.root_pending = B.root_pending;
     S.dq_hand = B.dq_hand;
     S.hand_words = B.hand_words;
+    S.dq_cap = B.dq_cap;
+    S.rel_slot = -1;
+    S.rel_seq = 0;
+    S.t0 = B.t0;
+    S.budget_ns = B.budget_ns;
     S.use_learnts = (P.mode == GPSAT_MODE_SOLVE) ? 1 : 0;
     S.arena = arena;
     S.arena_words = (int)P.arena_words;
@@ -1112,6 +1218,8 @@ GPSAT_DEV void gpsat_bind(WarpSolver &S, const gpsat_formula_view &F, const gpsa
     S.pool = B.pool;
     S.pool_cursor = B.pool_cursor;
     S.pool_cap_words = B.pool_cap_words;
+    S.xpool = B.xpool;
+    S.xpool_cursor = B.xpool_cursor;
 }
 
 // Runs one job (an original cube, or a child produced by a split) and folds its outcome into the record of the
@@ -1144,7 +1252,8 @@ GPSAT_DEV void gpsat_run_and_record(WarpSolver &S, int root, const int *cube, in
         const int flag = status == GPSAT_SAT ? GPSAT_FLAG_SAT
                        : status == GPSAT_UNSAT ? GPSAT_FLAG_UNSAT
                        : status == GPSAT_UNDEF ? GPSAT_FLAG_UNDEF
-                       : status == GPSAT_JOB_OOM ? GPSAT_FLAG_OOM : GPSAT_FLAG_ABORTED;
+                       : status == GPSAT_JOB_OOM ? GPSAT_FLAG_OOM
+                       : status == GPSAT_JOB_SUSPENDED ? 0 : GPSAT_FLAG_ABORTED;
         gpsat_atomic_max(B.root_flag + job, flag);
     }
     if (P.mode == GPSAT_MODE_PROPAGATE) {
@@ -1227,6 +1336,7 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
 {
     GPSAT_LANE_DECL
     int is_idle = 0;
+    unsigned long long busy_ns = 0;
     while (true) {
         LANEVAR(int, kind_v);   // 0 exit, 1 original cube, 2 queued child, 3 wait
         LANEVAR(int, idx_v);
@@ -1248,12 +1358,23 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
                     if (idx < B.n_cubes) kind = 1;
                 }
                 if (kind == 3 && P.mode == GPSAT_MODE_SOLVE && P.dynamic_split) {
-                    const int head = gpsat_ld_volatile(B.dq_ctrl + 1);
-                    int tail = gpsat_ld_volatile(B.dq_ctrl + 0);
-                    if (tail > GPSAT_DQ_CAP) tail = GPSAT_DQ_CAP;
-                    if (head < tail && gpsat_atomic_cas(B.dq_ctrl + 1, head, head + 1) == head) {
-                        idx = head;
-                        kind = 2;
+                    int pos = gpsat_ld_volatile(B.dq_ctrl + 1);
+                    for (int tries = 0; tries < 8; ++tries) {
+                        const int slot = pos & (B.dq_cap - 1);
+                        const int dif = gpsat_ld_volatile(B.dq_meta + 4 * slot + 2) - (pos + 1);
+                        if (dif == 0) {
+                            const int old = gpsat_atomic_cas(B.dq_ctrl + 1, pos, pos + 1);
+                            if (old == pos) {
+                                idx = pos;
+                                kind = 2;
+                                break;
+                            }
+                            pos = old;
+                        } else if (dif < 0) {
+                            break;   // empty (or the next child is still being written)
+                        } else {
+                            pos = gpsat_ld_volatile(B.dq_ctrl + 1);
+                        }
                     }
                 }
                 if (kind == 3 && gpsat_ld_volatile(B.dq_ctrl + 2) <= 0) kind = 0;   // nothing outstanding anywhere
@@ -1267,31 +1388,34 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
         if (kind == 3) {
             if (!is_idle && P.dynamic_split) {
                 is_idle = 1;
-                LANE0 { gpsat_atomic_add(B.dq_ctrl + 3, 1); }   // demand +1
+                LANE0 { gpsat_atomic_add(B.dq_ctrl + 3, 1); }   // one more idle warp
             }
             gpsat_nanosleep(4000);   // idle warps must not steal issue slots from the busy ones
             continue;
         }
         if (is_idle) {
             is_idle = 0;
-            // popping a queued child consumes the unit of demand its split claimed; any other exit returns ours
-            if (kind != 2) {
-                LANE0 { gpsat_atomic_add(B.dq_ctrl + 3, -1); }
-            }
+            LANE0 { gpsat_atomic_add(B.dq_ctrl + 3, -1); }
         }
+        const unsigned long long t_job = gpsat_now_ns();
         if (kind == 1) {
             const long long c0 = B.cube_offsets[idx], c1 = B.cube_offsets[idx + 1];
             gpsat_run_and_record(S, idx, B.cube_lits + c0, (int)(c1 - c0), nullptr, P, B);
         } else {
-            int len = 0;
-            while ((len = gpsat_ld_volatile(B.dq_meta + 2 * idx + 1)) == 0) gpsat_nanosleep(200);   // being published
+            const int slot = idx & (B.dq_cap - 1);
             gpsat_threadfence();
-            const int root = B.dq_meta[2 * idx];
-            const int *hand = B.dq_hand ? B.dq_hand + (long long)idx * B.hand_words : nullptr;
-            gpsat_run_and_record(S, root, B.dq_lits + (long long)idx * GPSAT_DQ_MAXK, len, hand, P, B);
+            const int root = B.dq_meta[4 * slot];
+            const int len = B.dq_meta[4 * slot + 1];
+            const int *hand = B.dq_hand + (long long)slot * B.hand_words;
+            S.rel_slot = slot;
+            S.rel_seq = idx + B.dq_cap;   // the ticket that may write this slot next
+            gpsat_run_and_record(S, root, B.dq_lits + (long long)slot * GPSAT_DQ_MAXK, len, hand, P, B);
         }
+        busy_ns += gpsat_now_ns() - t_job;
     }
-    if (is_idle) {
-        LANE0 { gpsat_atomic_add(B.dq_ctrl + 3, -1); }
+    LANE0
+    {
+        if (is_idle) gpsat_atomic_add(B.dq_ctrl + 3, -1);
+        if (B.busy_ns) gpsat_atomic_add_ll(B.busy_ns, (long long)busy_ns);   // utilisation = busy / (warps x kernel time)
     }
 }

@@ -97,12 +97,11 @@ struct gpsat {
     DevBuf<int32_t> implied, n_implied;
     DevBuf<int64_t> conflict_clause;
     DevBuf<int32_t> gstate;
-    DevBuf<int32_t> pool, pool_cursor;
+    DevBuf<int32_t> pool, pool_cursor, xpool, xpool_cursor;
     DevBuf<int32_t> dq_lits, dq_meta, dq_ctrl, root_pending, root_flag, dq_hand;
     std::vector<int32_t> root_pending_h, root_flag_h;
     int32_t *arena = nullptr;
     size_t arena_total_words = 0;
-    int64_t pool_export_mark = 0;
     // geometry
     gpsat_state_layout Ly{};
     int blocks = 0, warps_per_block = 0, state_in_smem = 0, formula_in_smem = 0, formula_smem_words = 0;
@@ -119,7 +118,25 @@ struct gpsat {
 
 namespace {
 
-const int64_t kPoolWords = 1 << 22;   // 16 MB shared learnt pool per GPU
+const int64_t kPoolWords = 1 << 22;   // 16 MB shared learnt pool per GPU (and as much for clauses from other GPUs)
+const int64_t kPoolSlots = kPoolWords / GPSAT_POOL_SLOT_WORDS;
+
+int ensure_pools(gpsat *h, bool foreign)
+{
+    if (!h->pool.p) {
+        CU(h->pool.ensure((size_t)kPoolWords));
+        CU(h->pool_cursor.ensure(4));
+        CU(cudaMemsetAsync(h->pool_cursor.p, 0, 4 * sizeof(int32_t), h->stream));
+        CU(cudaMemsetAsync(h->pool.p, 0, (size_t)kPoolWords * sizeof(int32_t), h->stream));
+    }
+    if (foreign && !h->xpool.p) {
+        CU(h->xpool.ensure((size_t)kPoolWords));
+        CU(h->xpool_cursor.ensure(4));
+        CU(cudaMemsetAsync(h->xpool_cursor.p, 0, 4 * sizeof(int32_t), h->stream));
+        CU(cudaMemsetAsync(h->xpool.p, 0, (size_t)kPoolWords * sizeof(int32_t), h->stream));
+    }
+    return GPSAT_OK;
+}
 
 gpsat_formula_view make_view(gpsat *h)
 {
@@ -166,6 +183,8 @@ gpsat_solve_params make_params(gpsat *h, int mode, int64_t implied_stride)
     P.implied_stride = implied_stride;
     P.dynamic_split = (mode == GPSAT_MODE_SOLVE && h->opts.dynamic_split) ? 1 : 0;
     P.split_force = 0;
+    P.split_gap = h->opts.split_gap > 0 ? h->opts.split_gap : 8;
+    P.split_burst = h->opts.split_burst > 0 ? h->opts.split_burst : 4;
     return P;
 }
 
@@ -233,21 +252,19 @@ int ensure_run_buffers(gpsat *h, int mode)
 {
     const size_t n_warps = (size_t)h->blocks * h->warps_per_block;
     CU(h->ctrl.ensure(4));
-    CU(h->t0.ensure(1));
+    CU(h->t0.ensure(2));   // [0] globaltimer stamp of the launch, [1] summed busy time of the warps
     CU(h->model.ensure((size_t)std::max(h->D.n_vars, 1)));
     CU(h->records.ensure((size_t)std::max(h->n_cubes, 1)));
-    if (!h->pool.p) {
-        CU(h->pool.ensure((size_t)kPoolWords));
-        CU(h->pool_cursor.ensure(2));
-        CU(cudaMemsetAsync(h->pool_cursor.p, 0, 2 * sizeof(int32_t), h->stream));
-        CU(cudaMemsetAsync(h->pool.p, 0, (size_t)kPoolWords * sizeof(int32_t), h->stream));
+    if (h->opts.share_learnts) {   // the pools exist only when clause sharing is on
+        int rc = ensure_pools(h, false);
+        if (rc != GPSAT_OK) return rc;
     }
-    CU(h->dq_ctrl.ensure(4));
+    CU(h->dq_ctrl.ensure(8));
     CU(h->root_pending.ensure((size_t)std::max(h->n_cubes, 1)));
     CU(h->root_flag.ensure((size_t)std::max(h->n_cubes, 1)));
     if (mode == GPSAT_MODE_SOLVE && h->opts.dynamic_split) {
         CU(h->dq_lits.ensure((size_t)GPSAT_DQ_CAP * GPSAT_DQ_MAXK));
-        CU(h->dq_meta.ensure((size_t)GPSAT_DQ_CAP * 2));
+        CU(h->dq_meta.ensure((size_t)GPSAT_DQ_CAP * 4));
         CU(h->dq_hand.ensure((size_t)GPSAT_DQ_CAP * (size_t)(1 + 2 * h->D.n_vars + GPSAT_HAND_CLAUSE_WORDS)));
     }
     if (!h->state_in_smem) CU(h->gstate.ensure(n_warps * (size_t)h->Ly.total_words));
@@ -291,6 +308,8 @@ gpsat_run_buffers make_buffers(gpsat *h, int mode, double budget_ms)
     B.pool = h->pool.p;
     B.pool_cursor = h->pool_cursor.p;
     B.pool_cap_words = (int32_t)kPoolWords;
+    B.xpool = h->xpool.p;
+    B.xpool_cursor = h->xpool_cursor.p;
     B.state_in_smem = h->state_in_smem;
     B.formula_in_smem = h->formula_in_smem;
     B.formula_smem_words = h->formula_smem_words;
@@ -300,8 +319,10 @@ gpsat_run_buffers make_buffers(gpsat *h, int mode, double budget_ms)
     B.root_pending = h->root_pending.p;
     B.dq_hand = h->dq_hand.p;
     B.hand_words = 1 + 2 * h->D.n_vars + GPSAT_HAND_CLAUSE_WORDS;
+    B.dq_cap = GPSAT_DQ_CAP;
     B.root_flag = h->root_flag.p;
     B.t0 = h->t0.p;
+    B.busy_ns = (long long *)(h->t0.p + 1);
     B.budget_ns = budget_ms > 0 ? (unsigned long long)(budget_ms * 1e6) : 0ull;
     return B;
 }
@@ -310,15 +331,21 @@ int reset_ctrl(gpsat *h)
 {
     const size_t nc = (size_t)std::max(h->n_cubes, 1);
     const int32_t init[4] = {0, 0, -1, 0};
-    const int32_t dq_init[4] = {0, 0, h->n_cubes, 0};   // tail, head, outstanding jobs, idle warps
+    const int32_t dq_init[8] = {0, 0, h->n_cubes, 0, 0, 0, 0, 0};   // tail, head, outstanding jobs, idle warps, splits in flight
     CU(cudaMemcpyAsync(h->ctrl.p, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->dq_ctrl.p, dq_init, sizeof(dq_init), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemsetAsync(h->records.p, 0, nc * sizeof(gpsat_job_record), h->stream));
+    CU(cudaMemsetAsync(h->t0.p, 0, 2 * sizeof(unsigned long long), h->stream));
     CU(cudaMemsetAsync(h->root_flag.p, 0, nc * sizeof(int32_t), h->stream));
     std::vector<int32_t> ones(nc, 1);
     CU(cudaMemcpyAsync(h->root_pending.p, ones.data(), nc * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    if (h->dq_meta.p) CU(cudaMemsetAsync(h->dq_meta.p, 0, (size_t)GPSAT_DQ_CAP * 2 * sizeof(int32_t), h->stream));
-    CU(cudaStreamSynchronize(h->stream));   // `ones` is pageable host memory
+    std::vector<int32_t> meta;
+    if (h->dq_meta.p) {   // ring slots start empty: sequence number = slot index
+        meta.assign((size_t)GPSAT_DQ_CAP * 4, 0);
+        for (int i = 0; i < GPSAT_DQ_CAP; i++) meta[4 * (size_t)i + 2] = i;
+        CU(cudaMemcpyAsync(h->dq_meta.p, meta.data(), meta.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));   // `ones` / `meta` are pageable host memory
     return GPSAT_OK;
 }
 
@@ -371,10 +398,17 @@ void fill_stats(gpsat *h, gpsat_stats *s)
         s->restarts += r.restarts;
         s->watchers_visited += r.watchers_visited;
         s->clause_words_read += r.clause_words_read;
+        s->splits += r.reserved;
     }
-    int32_t cur[2] = {0, 0};
+    int32_t cur[2] = {0, 0}, xcur[2] = {0, 0};
     if (h->pool_cursor.p) cudaMemcpy(cur, h->pool_cursor.p, sizeof(cur), cudaMemcpyDeviceToHost);
+    if (h->xpool_cursor.p) cudaMemcpy(xcur, h->xpool_cursor.p, sizeof(xcur), cudaMemcpyDeviceToHost);
     s->pool_clauses = cur[1];
+    s->foreign_clauses = xcur[0];
+    unsigned long long busy = 0;
+    if (h->t0.p && h->run_mode == GPSAT_MODE_SOLVE) cudaMemcpy(&busy, h->t0.p + 1, sizeof(busy), cudaMemcpyDeviceToHost);
+    const double warp_ms = (double)h->blocks * h->warps_per_block * h->kernel_ms;
+    s->warp_busy_frac = warp_ms > 0 ? (double)busy * 1e-6 / warp_ms : 0.0;
     s->kernel_ms = h->kernel_ms;
     s->kernel_launches = h->kernel_launches;
     s->blocks = h->blocks;
@@ -796,6 +830,15 @@ int gpsat_solve_begin(gpsat_t *h)
     if (rc != GPSAT_OK) return rc;
     rc = reset_ctrl(h);
     if (rc != GPSAT_OK) return rc;
+    // every solve starts without shared knowledge: clauses of an earlier run on this handle would be cached work
+    if (h->pool.p) {
+        CU(cudaMemsetAsync(h->pool_cursor.p, 0, 4 * sizeof(int32_t), h->stream));
+        CU(cudaMemsetAsync(h->pool.p, 0, (size_t)kPoolWords * sizeof(int32_t), h->stream));
+    }
+    if (h->xpool.p) {
+        CU(cudaMemsetAsync(h->xpool_cursor.p, 0, 4 * sizeof(int32_t), h->stream));
+        CU(cudaMemsetAsync(h->xpool.p, 0, (size_t)kPoolWords * sizeof(int32_t), h->stream));
+    }
     h->kernel_ms = 0;
     h->kernel_launches = 0;
     h->run_mode = GPSAT_MODE_SOLVE;
@@ -892,28 +935,27 @@ int gpsat_pool_export(gpsat_t *h, int32_t *buf, int64_t cap_words, int64_t *n_wo
     }
     *n_words = 0;
     if (!h->pool.p) return GPSAT_OK;
-    int32_t cur[2] = {0, 0};
+    int32_t cur[4] = {0, 0, 0, 0};
     CU(cudaMemcpy(cur, h->pool_cursor.p, sizeof(cur), cudaMemcpyDeviceToHost));
-    int64_t used = std::min<int64_t>(cur[0], kPoolWords);
-    int64_t fresh = used - h->pool_export_mark;
-    if (fresh <= 0) return GPSAT_OK;
-    if (fresh > cap_words) {
-        // hand out whole records only: walk headers on the host
-        std::vector<int32_t> tmp((size_t)fresh);
-        CU(cudaMemcpy(tmp.data(), h->pool.p + h->pool_export_mark, (size_t)fresh * sizeof(int32_t), cudaMemcpyDeviceToHost));
-        int64_t at = 0;
-        while (at < fresh && tmp[(size_t)at] > 0 && at + 1 + tmp[(size_t)at] <= cap_words) at += 1 + tmp[(size_t)at];
-        std::memcpy(buf, tmp.data(), (size_t)at * sizeof(int32_t));
-        *n_words = at;
-        h->pool_export_mark += at;
-        return GPSAT_OK;
-    }
-    CU(cudaMemcpy(buf, h->pool.p + h->pool_export_mark, (size_t)fresh * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    // a record whose header is still 0 was reserved but dropped (pool overflow); stop there
+    const int64_t used = std::min<int64_t>(cur[0], kPoolSlots);
+    int64_t mark = cur[2];
+    if (used <= mark) return GPSAT_OK;
+    std::vector<int32_t> tmp((size_t)(used - mark) * GPSAT_POOL_SLOT_WORDS);
+    CU(cudaMemcpy(tmp.data(), h->pool.p + mark * GPSAT_POOL_SLOT_WORDS, tmp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
     int64_t at = 0;
-    while (at < fresh && buf[at] > 0 && at + 1 + buf[at] <= fresh) at += 1 + buf[at];
+    for (int64_t sl = 0; sl < used - mark; sl++) {   // fixed slots -> packed records, whole records only
+        const int32_t *rec = tmp.data() + sl * GPSAT_POOL_SLOT_WORDS;
+        const int32_t len = rec[0];
+        if (len > 0 && len < GPSAT_POOL_SLOT_WORDS) {
+            if (at + 1 + len > cap_words) break;
+            std::memcpy(buf + at, rec, (size_t)(1 + len) * sizeof(int32_t));
+            at += 1 + len;
+        }
+        mark++;
+    }
     *n_words = at;
-    h->pool_export_mark += (at == fresh) ? fresh : at;
+    const int32_t m32 = (int32_t)mark;
+    CU(cudaMemcpy(h->pool_cursor.p + 2, &m32, sizeof(m32), cudaMemcpyHostToDevice));
     return GPSAT_OK;
 }
 
@@ -924,13 +966,10 @@ int gpsat_pool_import(gpsat_t *h, const int32_t *buf, int64_t n_words)
         return GPSAT_E_ARG;
     }
     if (n_words == 0) return GPSAT_OK;
-    if (!h->pool.p) {
-        CU(h->pool.ensure((size_t)kPoolWords));
-        CU(h->pool_cursor.ensure(2));
-        CU(cudaMemset(h->pool_cursor.p, 0, 2 * sizeof(int32_t)));
-        CU(cudaMemset(h->pool.p, 0, (size_t)kPoolWords * sizeof(int32_t)));
-    }
-    int64_t at = 0, n_rec = 0;
+    int rc = ensure_pools(h, true);
+    if (rc != GPSAT_OK) return rc;
+    std::vector<int32_t> slots;
+    int64_t at = 0;
     while (at < n_words) {
         const int32_t len = buf[at];
         if (len <= 0 || at + 1 + len > n_words) {
@@ -942,19 +981,86 @@ int gpsat_pool_import(gpsat_t *h, const int32_t *buf, int64_t n_words)
                 set_error("pool literal out of range");
                 return GPSAT_E_ARG;
             }
+        if (len < GPSAT_POOL_SLOT_WORDS) {   // longer clauses do not fit a slot: optional knowledge, dropped
+            const size_t o = slots.size();
+            slots.resize(o + GPSAT_POOL_SLOT_WORDS, 0);
+            std::memcpy(slots.data() + o, buf + at, (size_t)(1 + len) * sizeof(int32_t));
+        }
         at += 1 + len;
-        n_rec++;
     }
-    int32_t cur[2] = {0, 0};
-    CU(cudaMemcpy(cur, h->pool_cursor.p, sizeof(cur), cudaMemcpyDeviceToHost));
-    const int64_t used = std::min<int64_t>(cur[0], kPoolWords);
-    if (used + n_words > kPoolWords) return GPSAT_OK;   // pool full: foreign clauses are optional knowledge
-    CU(cudaMemcpy(h->pool.p + used, buf, (size_t)n_words * sizeof(int32_t), cudaMemcpyHostToDevice));
-    cur[0] = (int32_t)(used + n_words);
-    cur[1] += (int32_t)n_rec;
-    CU(cudaMemcpy(h->pool_cursor.p, cur, sizeof(cur), cudaMemcpyHostToDevice));
-    // imported records are not re-exported
-    if (h->pool_export_mark == used) h->pool_export_mark = used + n_words;
+    int32_t cur[4] = {0, 0, 0, 0};
+    CU(cudaMemcpy(cur, h->xpool_cursor.p, sizeof(cur), cudaMemcpyDeviceToHost));
+    const int64_t n_slots = (int64_t)slots.size() / GPSAT_POOL_SLOT_WORDS;
+    if (n_slots == 0 || cur[0] + n_slots > kPoolSlots) return GPSAT_OK;   // pool full: foreign clauses are optional
+    CU(cudaMemcpy(h->xpool.p + (int64_t)cur[0] * GPSAT_POOL_SLOT_WORDS, slots.data(), slots.size() * sizeof(int32_t),
+                  cudaMemcpyHostToDevice));
+    cur[0] += (int32_t)n_slots;
+    cur[1] += (int32_t)n_slots;
+    CU(cudaMemcpy(h->xpool_cursor.p, cur, sizeof(cur), cudaMemcpyHostToDevice));
+    return GPSAT_OK;
+}
+
+int64_t gpsat_exchange_block_words(int32_t max_clauses)
+{
+    return GPSAT_XCHG_HEADER_WORDS + (int64_t)std::max(max_clauses, 0) * GPSAT_POOL_SLOT_WORDS;
+}
+
+int gpsat_exchange_pack(gpsat_t *h, void *dev_block, int64_t block_words, int32_t rank, int32_t done, int32_t verdict)
+{
+    if (!h || !dev_block || block_words < GPSAT_XCHG_HEADER_WORDS || block_words > INT32_MAX) {
+        set_error("bad arguments");
+        return GPSAT_E_ARG;
+    }
+    int rc = ensure_pools(h, true);
+    if (rc != GPSAT_OK) return rc;
+    int64_t jobs_done = 0;
+    for (size_t j = 0; j < h->records_h.size() && j < (size_t)h->n_cubes; j++) {
+        const int st = h->records_h[j].status;
+        jobs_done += (st == GPSAT_SAT || st == GPSAT_UNSAT || st == GPSAT_UNDEF) ? 1 : 0;
+    }
+    CU(gpsat_kernels::launch_xchg_pack(h->pool.p, h->pool_cursor.p, (int)kPoolSlots, (int *)dev_block, (int)block_words,
+                                       rank, done, verdict, (int)jobs_done, h->stream));
+    CU(cudaStreamSynchronize(h->stream));   // the caller's collective runs on another stream
+    return GPSAT_OK;
+}
+
+int gpsat_exchange_unpack(gpsat_t *h, const void *dev_blocks, int32_t n_ranks, int32_t my_rank, int64_t block_words,
+                          int32_t *sat_rank, int32_t *all_done, int32_t *any_undef, int64_t *imported_clauses,
+                          int64_t *jobs_done_total)
+{
+    if (!h || !dev_blocks || n_ranks <= 0 || my_rank < 0 || my_rank >= n_ranks ||
+        block_words < GPSAT_XCHG_HEADER_WORDS || block_words > INT32_MAX) {
+        set_error("bad arguments");
+        return GPSAT_E_ARG;
+    }
+    int rc = ensure_pools(h, true);
+    if (rc != GPSAT_OK) return rc;
+    CU(gpsat_kernels::launch_xchg_unpack((const int *)dev_blocks, n_ranks, my_rank, (int)block_words, h->xpool.p,
+                                         h->xpool_cursor.p, (int)kPoolSlots, h->stream));
+    std::vector<int32_t> hdr((size_t)n_ranks * GPSAT_XCHG_HEADER_WORDS);
+    CU(cudaMemcpy2DAsync(hdr.data(), GPSAT_XCHG_HEADER_WORDS * sizeof(int32_t), dev_blocks,
+                         (size_t)block_words * sizeof(int32_t), GPSAT_XCHG_HEADER_WORDS * sizeof(int32_t), (size_t)n_ranks,
+                         cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    int32_t sat = -1, done = 1, undef = 0;
+    int64_t imported = 0, jobs = 0;
+    for (int r = 0; r < n_ranks; r++) {
+        const int32_t *b = hdr.data() + (size_t)r * GPSAT_XCHG_HEADER_WORDS;
+        if (b[0] != GPSAT_XCHG_MAGIC) {
+            set_error("exchange block without header (rank " + std::to_string(r) + ")");
+            return GPSAT_E_ARG;
+        }
+        if (b[1] == GPSAT_SAT && sat < 0) sat = r;
+        if (!b[2]) done = 0;
+        else if (b[1] == GPSAT_UNDEF) undef = 1;
+        if (r != my_rank) imported += b[4];
+        jobs += b[6];
+    }
+    if (sat_rank) *sat_rank = sat;
+    if (all_done) *all_done = done;
+    if (any_undef) *any_undef = undef;
+    if (imported_clauses) *imported_clauses = imported;
+    if (jobs_done_total) *jobs_done_total = jobs;
     return GPSAT_OK;
 }
 

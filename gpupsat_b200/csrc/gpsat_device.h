@@ -23,11 +23,16 @@
 #define GPSAT_JOB_NOT_RUN (-1)
 #define GPSAT_JOB_ABORTED (-2)   // stopped by the early-termination flag
 #define GPSAT_JOB_OOM (-3)       // learnt arena exhausted even after reduction
+#define GPSAT_JOB_SUSPENDED (-4) // parked in the ring at the end of a budgeted step; a later launch resumes it
 
 // dynamic cube queue (children of split cubes)
 #define GPSAT_DQ_MAXK 64         // literals per queued cube
-#define GPSAT_DQ_CAP 16384       // queued cubes per run
-#define GPSAT_HAND_CLAUSE_WORDS 4096   // learnt-clause words a child inherits from the cube it was split off
+#define GPSAT_DQ_CAP 16384       // slots of the ring of queued cubes (power of two, > 2 x resident warps)
+#define GPSAT_HAND_CLAUSE_WORDS 8192   // learnt-clause words a queued cube inherits from the job that queued it
+// shared learnt-clause pools: fixed slots [len, lit0 .. ] (len written last); exchange block = header + slots
+#define GPSAT_POOL_SLOT_WORDS 16
+#define GPSAT_XCHG_HEADER_WORDS 8
+#define GPSAT_XCHG_MAGIC 0x47505358
 // per-root outcome flags, combined with atomicMax (higher wins)
 #define GPSAT_FLAG_UNSAT 1
 #define GPSAT_FLAG_ABORTED 2
@@ -66,6 +71,8 @@ struct gpsat_solve_params {
     int64_t implied_stride;      // propagate mode: words reserved per cube in `implied`
     int32_t dynamic_split;       // 1: a long-running cube hands half of its search space to an idle warp at restarts
     int32_t split_force;         // test hook: split at every restart even when no warp is idle
+    int32_t split_gap;           // conflicts a job runs between two rounds of splitting
+    int32_t split_burst;         // children handed out per round while warps are idle
 };
 
 // word offsets (int32 units) of the per-warp state arrays inside one warp's state block
@@ -90,21 +97,25 @@ struct gpsat_run_buffers {
     int32_t *arena;                // n_warps * arena_words
     int32_t *gstate;               // n_warps * layout.total_words when state is not in shared memory
     int32_t *pool;                 // shared learnt pool words
-    int32_t *pool_cursor;          // [0] words used, [1] clauses
+    int32_t *pool_cursor;          // [0] slots reserved, [1] clauses published, [2] export mark (slots)
     int32_t pool_cap_words;
+    const int32_t *xpool;          // clauses received from other GPUs (same slot format, may be null)
+    const int32_t *xpool_cursor;   // [0] slots used
     int32_t state_in_smem;
     int32_t formula_in_smem;       // cl2 / occ2 / ostart staged once per block in front of the warps' state blocks
     int32_t formula_smem_words;    // size of that staging area (multiple of 4 words)
     // dynamic splitting: children of split cubes are queued here and popped by idle warps
-    int32_t *dq_lits;              // GPSAT_DQ_CAP * GPSAT_DQ_MAXK
-    int32_t *dq_meta;              // GPSAT_DQ_CAP * 2 : (root cube, length); length written last (0 = not published)
-    int32_t *dq_ctrl;              // [0] tail (pushed) [1] head (popped) [2] outstanding jobs [3] demand = idle warps - queued children - splits in flight
-    int32_t *dq_hand;              // GPSAT_DQ_CAP * hand_words : per queued child [n][vs 2n][records] (may be null)
+    int32_t *dq_lits;              // dq_cap * GPSAT_DQ_MAXK
+    int32_t *dq_meta;              // dq_cap * 4 : (root cube, length, slot sequence number, -); sequence starts at the slot index
+    int32_t *dq_ctrl;              // [0] tail (push tickets) [1] head (pop tickets) [2] outstanding jobs [3] idle warps [4] splits in flight
+    int32_t *dq_hand;              // dq_cap * hand_words : per queued cube [n][vs 2n][records] (non-null when dynamic_split)
     int32_t hand_words;
+    int32_t dq_cap;                // ring slots (power of two)
     int32_t *root_pending;         // n_cubes: open jobs descending from each original cube
     int32_t *root_flag;            // n_cubes: GPSAT_FLAG_* (atomicMax)
     const unsigned long long *t0;     // globaltimer stamp taken right before the launch
     unsigned long long budget_ns;     // warps stop pulling new cubes once now > *t0 + budget_ns (0 = no limit)
+    long long *busy_ns;               // sum over warps of the time spent inside jobs (may be null)
 };
 
 // per-warp state block: word offsets of each array (every array starts on a 16-byte boundary)

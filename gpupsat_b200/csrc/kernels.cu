@@ -111,6 +111,70 @@ gpsat_eval_kernel(int32_t n_vars, int32_t n_clauses, const int32_t *__restrict__
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Epoch exchange (multi-GPU; no reference equivalent — the reference is single-GPU).
+// One exchange block per GPU: [magic, verdict, done, payload words, clauses, rank, jobs done, -] + pool slots.  The blocks
+// of all ranks are all-gathered by ONE NCCL collective per epoch; unpack appends the other ranks' slots to the
+// foreign pool that jobs import when they start.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gpsat_xchg_pack_kernel(const int *__restrict__ pool, int *pool_cursor, int pool_cap_slots, int *__restrict__ block,
+                       int block_words, int rank, int done, int verdict, int jobs_done)
+{
+    __shared__ int s_from, s_n;
+    if (threadIdx.x == 0) {
+        int used = pool_cursor[0];
+        if (used > pool_cap_slots) used = pool_cap_slots;
+        const int mark = pool_cursor[2];
+        const int room = (block_words - GPSAT_XCHG_HEADER_WORDS) / GPSAT_POOL_SLOT_WORDS;
+        int n = used - mark;
+        if (n > room) n = room;
+        if (n < 0) n = 0;
+        s_from = mark;
+        s_n = n;
+    }
+    __syncthreads();
+    const int from = s_from, n = s_n;
+    const int4 *src = reinterpret_cast<const int4 *>(pool + (size_t)from * GPSAT_POOL_SLOT_WORDS);
+    int4 *dst = reinterpret_cast<int4 *>(block + GPSAT_XCHG_HEADER_WORDS);
+    for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < n * (GPSAT_POOL_SLOT_WORDS / 4);
+         i += (int)(gridDim.x * blockDim.x))
+        dst[i] = src[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        block[0] = GPSAT_XCHG_MAGIC;
+        block[1] = verdict;
+        block[2] = done;
+        block[3] = n * GPSAT_POOL_SLOT_WORDS;
+        block[4] = n;
+        block[5] = rank;
+        block[6] = jobs_done;
+        block[7] = 0;
+        pool_cursor[2] = from + n;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gpsat_xchg_unpack_kernel(const int *__restrict__ blocks, int n_ranks, int my_rank, int block_words,
+                         int *__restrict__ xpool, int *xpool_cursor, int xpool_cap_slots)
+{
+    // every thread recomputes the (tiny) prefix over ranks; thread 0 publishes the new cursor at the end
+    int base = xpool_cursor[0];
+    for (int r = 0; r < n_ranks; ++r) {
+        const int *b = blocks + (size_t)r * block_words;
+        if (r == my_rank || b[0] != GPSAT_XCHG_MAGIC) continue;
+        int n = b[4];
+        if (n > xpool_cap_slots - base) n = xpool_cap_slots - base;
+        if (n <= 0) continue;
+        const int4 *src = reinterpret_cast<const int4 *>(b + GPSAT_XCHG_HEADER_WORDS);
+        int4 *dst = reinterpret_cast<int4 *>(xpool + (size_t)base * GPSAT_POOL_SLOT_WORDS);
+        for (int i = (int)threadIdx.x; i < n * (GPSAT_POOL_SLOT_WORDS / 4); i += (int)blockDim.x) dst[i] = src[i];
+        base += n;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) xpool_cursor[0] = base;
+}
+
 }  // namespace
 
 namespace gpsat_kernels {
@@ -150,6 +214,22 @@ cudaError_t cdcl_attributes(int *regs_per_thread, size_t *local_bytes)
     *regs_per_thread = a.numRegs;
     *local_bytes = a.localSizeBytes;
     return cudaSuccess;
+}
+
+cudaError_t launch_xchg_pack(const int *pool, int *pool_cursor, int pool_cap_slots, int *block, int block_words,
+                             int rank, int done, int verdict, int jobs_done, cudaStream_t stream)
+{
+    gpsat_xchg_pack_kernel<<<1, 256, 0, stream>>>(pool, pool_cursor, pool_cap_slots, block, block_words, rank, done,
+                                                  verdict, jobs_done);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_xchg_unpack(const int *blocks, int n_ranks, int my_rank, int block_words, int *xpool,
+                               int *xpool_cursor, int xpool_cap_slots, cudaStream_t stream)
+{
+    gpsat_xchg_unpack_kernel<<<1, 256, 0, stream>>>(blocks, n_ranks, my_rank, block_words, xpool, xpool_cursor,
+                                                    xpool_cap_slots);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_stamp(unsigned long long *t0, cudaStream_t stream)
@@ -210,7 +290,9 @@ struct SweepArgs {
 
 __device__ __forceinline__ int sw_value(const uint32_t *vb, int x)
 {
-    const uint32_t w = vb[x >> 5];                 // var = x>>1, 16 vars per word -> word (x>>1)>>4
+    // L2-coherent load: other lanes assign through atomics (performed at L2); a line cached in L1 could be stale and
+    // hide BOTH sides of a unit clause from the two lanes that visit it (lost implication)
+    const uint32_t w = __ldcg(vb + (x >> 5));      // var = x>>1, 16 vars per word -> word (x>>1)>>4
     const uint32_t f = (w >> (((x >> 1) & 15) * 2)) & 3u;
     return (f & 2u) ? (int)((f & 1u) == (uint32_t)(x & 1)) : 2;   // 1 true, 0 false, 2 unassigned
 }
@@ -312,7 +394,7 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_kernel(const SweepArg
                 }
             }
             __syncwarp();
-            qhead += 32;
+            qhead = min(qhead + 32, total);   // literals appended during this batch start the next one
         }
         __syncwarp();
         const int n_imp = s_count[wib];

@@ -19,6 +19,13 @@ int cdcl_max_warps_per_block();
 // stamps *t0 with the GPU's globaltimer (deadline base for budgeted steps)
 cudaError_t launch_stamp(unsigned long long *t0, cudaStream_t stream);
 
+// epoch exchange between GPUs: pack this GPU's fresh pool slots + status header into an exchange block; append the
+// other ranks' slots (from the all-gathered blocks) to the foreign pool
+cudaError_t launch_xchg_pack(const int *pool, int *pool_cursor, int pool_cap_slots, int *block, int block_words,
+                             int rank, int done, int verdict, int jobs_done, cudaStream_t stream);
+cudaError_t launch_xchg_unpack(const int *blocks, int n_ranks, int my_rank, int block_words, int *xpool,
+                               int *xpool_cursor, int xpool_cap_slots, cudaStream_t stream);
+
 // clause evaluation: one thread per (assignment, clause)
 cudaError_t launch_eval_clauses(int32_t n_vars, int32_t n_clauses, const int32_t *coffsets, const int32_t *clits,
                                 int32_t n_assignments, const uint8_t *assignment, int32_t *status, int32_t *unit,

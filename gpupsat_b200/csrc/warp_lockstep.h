@@ -62,7 +62,9 @@ static inline int gpsat_atomic_max(int *p, int v) { int o = *p; if (v > o) *p = 
 static inline void gpsat_atomic_add_ll(long long *p, long long v) { *p += v; }
 static inline int gpsat_ld_volatile(const int *p) { return *(const volatile int *)p; }
 static inline void gpsat_nanosleep(unsigned) {}
-static inline unsigned long long gpsat_now_ns() { return 0; }
+// emulated clock: one tick per query, so tests can make budgeted steps expire deterministically
+static unsigned long long g_gpsat_emu_clock = 0;
+static inline unsigned long long gpsat_now_ns() { return ++g_gpsat_emu_clock; }
 static inline int gpsat_popc(unsigned m) { return __builtin_popcount(m); }
 static inline int gpsat_ffs(unsigned m) { return __builtin_ffs((int)m); }
 struct gpsat_int2 { int x, y; };

@@ -113,7 +113,9 @@ typedef struct gpsat_opts {
                                      space to an idle warp (the reference's wave-synchronous loop waits for the slowest
                                      job instead: SATSolver/main.cu:259-269).  Verdicts are unaffected; per-cube counters
                                      then depend on timing, so parity runs set 0. */
-    int32_t reserved[7];
+    int32_t split_gap;            /* conflicts a cube runs between two rounds of splitting; 0 = default (8) */
+    int32_t split_burst;          /* children handed out per round while warps are idle; 0 = default (4) */
+    int32_t reserved[5];
 } gpsat_opts;
 
 void gpsat_opts_default(gpsat_opts *o);
@@ -144,6 +146,9 @@ typedef struct gpsat_stats {
     int32_t blocks, warps_per_block, smem_bytes_per_block;
     int32_t state_in_smem;        /* 1: per-job assignment/trail/watch bitmap live in shared memory */
     int32_t reserved;
+    int64_t splits;               /* children created by dynamic splitting */
+    double  warp_busy_frac;       /* sum of the time warps spent inside jobs / (warps x kernel time) */
+    int64_t foreign_clauses;      /* clauses received from other GPUs (gpsat_exchange_unpack / gpsat_pool_import) */
 } gpsat_stats;
 
 /* ≙ DataToDevice ctor + CUDAClauseVec::alloc_and_copy_to_dev (SATSolver/DataToDevice.cu:11-56, Utils/CUDAClauseVec.cu:85-118):
@@ -198,10 +203,24 @@ int gpsat_solve_step(gpsat_t *h, double budget_ms, int32_t *done, int32_t *verdi
 int gpsat_solve_end(gpsat_t *h, int32_t *verdict, uint8_t *model, gpsat_stats *stats);
 /* raises the early-termination flag (another GPU found a model): running cubes abort, no new cube starts */
 int gpsat_request_stop(gpsat_t *h);
-/* learnt-clause pool exchange: records are [len, lit0, ..., lit(len-1)] packed back to back.
- * export returns clauses appended to this GPU's pool since the previous export; import appends foreign clauses. */
+/* learnt-clause pool exchange through HOST buffers: records are [len, lit0, ..., lit(len-1)] packed back to back.
+ * export returns clauses appended to this GPU's pool since the previous export / pack; import appends foreign clauses
+ * (clauses of 16 or more literals do not fit a pool slot and are dropped). */
 int gpsat_pool_export(gpsat_t *h, int32_t *buf, int64_t cap_words, int64_t *n_words);
 int gpsat_pool_import(gpsat_t *h, const int32_t *buf, int64_t n_words);
+/* Device-side exchange for ONE collective per epoch: gpsat_exchange_pack writes this GPU's exchange
+ * block — header [magic, verdict, done, payload words, clauses, rank, jobs done, 0] followed by the pool slots published
+ * since the previous pack (16-word slots [len, lit0 ...]) — into DEVICE memory owned by the caller (e.g. a torch
+ * tensor); the caller all-gathers the blocks of all ranks (ncclAllGather / torch.distributed.all_gather_into_tensor)
+ * and hands the gathered DEVICE buffer [n_ranks][block_words] to gpsat_exchange_unpack, which appends the other ranks'
+ * clauses to this GPU's foreign pool (imported by every job that starts afterwards) and reduces the headers:
+ * sat_rank (lowest rank that holds a model, -1 if none), all_done (every rank has closed all its cubes), any_undef (a finished rank ended
+ * UNDEF).  Both calls run on the handle's stream and return after it is idle. */
+int64_t gpsat_exchange_block_words(int32_t max_clauses);
+int gpsat_exchange_pack(gpsat_t *h, void *dev_block, int64_t block_words, int32_t rank, int32_t done, int32_t verdict);
+int gpsat_exchange_unpack(gpsat_t *h, const void *dev_blocks, int32_t n_ranks, int32_t my_rank, int64_t block_words,
+                          int32_t *sat_rank, int32_t *all_done, int32_t *any_undef, int64_t *imported_clauses,
+                          int64_t *jobs_done_total);
 /* raw device pointers so a caller can run NCCL collectives on the pool / flag without staging through the host */
 int gpsat_device_ptrs(gpsat_t *h, void **pool_words, void **pool_cursor, void **stop_flag, void **stream);
 

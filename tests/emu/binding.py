@@ -22,7 +22,8 @@ class SolveParams(C.Structure):
                 ("restart_factor", C.c_float), ("max_iterations", C.c_int32), ("stop_on_sat", C.c_int32),
                 ("share_learnts", C.c_int32), ("share_max_len", C.c_int32), ("max_learnts_first", C.c_int32),
                 ("learnt_refs_cap", C.c_int32), ("max_conflicts", C.c_int64), ("arena_words", C.c_int64),
-                ("implied_stride", C.c_int64), ("dynamic_split", C.c_int32), ("split_force", C.c_int32)]
+                ("implied_stride", C.c_int64), ("dynamic_split", C.c_int32), ("split_force", C.c_int32),
+                ("split_gap", C.c_int32), ("split_burst", C.c_int32)]
 
 
 def build(force=False):
@@ -41,7 +42,7 @@ def _p(a):
 def run(n_vars, offsets, lits, cube_offsets, cube_lits, *, mode=0, decision=1, restart_first=100, restart_factor=1.3,
         max_iterations=0, max_conflicts=0, max_learnts_first=None, learnt_refs_cap=16384, arena_words=1 << 19,
         stop_on_sat=True, share_learnts=0, share_max_len=8, pool=None, pool_cursor=None, dynamic_split=0,
-        split_force=0):
+        split_force=0, split_gap=8, split_burst=4, budget_ticks=0):
     build()
     lib = C.CDLL(SO)
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
@@ -54,20 +55,22 @@ def run(n_vars, offsets, lits, cube_offsets, cube_lits, *, mode=0, decision=1, r
         max_learnts_first = max(min(max(m // 3, 300), learnt_refs_cap - n_vars - 2), 1)
     P = SolveParams(mode, decision, 0, restart_first, restart_factor, max_iterations, 1 if stop_on_sat else 0,
                     share_learnts, share_max_len, max_learnts_first, learnt_refs_cap, max_conflicts, arena_words,
-                    n_vars, dynamic_split, split_force)
+                    n_vars, dynamic_split, split_force, split_gap, split_burst)
     rec = np.zeros(n_cubes, dtype=RECORD_DTYPE)
     model = np.zeros(max(n_vars, 1), dtype=np.uint8)
     sat_job = C.c_int32(-1)
+    launches = C.c_int32(0)
     implied = np.full(max(n_cubes * n_vars, 1), -1, dtype=np.int32)
     n_implied = np.zeros(n_cubes, dtype=np.int32)
     confl = np.full(n_cubes, -1, dtype=np.int64)
     if pool is None:
         pool = np.zeros(1 << 16, dtype=np.int32)
-        pool_cursor = np.zeros(2, dtype=np.int32)
+        pool_cursor = np.zeros(4, dtype=np.int32)
     rc = lib.gpsat_emu_run(C.c_int32(n_vars), C.c_int64(m), _p(offsets), _p(lits), C.byref(P), C.c_int32(n_cubes),
                            _p(co), _p(cl), _p(rec), _p(model), C.byref(sat_job), _p(implied), _p(n_implied), _p(confl),
-                           _p(pool), _p(pool_cursor), C.c_int32(len(pool)))
+                           _p(pool), _p(pool_cursor), C.c_int32(len(pool)), C.c_uint64(budget_ticks),
+                           C.byref(launches))
     assert rc == 0, rc
-    return {"records": rec, "sat_job": sat_job.value, "model": model[:n_vars],
+    return {"launches": launches.value, "records": rec, "sat_job": sat_job.value, "model": model[:n_vars],
             "implied": implied.reshape(n_cubes, n_vars) if n_vars else implied, "n_implied": n_implied,
             "conflict_clause": confl, "pool": pool, "pool_cursor": pool_cursor}

@@ -11,7 +11,7 @@ extern "C" int gpsat_emu_run(int32_t n_vars, int64_t n_clauses, const int64_t *o
                              const gpsat_solve_params *params, int32_t n_cubes, const int64_t *cube_offsets,
                              const int32_t *cube_lits, gpsat_job_record *records, uint8_t *model, int32_t *sat_job,
                              int32_t *implied, int32_t *n_implied, int64_t *conflict_clause, int32_t *pool,
-                             int32_t *pool_cursor, int32_t pool_cap_words)
+                             int32_t *pool_cursor, int32_t pool_cap_words, uint64_t budget_ticks, int32_t *n_launches)
 {
     gpsat_host::DeviceFormula D;
     int rc = gpsat_host::build_device_formula(n_vars, n_clauses, offsets, lits, D);
@@ -53,12 +53,14 @@ extern "C" int gpsat_emu_run(int32_t n_vars, int64_t n_clauses, const int64_t *o
     B.pool_cursor = pool_cursor;
     B.pool_cap_words = pool_cap_words;
     std::memset(records, 0, sizeof(gpsat_job_record) * (size_t)n_cubes);
-    std::vector<int32_t> dq_lits((size_t)GPSAT_DQ_CAP * GPSAT_DQ_MAXK, 0), dq_meta((size_t)GPSAT_DQ_CAP * 2, 0);
+    std::vector<int32_t> dq_lits((size_t)GPSAT_DQ_CAP * GPSAT_DQ_MAXK, 0), dq_meta((size_t)GPSAT_DQ_CAP * 4, 0);
+    for (int i = 0; i < GPSAT_DQ_CAP; i++) dq_meta[4 * (size_t)i + 2] = i;
     std::vector<int32_t> root_pending((size_t)n_cubes, 1), root_flag((size_t)n_cubes, 0);
-    int32_t dq_ctrl[4] = {0, 0, n_cubes, 0};
+    int32_t dq_ctrl[8] = {0, 0, n_cubes, 0, 0, 0, 0, 0};
     B.dq_lits = dq_lits.data();
     B.dq_meta = dq_meta.data();
     B.dq_ctrl = dq_ctrl;
+    B.dq_cap = GPSAT_DQ_CAP;
     B.root_pending = root_pending.data();
     B.hand_words = 1 + 2 * n_vars + GPSAT_HAND_CLAUSE_WORDS;
     std::vector<int32_t> dq_hand(P.dynamic_split ? (size_t)GPSAT_DQ_CAP * B.hand_words : 1, 0);
@@ -66,8 +68,18 @@ extern "C" int gpsat_emu_run(int32_t n_vars, int64_t n_clauses, const int64_t *o
     B.root_flag = root_flag.data();
     WarpSolver S;
     std::memset(&S, 0, sizeof(S));
-    gpsat_bind(S, F, P, Ly, state.data(), arena.data(), B);
-    gpsat_warp_loop(S, P, B);
+    // budgeted steps: relaunch the warp program until nothing is outstanding (≙ gpsat_solve_step in a loop)
+    unsigned long long t0 = 0;
+    B.t0 = &t0;
+    B.budget_ns = budget_ticks;
+    int launches = 0;
+    do {
+        t0 = gpsat_now_ns();
+        gpsat_bind(S, F, P, Ly, state.data(), arena.data(), B);
+        gpsat_warp_loop(S, P, B);
+        launches++;
+    } while (budget_ticks && dq_ctrl[2] > 0 && !stop_flag && launches < 100000);
+    if (n_launches) *n_launches = launches;
     for (int j = 0; j < n_cubes; j++) records[j].status = gpsat_root_status(root_flag[j], root_pending[j]);
     return 0;
 }

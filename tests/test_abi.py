@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_header():
     assert ctypes.sizeof(binding.GpsatOpts) == binding.default_opts().struct_size
     assert binding.RECORD_DTYPE.itemsize == 80
-    assert ctypes.sizeof(binding.GpsatStats) == 14 * 8 + 8 + 6 * 4
+    assert ctypes.sizeof(binding.GpsatStats) == 14 * 8 + 8 + 6 * 4 + 8 + 8 + 8
 
 
 def test_no_cpu_fallback(request):

@@ -106,18 +106,15 @@ def test_pool_import_and_publish():
     base = emu.run(60, pre.offsets, pre.lits, co, cl, stop_on_sat=False)
     first = emu.run(60, pre.offsets, pre.lits, co, cl, stop_on_sat=False, share_learnts=1, share_max_len=6)
     assert np.array_equal(base["records"]["status"], first["records"]["status"])
-    words = first["pool"][: first["pool_cursor"][0]]
-    assert first["pool_cursor"][1] > 0
+    slots = first["pool"][: 16 * first["pool_cursor"][0]].reshape(-1, 16)   # fixed 16-word slots [len, lit0 ...]
+    assert first["pool_cursor"][1] > 0 and first["pool_cursor"][1] == first["pool_cursor"][0]
     o = Oracle(60, pre.offsets, pre.lits)
-    at, checked = 0, 0
-    while at < len(words) and checked < 25:
-        ln = int(words[at])
-        clause = words[at + 1: at + 1 + ln]
-        neg = np.array([x ^ 1 for x in clause], dtype=np.int32)       # formula AND not(clause) must be UNSAT
+    for rec in slots[:25]:
+        ln = int(rec[0])
+        assert 1 <= ln <= 6
+        neg = np.array([x ^ 1 for x in rec[1: 1 + ln]], dtype=np.int32)   # formula AND not(clause) must be UNSAT
         r = o.run(np.array([0, ln], dtype=np.int64), neg)
         assert r["records"]["status"][0] == g.UNSAT
-        at += ln + 1
-        checked += 1
     again = emu.run(60, pre.offsets, pre.lits, co, cl, stop_on_sat=False, share_learnts=1, share_max_len=6,
                     pool=first["pool"], pool_cursor=first["pool_cursor"])
     assert np.array_equal(base["records"]["status"], again["records"]["status"])
@@ -142,3 +139,20 @@ def test_dynamic_split_keeps_verdicts():
         # without the hook (nobody is ever idle in the one-warp emulator) the run is identical to no splitting
         quiet_split = emu.run(n, pre.offsets, pre.lits, co, cl, stop_on_sat=False, dynamic_split=1)
         assert same(base["records"], quiet_split["records"]) == []
+
+
+def test_budgeted_steps_suspend_and_resume():
+    """gpsat_solve_step with a budget: a cube that outlives the step parks itself in the ring (cube, VSIDS counters,
+    level-0 facts, newest learnt clauses) and a later launch resumes it; verdicts are those of the unbudgeted run."""
+    for n, m, seed, bt in ((100, 426, 0, (1, 1)), (120, 511, 1, (1, 2)), (100, 426, 3, (1, 8))):
+        offs, lits = random_ksat(n, m, seed)
+        pre = g.Cnf.from_arrays(offs, lits).preprocess()
+        cubes = pre.choose_cubes(*bt)
+        co, cl = cube_csr(cubes)
+        base = emu.run(n, pre.offsets, pre.lits, co, cl, stop_on_sat=False)
+        stepped = emu.run(n, pre.offsets, pre.lits, co, cl, stop_on_sat=False, dynamic_split=1, budget_ticks=3)
+        assert np.array_equal(base["records"]["status"], stepped["records"]["status"])
+        if base["records"]["conflicts"].max() > 64:
+            assert stepped["launches"] > 1          # at least one job was parked and resumed by a later launch
+        if stepped["sat_job"] >= 0:
+            assert check_model(pre.offsets, pre.lits, stepped["model"])

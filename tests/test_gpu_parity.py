@@ -195,3 +195,73 @@ def test_config4_large_database_sample():
         want = o.run(co[j: j + 2] - co[j], cl[co[j]: co[j + 1]], mode=2, implied_stride=stride)
         assert want["records"]["status"][0] == g.UNDEF
         assert set(got["implied"][j, : got["n_implied"][j]].tolist()) == set(want["implied"][0, : want["n_implied"][0]].tolist())
+
+
+def test_budgeted_steps_and_device_exchange():
+    """Two handles on one GPU play two ranks: cubes sharded j mod 2, budgeted steps (unfinished cubes park and resume),
+    one exchange block per rank packed on the device, 'all-gathered' with torch.cat, unpacked into the other handle's
+    foreign pool.  Every cube ends with the oracle's status; clauses crossed; every received clause is implied."""
+    import torch
+    from gpupsat_b200 import multi_gpu as mg
+    offs, lits = random_ksat(150, 639, 2)
+    cnf, pre = _prep(offs, lits)
+    cubes = pre.choose_cubes(1, 4)
+    k = cubes.shape[1]
+    want = Oracle(cnf.n_vars, pre.offsets, pre.lits).run(np.arange(0, cubes.size + 1, k, dtype=np.int64),
+                                                          cubes.reshape(-1), stop_on_sat=False)
+    words = mg.block_words(256)
+    dev = torch.device("cuda", 0)
+    solvers = [g.Solver(cnf.n_vars, pre.offsets, pre.lits, stop_on_sat=0, share_learnts=1, share_max_len=8)
+               for _ in range(2)]
+    blocks = [torch.zeros(words, dtype=torch.int32, device=dev) for _ in range(2)]
+    for r, s in enumerate(solvers):
+        s.set_cubes(mg.shard_cubes(cubes, r, 2))
+        s.solve_begin()
+    epochs, imported = 0, [0, 0]
+    while True:
+        for r, s in enumerate(solvers):
+            done, verdict = s.solve_step(budget_ms=0.5)
+            s.exchange_pack(blocks[r], r, done, verdict)
+        gathered = torch.cat(blocks)
+        torch.cuda.synchronize()
+        infos = [s.exchange_unpack(gathered, 2, r) for r, s in enumerate(solvers)]
+        assert infos[0]["all_done"] == infos[1]["all_done"] and infos[0]["sat_rank"] == infos[1]["sat_rank"]
+        imported = [imported[r] + infos[r]["imported_clauses"] for r in range(2)]
+        epochs += 1
+        assert epochs < 5000
+        if infos[0]["all_done"]:
+            break
+    g_host = gathered.cpu().numpy().reshape(2, -1)
+    assert (g_host[:, 0] == mg.MAGIC).all()
+    for r, s in enumerate(solvers):
+        verdict, model, stats = s.solve_end()
+        rec = s.job_records()
+        assert np.array_equal(rec["status"], want["records"]["status"][r::2])
+        assert stats["jobs_done"] == len(rec)
+        assert stats["foreign_clauses"] == imported[r]
+        if verdict == g.SAT:
+            assert check_model(pre.offsets, pre.lits, model)
+        s.close()
+    assert epochs > 1 and sum(imported) > 0
+
+
+def test_exchanged_clauses_are_implied():
+    """every clause a handle exports (host-staged gpsat_pool_export) is refuted-when-negated by the oracle"""
+    offs, lits = random_ksat(100, 426, 0)
+    cnf, pre = _prep(offs, lits)
+    cubes = pre.choose_cubes(1, 2)
+    with g.Solver(cnf.n_vars, pre.offsets, pre.lits, stop_on_sat=0, share_learnts=1, share_max_len=6) as s:
+        s.set_cubes(cubes)
+        s.solve()
+        words = s.pool_export()
+        assert len(s.pool_export()) == 0            # the export mark advanced
+    o = Oracle(cnf.n_vars, pre.offsets, pre.lits)
+    at, checked = 0, 0
+    assert len(words) > 0
+    while at < len(words) and checked < 40:
+        ln = int(words[at])
+        assert 1 <= ln <= 6
+        neg = (words[at + 1: at + 1 + ln] ^ 1).astype(np.int32)
+        assert o.run(np.array([0, ln], dtype=np.int64), neg)["records"]["status"][0] == g.UNSAT
+        at += ln + 1
+        checked += 1

@@ -19,6 +19,6 @@ for spec in sys.argv[1:] or [""]:
         d = json.loads(out.stdout.strip().splitlines()[-1])
         print(f"[{spec}] warps/block {d['launch']['warps_per_block']} blocks {d['launch']['blocks']} "
               f"ms/step {d['ms_per_step']:.2f} impl/s {d['value']:.3e} impl/step {d['implications_per_step']:.3e} "
-              f"confl/s {d['conflicts_per_sec']:.3e} e2e_ms {d['e2e']['ms_per_step']:.2f} {d['verdict']}", flush=True)
+              f"confl/s {d['conflicts_per_sec']:.3e} busy {d['launch']['warp_busy_frac']:.2f} splits {d['launch']['splits_per_step']:.0f} e2e_ms {d['e2e']['ms_per_step']:.2f} {d['verdict']}", flush=True)
     except Exception as e:
         print(f"[{spec}] FAILED {e}: {out.stdout[-500:]} {out.stderr[-1500:]}", flush=True)
