@@ -99,6 +99,7 @@ def lib():
     L.gpsat_exchange_pack.argtypes = [vp, vp, i64, i32, i32, i32]
     L.gpsat_exchange_unpack.argtypes = [vp, vp, i32, i32, i64, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32),
                                         C.POINTER(i64), C.POINTER(i64)]
+    L.gpsat_debug_ctrl.argtypes = [vp, vp]
     L.gpsat_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     _lib = L
     return L
@@ -300,6 +301,11 @@ class Solver:
         st = GpsatStats()
         _check(lib().gpsat_solve_end(self.h, C.byref(verdict), _p(model), C.byref(st)))
         return verdict.value, model[: self.n_vars], st.as_dict()
+
+    def debug_ctrl(self):
+        out = np.zeros(16, dtype=np.int32)
+        _check(lib().gpsat_debug_ctrl(self.h, _p(out)))
+        return out
 
     def request_stop(self):
         _check(lib().gpsat_request_stop(self.h))

@@ -77,6 +77,8 @@ struct WarpSolver {
     int pool_cap_words;
     const int *xpool;     // clauses received from the other GPUs (same slot format, filled between launches)
     const int *xpool_cursor;
+    int pool_mark, xpool_mark;   // slots of the two pools this job has already imported
+    int *park;                   // this warp's parking block (budgeted steps), see park_job()
     // counters (uniform) + per-lane counters
     long long c_decisions, c_implications, c_conflicts, c_learnt_clauses, c_learnt_literals, c_restarts;
     unsigned long long c_hash;
@@ -741,7 +743,9 @@ struct WarpSolver {
     }
 
     // ---- job -------------------------------------------------------------------------------------------------
-    GPSAT_DEV void reset_job()
+    // keep_learnts: a parked job resumes in this warp — its learnt clauses, their watch vectors and the VSIDS counters
+    // are still in place (every watch is legal on an empty trail); only the per-job assignment state starts over
+    GPSAT_DEV void reset_job(bool keep_learnts = false)
     {
         GPSAT_LANE_DECL
         LANES
@@ -751,7 +755,7 @@ struct WarpSolver {
                 seen[v] = 0;
             }
             for (int w = lane; w < wbits_words; w += 32) wbits[w] = wbits0[w];
-            if (use_learnts) {
+            if (use_learnts && !keep_learnts) {
                 for (int x = lane; x < 2 * n_vars; x += 32) {
                     vs[x] = vsids0[x];
                     lw_size[x] = 0;
@@ -763,12 +767,15 @@ struct WarpSolver {
             LV(l_words) = 0;
         }
         trail_size = qhead = dlevel = 0;
-        arena_top = clause_base;
-        watch_bot = arena_words;
-        n_learnts = 0;
-        conflicts_since_restart = 0;
-        restart_limit = restart_first;
-        vs_clauses = n_clauses;
+        if (!keep_learnts) {
+            arena_top = clause_base;
+            watch_bot = arena_words;
+            n_learnts = 0;
+            conflicts_since_restart = 0;
+            restart_limit = restart_first;
+            vs_clauses = n_clauses;
+            pool_mark = xpool_mark = 0;
+        }
         oom = 0;
         c_decisions = c_implications = c_conflicts = c_learnt_clauses = c_learnt_literals = c_restarts = 0;
         c_hash = 0;
@@ -784,16 +791,22 @@ struct WarpSolver {
     {
         if (!share_learnts) return GPSAT_UNDEF;
         const int cap_slots = pool_cap_words / GPSAT_POOL_SLOT_WORDS;
-        if (pool != nullptr) {
+        if (pool != nullptr) {   // slots [pool_mark, used): a resumed job only looks at what arrived since it parked
             int used = gpsat_ld_volatile(pool_cursor);
             if (used > cap_slots) used = cap_slots;
-            const int st = import_records(pool, used * GPSAT_POOL_SLOT_WORDS, GPSAT_POOL_SLOT_WORDS);
+            const int from = pool_mark < used ? pool_mark : used;
+            pool_mark = used;
+            const int st = import_records(pool + from * GPSAT_POOL_SLOT_WORDS, (used - from) * GPSAT_POOL_SLOT_WORDS,
+                                          GPSAT_POOL_SLOT_WORDS);
             if (st != GPSAT_UNDEF) return st;
         }
         if (xpool != nullptr) {
             int used = gpsat_ld_volatile(xpool_cursor);
             if (used > cap_slots) used = cap_slots;
-            const int st = import_records(xpool, used * GPSAT_POOL_SLOT_WORDS, GPSAT_POOL_SLOT_WORDS);
+            const int from = xpool_mark < used ? xpool_mark : used;
+            xpool_mark = used;
+            const int st = import_records(xpool + from * GPSAT_POOL_SLOT_WORDS, (used - from) * GPSAT_POOL_SLOT_WORDS,
+                                          GPSAT_POOL_SLOT_WORDS);
             if (st != GPSAT_UNDEF) return st;
         }
         return GPSAT_UNDEF;
@@ -809,7 +822,7 @@ struct WarpSolver {
             const int len = gpsat_ld_volatile(pool + at);
             if (stride == 0 && (len <= 0 || at + 1 + len > used)) break;
             if (len == 1) {
-                const int u = pool[at + 1];
+                const int u = gpsat_ld_cg(pool + at + 1);
                 const int v = lit_value(u);
                 if (v == 0) return GPSAT_UNSAT;
                 if (v == 2) enqueue(u, GPSAT_REASON_NONE);
@@ -826,7 +839,7 @@ struct WarpSolver {
                 LANEVAR(int, v);
                 LANES
                 {
-                    LV(x) = lane < len ? pool[at + 1 + lane] : 0;
+                    LV(x) = lane < len ? gpsat_ld_cg(pool + at + 1 + lane) : 0;
                     LV(v) = lane < len ? lit_value(LV(x)) : 0;
                 }
                 const unsigned in = len == 32 ? 0xffffffffu : ((1u << len) - 1u);
@@ -1014,43 +1027,96 @@ struct WarpSolver {
         return k + 1;
     }
 
-    // Budgeted steps (gpsat_solve_step): park this job in the ring — same cube, VSIDS counters, level-0 facts and the
-    // newest learnt clauses — so that the kernel can end and the host can run the epoch's exchange; a warp of the
-    // next launch picks it up.  Returns false when the ring is full (the job then simply keeps running).
-    GPSAT_DEV bool suspend(int k)
+    // Budgeted steps (gpsat_solve_step): when the step's budget is spent the job parks itself so that the kernel can
+    // end and the host can run the epoch's exchange.  Everything expensive stays where it is — the learnt clauses and
+    // their watch vectors in this warp's arena — and the parking block only records the cube, the level-0 facts, the
+    // VSIDS counters and a few scalars; the same warp of the next launch resumes from there (a restart that loses
+    // nothing).  Block layout: [valid, root, k, n_facts, n_learnts, arena_top, watch_bot, max_learnts, vs_clauses,
+    // restart_limit, conflicts_since_restart, pool_mark, xpool_mark, -, -, -][cube 64][facts n][vs 2n]
+    GPSAT_DEV void park_job(int k)
     {
-        int ticket = 0;
-        const int slot = dq_acquire(ticket);
-        if (slot < 0) return false;
-        dq_fill_and_publish(slot, ticket, k, -1);
-        return true;
+        GPSAT_LANE_DECL
+        const int n0 = dlevel > 0 ? trail_lim[0] : trail_size;
+        LANES
+        {
+            for (int i = lane; i < k; i += 32) park[16 + i] = cube_buf[i];
+            for (int i = lane; i < n0; i += 32) park[16 + GPSAT_DQ_MAXK + i] = trail[i];
+            for (int x = lane; x < 2 * n_vars; x += 32) park[16 + GPSAT_DQ_MAXK + n_vars + x] = vs[x];
+        }
+        LANE0
+        {
+            park[1] = root;
+            park[2] = k;
+            park[3] = n0;
+            park[4] = n_learnts;
+            park[5] = arena_top;
+            park[6] = watch_bot;
+            park[7] = max_learnts;
+            park[8] = vs_clauses;
+            park[9] = restart_limit;
+            park[10] = conflicts_since_restart;
+            park[11] = pool_mark;
+            park[12] = xpool_mark;
+        }
+        SYNCWARP();
+        gpsat_threadfence();
+        LANE0 { ((volatile int *)park)[0] = 1; }
+        SYNCWARP();
     }
 
     GPSAT_DEV int run_job(const int *cube, int k, int mode, volatile const int *stop_flag, int &conflict_out,
-                          const int *hand)
+                          const int *hand, bool resume)
     {
         GPSAT_LANE_DECL
         conflict_out = GPSAT_NO_CONFLICT;
-        reset_job();
+        reset_job(resume);
+        if (resume) {   // parked by this warp at the end of the previous step (see park_job)
+            n_learnts = park[4];
+            arena_top = park[5];
+            watch_bot = park[6];
+            max_learnts = park[7];
+            vs_clauses = park[8];
+            restart_limit = park[9];
+            conflicts_since_restart = park[10];
+            pool_mark = park[11];
+            xpool_mark = park[12];
+            cube = park + 16;
+            const int n0 = park[3];
+            LANES
+            {
+                for (int x = lane; x < 2 * n_vars; x += 32) vs[x] = park[16 + GPSAT_DQ_MAXK + n_vars + x];
+            }
+            SYNCWARP();
+            for (int i = 0; i < n0; ++i) {
+                const int u = park[16 + GPSAT_DQ_MAXK + i];
+                const int v = lit_value(u);
+                if (v == 0) return GPSAT_UNSAT;
+                if (v == 2) enqueue(u, GPSAT_REASON_NONE);
+            }
+        }
         const bool queued_ok = mode == GPSAT_MODE_SOLVE && dynamic_split;
         const bool may_split = queued_ok && k + 1 < GPSAT_DQ_MAXK;
         int want_split = 0, burst = 0;
         long long last_split_at = 0;
-        if (queued_ok) {   // the cube may grow (splits) or be re-queued (budgeted steps): work on a private copy
+        if (queued_ok) {   // the cube may grow (splits) or be parked (budgeted steps): work on a private copy
             LANES
             {
-                for (int i = lane; i < k; i += 32) cube_buf[i] = cube[i];
+                for (int i = lane; i < k; i += 32) cube_buf[i] = gpsat_ld_cg(cube + i);
             }
             SYNCWARP();
             cube = cube_buf;
         }
+        if (resume) {
+            LANE0 { ((volatile int *)park)[0] = 0; }
+            SYNCWARP();
+        }
         if (hand != nullptr) {   // popped from the ring: inherit the parent's counters, facts and newest clauses
             LANES
             {
-                for (int x = lane; x < 2 * n_vars; x += 32) vs[x] = hand[1 + x];
+                for (int x = lane; x < 2 * n_vars; x += 32) vs[x] = gpsat_ld_cg(hand + 1 + x);
             }
             SYNCWARP();
-            const int st = import_records(hand + 1 + 2 * n_vars, hand[0], 0);
+            const int st = import_records(hand + 1 + 2 * n_vars, gpsat_ld_cg(hand), 0);
             release_slot();
             if (st != GPSAT_UNDEF) return st;
         }
@@ -1089,7 +1155,10 @@ struct WarpSolver {
                         LANEVAR(int, late_v);
                         LANES { LV(late_v) = 0; }
                         LANE0 { LV(late_v) = gpsat_now_ns() > *t0 + budget_ns ? 1 : 0; }
-                        if (SHFL(late_v, 0) && suspend(k)) return GPSAT_JOB_SUSPENDED;
+                        if (SHFL(late_v, 0) && park != nullptr) {
+                            park_job(k);
+                            return GPSAT_JOB_SUSPENDED;
+                        }
                     }
                 }
                 if (may_split && !want_split && c_conflicts - last_split_at >= split_gap && demand_hint() > 0) {
@@ -1158,8 +1227,10 @@ struct WarpSolver {
 // glue shared by the kernel and the test-only emulator: point a WarpSolver at its memory, run one job, record it
 // ---------------------------------------------------------------------------------------------------------------
 GPSAT_DEV void gpsat_bind(WarpSolver &S, const gpsat_formula_view &F, const gpsat_solve_params &P,
-                          const gpsat_state_layout &Ly, int *state, int *arena, const gpsat_run_buffers &B)
+                          const gpsat_state_layout &Ly, int *state, int *arena, int *park, const gpsat_run_buffers &B)
 {
+    S.park = park;
+    S.pool_mark = S.xpool_mark = 0;
     S.n_vars = F.n_vars;
     S.n_clauses = F.n_clauses;
     S.n_lits = F.n_lits;
@@ -1225,14 +1296,14 @@ GPSAT_DEV void gpsat_bind(WarpSolver &S, const gpsat_formula_view &F, const gpsa
 // Runs one job (an original cube, or a child produced by a split) and folds its outcome into the record of the
 // original cube it descends from.
 GPSAT_DEV void gpsat_run_and_record(WarpSolver &S, int root, const int *cube, int k, const int *hand,
-                                    const gpsat_solve_params &P, const gpsat_run_buffers &B)
+                                    const gpsat_solve_params &P, const gpsat_run_buffers &B, bool resume = false)
 {
     GPSAT_LANE_DECL
     int confl;
     S.max_learnts = P.max_learnts_first;
     S.root = root;
     const int job = root;
-    const int status = S.run_job(cube, k, P.mode, B.stop_flag, confl, hand);
+    const int status = S.run_job(cube, k, P.mode, B.stop_flag, confl, hand, resume);
 
     const long long watchers = LANE_SUM_I64(S.l_watchers) + S.c_lwatchers;
     const long long words = LANE_SUM_I64(S.l_words) + S.c_lwords;
@@ -1320,11 +1391,14 @@ GPSAT_DEV void gpsat_run_and_record(WarpSolver &S, int root, const int *cube, in
         }
     }
     // this job is closed: one fewer open descendant of the original cube, one fewer outstanding job
+    // (a parked job stays open: the next launch resumes it)
     gpsat_threadfence();
     LANE0
     {
-        gpsat_atomic_add(B.root_pending + job, -1);
-        gpsat_atomic_add(B.dq_ctrl + 2, -1);
+        if (status != GPSAT_JOB_SUSPENDED) {
+            gpsat_atomic_add(B.root_pending + job, -1);
+            gpsat_atomic_add(B.dq_ctrl + 2, -1);
+        }
     }
     SYNCWARP();
 }
@@ -1338,7 +1412,7 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
     int is_idle = 0;
     unsigned long long busy_ns = 0;
     while (true) {
-        LANEVAR(int, kind_v);   // 0 exit, 1 original cube, 2 queued child, 3 wait
+        LANEVAR(int, kind_v);   // 0 exit, 1 original cube, 2 queued child, 3 wait, 4 resume the job this warp parked
         LANEVAR(int, idx_v);
         LANES
         {
@@ -1352,6 +1426,8 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
                 kind = 0;
             } else if (B.budget_ns && gpsat_now_ns() > *B.t0 + B.budget_ns) {
                 kind = 0;
+            } else if (S.park != nullptr && gpsat_ld_volatile(S.park) == 1) {
+                kind = 4;   // this warp parked a job at the end of the previous step
             } else {
                 if (gpsat_ld_volatile(B.next_job) < B.n_cubes) {
                     idx = gpsat_atomic_add(B.next_job, 1);
@@ -1398,14 +1474,16 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
             LANE0 { gpsat_atomic_add(B.dq_ctrl + 3, -1); }
         }
         const unsigned long long t_job = gpsat_now_ns();
-        if (kind == 1) {
+        if (kind == 4) {
+            gpsat_run_and_record(S, S.park[1], S.park + 16, S.park[2], nullptr, P, B, true);
+        } else if (kind == 1) {
             const long long c0 = B.cube_offsets[idx], c1 = B.cube_offsets[idx + 1];
             gpsat_run_and_record(S, idx, B.cube_lits + c0, (int)(c1 - c0), nullptr, P, B);
         } else {
             const int slot = idx & (B.dq_cap - 1);
             gpsat_threadfence();
-            const int root = B.dq_meta[4 * slot];
-            const int len = B.dq_meta[4 * slot + 1];
+            const int root = gpsat_ld_cg(B.dq_meta + 4 * slot);
+            const int len = gpsat_ld_cg(B.dq_meta + 4 * slot + 1);
             const int *hand = B.dq_hand + (long long)slot * B.hand_words;
             S.rel_slot = slot;
             S.rel_seq = idx + B.dq_cap;   // the ticket that may write this slot next

@@ -29,23 +29,89 @@ using gpsat_host::set_error;
         }                                                                                            \
     } while (0)
 
+// Big device buffers (per-warp arenas, hand-off blocks, pools: hundreds of MB) are recycled through a small
+// process-wide cache, so that create/solve/destroy cycles — one per solve in the end-to-end path — do not pay
+// cudaMalloc/cudaFree for them every time.
+struct CachedBlock {
+    int device;
+    void *p;
+    size_t bytes;
+};
+std::vector<CachedBlock> g_block_cache;
+const size_t kCacheMinBytes = (size_t)1 << 20;
+const size_t kCacheMaxBlocks = 24;
+
+cudaError_t cached_alloc(void **p, size_t bytes, size_t *got)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (bytes >= kCacheMinBytes) {
+        size_t best = g_block_cache.size();
+        for (size_t i = 0; i < g_block_cache.size(); i++) {
+            const CachedBlock &b = g_block_cache[i];
+            if (b.device == dev && b.bytes >= bytes && b.bytes <= 2 * bytes &&
+                (best == g_block_cache.size() || b.bytes < g_block_cache[best].bytes))
+                best = i;
+        }
+        if (best < g_block_cache.size()) {
+            *p = g_block_cache[best].p;
+            *got = g_block_cache[best].bytes;
+            g_block_cache.erase(g_block_cache.begin() + (long)best);
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess && !g_block_cache.empty()) {   // out of memory: drop the cache and retry once
+        for (auto &b : g_block_cache) cudaFree(b.p);
+        g_block_cache.clear();
+        cudaGetLastError();
+        e = cudaMalloc(p, bytes);
+    }
+    *got = bytes;
+    return e;
+}
+
+void cached_free(void *p, size_t bytes)
+{
+    if (!p) return;
+    if (bytes < kCacheMinBytes) {
+        cudaFree(p);
+        return;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (g_block_cache.size() >= kCacheMaxBlocks) {
+        cudaFree(g_block_cache.front().p);
+        g_block_cache.erase(g_block_cache.begin());
+    }
+    g_block_cache.push_back({dev, p, bytes});
+}
+
 template <class T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    size_t bytes = 0;
     ~DevBuf() { release(); }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p) cached_free(p, bytes);
         p = nullptr;
         n = 0;
+        bytes = 0;
     }
     cudaError_t ensure(size_t count)
     {
         if (count <= n && p) return cudaSuccess;
         release();
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
-        if (e == cudaSuccess) n = count;
+        void *q = nullptr;
+        size_t got = 0;
+        cudaError_t e = cached_alloc(&q, std::max<size_t>(count, 1) * sizeof(T), &got);
+        if (e == cudaSuccess) {
+            p = (T *)q;
+            n = count;
+            bytes = got;
+        }
         return e;
     }
     cudaError_t upload(const T *src, size_t count, cudaStream_t s)
@@ -55,15 +121,6 @@ struct DevBuf {
         return cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s);
     }
 };
-
-// The per-warp arenas are the one big allocation (GBs).  Keep the last released one per device so that
-// create/destroy cycles (one per solve in the e2e path) do not pay cudaMalloc/cudaFree of it every time.
-struct ArenaCache {
-    int device = -1;
-    int32_t *p = nullptr;
-    size_t words = 0;
-};
-ArenaCache g_arena_cache;
 
 }  // namespace
 
@@ -98,10 +155,9 @@ struct gpsat {
     DevBuf<int64_t> conflict_clause;
     DevBuf<int32_t> gstate;
     DevBuf<int32_t> pool, pool_cursor, xpool, xpool_cursor;
-    DevBuf<int32_t> dq_lits, dq_meta, dq_ctrl, root_pending, root_flag, dq_hand;
+    DevBuf<int32_t> dq_lits, dq_meta, dq_ctrl, root_pending, root_flag, dq_hand, park;
     std::vector<int32_t> root_pending_h, root_flag_h;
-    int32_t *arena = nullptr;
-    size_t arena_total_words = 0;
+    DevBuf<int32_t> arena;
     // geometry
     gpsat_state_layout Ly{};
     int blocks = 0, warps_per_block = 0, state_in_smem = 0, formula_in_smem = 0, formula_smem_words = 0;
@@ -267,27 +323,10 @@ int ensure_run_buffers(gpsat *h, int mode)
         CU(h->dq_meta.ensure((size_t)GPSAT_DQ_CAP * 4));
         CU(h->dq_hand.ensure((size_t)GPSAT_DQ_CAP * (size_t)(1 + 2 * h->D.n_vars + GPSAT_HAND_CLAUSE_WORDS)));
     }
+    if (mode == GPSAT_MODE_SOLVE && h->opts.dynamic_split)
+        CU(h->park.ensure(n_warps * (size_t)gpsat_park_words(h->D.n_vars)));
     if (!h->state_in_smem) CU(h->gstate.ensure(n_warps * (size_t)h->Ly.total_words));
-    if (mode == GPSAT_MODE_SOLVE) {
-        const size_t want = n_warps * (size_t)h->arena_words;
-        if (h->arena_total_words < want) {
-            if (h->arena) cudaFree(h->arena);
-            h->arena = nullptr;
-            h->arena_total_words = 0;
-            if (g_arena_cache.p && g_arena_cache.device == h->device && g_arena_cache.words >= want) {
-                h->arena = g_arena_cache.p;
-                h->arena_total_words = g_arena_cache.words;
-                g_arena_cache = ArenaCache();
-            } else {
-                if (g_arena_cache.p && g_arena_cache.device == h->device) {
-                    cudaFree(g_arena_cache.p);
-                    g_arena_cache = ArenaCache();
-                }
-                CU(cudaMalloc(&h->arena, want * sizeof(int32_t)));
-                h->arena_total_words = want;
-            }
-        }
-    }
+    if (mode == GPSAT_MODE_SOLVE) CU(h->arena.ensure(n_warps * (size_t)h->arena_words));
     return GPSAT_OK;
 }
 
@@ -303,7 +342,7 @@ gpsat_run_buffers make_buffers(gpsat *h, int mode, double budget_ms)
     B.sat_job = h->ctrl.p + 2;
     B.model = h->model.p;
     B.records = h->records.p;
-    B.arena = mode == GPSAT_MODE_SOLVE ? h->arena : nullptr;
+    B.arena = mode == GPSAT_MODE_SOLVE ? h->arena.p : nullptr;
     B.gstate = h->gstate.p;
     B.pool = h->pool.p;
     B.pool_cursor = h->pool_cursor.p;
@@ -323,6 +362,8 @@ gpsat_run_buffers make_buffers(gpsat *h, int mode, double budget_ms)
     B.root_flag = h->root_flag.p;
     B.t0 = h->t0.p;
     B.busy_ns = (long long *)(h->t0.p + 1);
+    B.park = mode == GPSAT_MODE_SOLVE ? h->park.p : nullptr;
+    B.park_words = gpsat_park_words(h->D.n_vars);
     B.budget_ns = budget_ms > 0 ? (unsigned long long)(budget_ms * 1e6) : 0ull;
     return B;
 }
@@ -336,6 +377,7 @@ int reset_ctrl(gpsat *h)
     CU(cudaMemcpyAsync(h->dq_ctrl.p, dq_init, sizeof(dq_init), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemsetAsync(h->records.p, 0, nc * sizeof(gpsat_job_record), h->stream));
     CU(cudaMemsetAsync(h->t0.p, 0, 2 * sizeof(unsigned long long), h->stream));
+    if (h->park.p) CU(cudaMemsetAsync(h->park.p, 0, h->park.n * sizeof(int32_t), h->stream));
     CU(cudaMemsetAsync(h->root_flag.p, 0, nc * sizeof(int32_t), h->stream));
     std::vector<int32_t> ones(nc, 1);
     CU(cudaMemcpyAsync(h->root_pending.p, ones.data(), nc * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
@@ -657,13 +699,6 @@ int gpsat_create(gpsat_t **out, int32_t n_vars, int64_t n_clauses, const int64_t
 void gpsat_destroy(gpsat_t *h)
 {
     if (!h) return;
-    if (h->arena) {
-        if (g_arena_cache.p) cudaFree(g_arena_cache.p);
-        g_arena_cache.p = h->arena;
-        g_arena_cache.words = h->arena_total_words;
-        g_arena_cache.device = h->device;
-        h->arena = nullptr;
-    }
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -943,7 +978,8 @@ int gpsat_pool_export(gpsat_t *h, int32_t *buf, int64_t cap_words, int64_t *n_wo
     std::vector<int32_t> tmp((size_t)(used - mark) * GPSAT_POOL_SLOT_WORDS);
     CU(cudaMemcpy(tmp.data(), h->pool.p + mark * GPSAT_POOL_SLOT_WORDS, tmp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
     int64_t at = 0;
-    for (int64_t sl = 0; sl < used - mark; sl++) {   // fixed slots -> packed records, whole records only
+    const int64_t n_fresh = used - mark;
+    for (int64_t sl = 0; sl < n_fresh; sl++) {   // fixed slots -> packed records, whole records only
         const int32_t *rec = tmp.data() + sl * GPSAT_POOL_SLOT_WORDS;
         const int32_t len = rec[0];
         if (len > 0 && len < GPSAT_POOL_SLOT_WORDS) {
@@ -1061,6 +1097,24 @@ int gpsat_exchange_unpack(gpsat_t *h, const void *dev_blocks, int32_t n_ranks, i
     if (any_undef) *any_undef = undef;
     if (imported_clauses) *imported_clauses = imported;
     if (jobs_done_total) *jobs_done_total = jobs;
+    return GPSAT_OK;
+}
+
+int gpsat_debug_ctrl(gpsat_t *h, int32_t *out16)
+{
+    if (!h || !out16 || !h->ctrl.p || !h->dq_ctrl.p) {
+        set_error("no run buffers");
+        return GPSAT_E_STATE;
+    }
+    // cudaMemcpy on the legacy stream does not wait for the handle's non-blocking stream: usable while a kernel runs
+    CU(cudaMemcpy(out16, h->ctrl.p, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out16 + 4, h->dq_ctrl.p, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    unsigned long long t[2] = {0, 0};
+    CU(cudaMemcpy(t, h->t0.p, sizeof(t), cudaMemcpyDeviceToHost));
+    out16[12] = (int32_t)(t[0] & 0x7fffffff);
+    out16[13] = (int32_t)(t[1] / 1000);
+    out16[14] = h->blocks;
+    out16[15] = h->warps_per_block;
     return GPSAT_OK;
 }
 

@@ -116,6 +116,8 @@ struct gpsat_run_buffers {
     const unsigned long long *t0;     // globaltimer stamp taken right before the launch
     unsigned long long budget_ns;     // warps stop pulling new cubes once now > *t0 + budget_ns (0 = no limit)
     long long *busy_ns;               // sum over warps of the time spent inside jobs (may be null)
+    int32_t *park;                    // n_warps * park_words: per-warp parking blocks of budgeted steps (may be null)
+    int32_t park_words;
 };
 
 // per-warp state block: word offsets of each array (every array starts on a 16-byte boundary)
@@ -142,6 +144,8 @@ static inline void gpsat_make_layout(int32_t n_vars, int64_t n_lits, gpsat_state
 #undef GPSAT_TAKE
     ly->total_words = at;
 }
+
+static inline int32_t gpsat_park_words(int32_t n_vars) { return ((16 + GPSAT_DQ_MAXK + 3 * (n_vars > 0 ? n_vars : 1)) + 3) / 4 * 4; }
 
 // outcome of an original cube from the flags of all jobs that descend from it
 static inline int32_t gpsat_root_status(int32_t flag, int32_t pending)

@@ -62,8 +62,10 @@ gpsat_cdcl_kernel(const gpsat_formula_view F, const gpsat_solve_params P, const 
     else state = B.gstate + (size_t)gwarp * Ly.total_words;
     int *arena = B.arena ? B.arena + (size_t)gwarp * (size_t)P.arena_words : nullptr;
 
+    int *park = B.park ? B.park + (size_t)gwarp * (size_t)B.park_words : nullptr;
+
     WarpSolver S;
-    gpsat_bind(S, Fv, P, Ly, state, arena, B);
+    gpsat_bind(S, Fv, P, Ly, state, arena, park, B);
     gpsat_warp_loop(S, P, B);
 }
 

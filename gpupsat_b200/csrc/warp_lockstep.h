@@ -61,6 +61,7 @@ static inline void gpsat_threadfence() {}
 static inline int gpsat_atomic_max(int *p, int v) { int o = *p; if (v > o) *p = v; return o; }
 static inline void gpsat_atomic_add_ll(long long *p, long long v) { *p += v; }
 static inline int gpsat_ld_volatile(const int *p) { return *(const volatile int *)p; }
+static inline int gpsat_ld_cg(const int *p) { return *p; }
 static inline void gpsat_nanosleep(unsigned) {}
 // emulated clock: one tick per query, so tests can make budgeted steps expire deterministically
 static unsigned long long g_gpsat_emu_clock = 0;
@@ -122,6 +123,9 @@ __device__ __forceinline__ void gpsat_atomic_add_ll(long long *p, long long v)
     atomicAdd((unsigned long long *)p, (unsigned long long)v);
 }
 __device__ __forceinline__ int gpsat_ld_volatile(const int *p) { return *(const volatile int *)p; }
+// L2-coherent load for data another SM wrote during this launch (queue slots, hand-off blocks, pool slots): a line
+// cached in this SM's L1 before the writer published could otherwise be served stale
+__device__ __forceinline__ int gpsat_ld_cg(const int *p) { return __ldcg(p); }
 __device__ __forceinline__ void gpsat_nanosleep(unsigned ns) { __nanosleep(ns); }
 __device__ __forceinline__ unsigned long long gpsat_now_ns()
 {

@@ -221,6 +221,9 @@ int gpsat_exchange_pack(gpsat_t *h, void *dev_block, int64_t block_words, int32_
 int gpsat_exchange_unpack(gpsat_t *h, const void *dev_blocks, int32_t n_ranks, int32_t my_rank, int64_t block_words,
                           int32_t *sat_rank, int32_t *all_done, int32_t *any_undef, int64_t *imported_clauses,
                           int64_t *jobs_done_total);
+/* diagnostics: [next_job, stop_flag, sat_job, -, queue tail, head, outstanding jobs, idle warps, splits in flight, -,-,-,
+ * launch stamp (low bits), busy us, blocks, warps per block]; may be called from another host thread while a step runs */
+int gpsat_debug_ctrl(gpsat_t *h, int32_t *out16);
 /* raw device pointers so a caller can run NCCL collectives on the pool / flag without staging through the host */
 int gpsat_device_ptrs(gpsat_t *h, void **pool_words, void **pool_cursor, void **stop_flag, void **stream);
 

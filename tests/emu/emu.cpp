@@ -69,13 +69,16 @@ extern "C" int gpsat_emu_run(int32_t n_vars, int64_t n_clauses, const int64_t *o
     WarpSolver S;
     std::memset(&S, 0, sizeof(S));
     // budgeted steps: relaunch the warp program until nothing is outstanding (≙ gpsat_solve_step in a loop)
+    std::vector<int32_t> park((size_t)gpsat_park_words(n_vars), 0);
+    B.park = park.data();
+    B.park_words = (int32_t)park.size();
     unsigned long long t0 = 0;
     B.t0 = &t0;
     B.budget_ns = budget_ticks;
     int launches = 0;
     do {
         t0 = gpsat_now_ns();
-        gpsat_bind(S, F, P, Ly, state.data(), arena.data(), B);
+        gpsat_bind(S, F, P, Ly, state.data(), arena.data(), B.park, B);
         gpsat_warp_loop(S, P, B);
         launches++;
     } while (budget_ticks && dq_ctrl[2] > 0 && !stop_flag && launches < 100000);
