@@ -221,11 +221,15 @@ def run_ours(args):
     if os.environ.get("GPSAT_DYNAMIC_SPLIT"):
         extra["dynamic_split"] = int(os.environ["GPSAT_DYNAMIC_SPLIT"])
     for env_name, opt in (("GPSAT_SHARE_LEARNTS", "share_learnts"), ("GPSAT_SPLIT_GAP", "split_gap"),
-                          ("GPSAT_SPLIT_BURST", "split_burst")):
+                          ("GPSAT_SPLIT_BURST", "split_burst"), ("GPSAT_SHARE_MAX_LEN", "share_max_len"),
+                          ("GPSAT_SHARE_IMPORT_MAX", "share_import_max")):
         if os.environ.get(env_name):
             extra[opt] = int(os.environ[env_name])
     if n_gpus > 1:
-        extra.setdefault("share_learnts", 1)        # short learnt clauses ride the per-epoch all-gather
+        # learnt units and binaries ride the per-epoch all-gather; longer clauses were measured to cost more than they
+        # save on this workload (cubes of ~200 conflicts; DESIGN.md "multi-GPU"), GPSAT_SHARE_MAX_LEN overrides
+        extra.setdefault("share_learnts", 1)
+        extra.setdefault("share_max_len", 2)
     solver = g.Solver(cnf.n_vars, offs, lits, device=local_rank, **extra)
     solver.set_cubes(mine)
 

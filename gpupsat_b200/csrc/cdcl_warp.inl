@@ -60,7 +60,7 @@ struct WarpSolver {
     int oom;
     int use_learnts;   // 0 in propagate-only runs: no learnt arena, no VSIDS state
     // params
-    int decision_mode, restart_first, max_iterations, share_learnts, share_max_len;
+    int decision_mode, restart_first, max_iterations, share_learnts, share_max_len, share_import_max;
     float restart_factor;
     long long max_conflicts;
     // dynamic splitting
@@ -77,6 +77,7 @@ struct WarpSolver {
     int pool_cap_words;
     const int *xpool;     // clauses received from the other GPUs (same slot format, filled between launches)
     const int *xpool_cursor;
+    uint8_t *facts;              // per variable: 0 none, 1 false, 2 true — unit clauses learnt by any job on any GPU
     int pool_mark, xpool_mark;   // slots of the two pools this job has already imported
     int *park;                   // this warp's parking block (budgeted steps), see park_job()
     // counters (uniform) + per-lane counters
@@ -523,6 +524,9 @@ struct WarpSolver {
     {
         GPSAT_LANE_DECL
         if (!share_learnts || n_out > share_max_len || n_out >= GPSAT_POOL_SLOT_WORDS || pool == nullptr) return;
+        if (n_out == 1 && facts != nullptr) {
+            LANE0 { ((volatile uint8_t *)facts)[lbuf[0] >> 1] = (uint8_t)(1 + (lbuf[0] & 1)); }
+        }
         LANEVAR(int, off);
         LANES { LV(off) = 0; }
         LANE0 { LV(off) = gpsat_atomic_add(pool_cursor, 1); }
@@ -784,20 +788,122 @@ struct WarpSolver {
         SYNCWARP();
     }
 
-    // Import the shared pool into this job's private database.  Pass 1: unit clauses become level-0 facts and are
-    // propagated; pass 2: longer clauses are attached with two non-false literals in front (or become facts /
-    // refute the formula).  Only records whose header is already published are read.
+    // Attach one foreign clause rec[0..len) (2 <= len <= 32) to this job's private database at the current (root)
+    // level: satisfied clauses are skipped, a clause with one non-false literal becomes a fact, none refutes the job.
+    // returns GPSAT_UNDEF to go on, GPSAT_UNSAT, or GPSAT_JOB_OOM
+    GPSAT_DEV int attach_record(const int *rec, int len)
+    {
+        GPSAT_LANE_DECL
+        LANEVAR(int, x);
+        LANEVAR(int, v);
+        LANES
+        {
+            LV(x) = lane < len ? gpsat_ld_cg(rec + lane) : 0;
+            LV(v) = lane < len ? lit_value(LV(x)) : 0;
+        }
+        const unsigned in = len == 32 ? 0xffffffffu : ((1u << len) - 1u);
+        const unsigned mt = BALLOT(LV(v) == 1) & in;
+        const unsigned mnf = BALLOT(LV(v) != 0) & in;
+        if (mt) return GPSAT_UNDEF;
+        const int nf = gpsat_popc(mnf);
+        if (nf == 0) return GPSAT_UNSAT;
+        LANES
+        {
+            if (lane < len) {
+                const bool isnf = (mnf >> lane) & 1u;
+                const int dst = isnf ? gpsat_popc(mnf & GPSAT_LANEMASK_LT) : nf + gpsat_popc(~mnf & in & GPSAT_LANEMASK_LT);
+                lbuf[dst] = LV(x);
+            }
+        }
+        SYNCWARP();
+        if (nf == 1) {
+            enqueue(lbuf[0], GPSAT_REASON_NONE);
+        } else if (learn(len) == GPSAT_NO_CONFLICT) {
+            return GPSAT_JOB_OOM;
+        }
+        return GPSAT_UNDEF;
+    }
+
+    // room left for foreign clauses: they may take at most half of the arena and a quarter of the clause list
+    GPSAT_DEV bool import_room() const
+    {
+        return (watch_bot - arena_top) >= (arena_words - clause_base) / 2 && n_learnts < refs_cap / 4;
+    }
+
+    // Unit clauses learnt anywhere (this GPU's jobs publish them, the exchange kernels add those of other GPUs) live
+    // in one byte per variable; a job takes them all as level-0 facts when it starts or resumes.
+    GPSAT_DEV int import_facts()
+    {
+        GPSAT_LANE_DECL
+        if (facts == nullptr) return GPSAT_UNDEF;
+        for (int v0 = 0; v0 < n_vars; v0 += 32) {
+            LANEVAR(int, f);
+            LANES
+            {
+                const int v = v0 + lane;
+                LV(f) = v < n_vars ? (int)((volatile const uint8_t *)facts)[v] : 0;
+            }
+            unsigned m = BALLOT(LV(f) != 0);
+            while (m) {
+                const int src = gpsat_ffs(m) - 1;
+                m &= m - 1;
+                const int lit = 2 * (v0 + src) + (SHFL(f, src) - 1);
+                const int v = lit_value(lit);
+                if (v == 0) return GPSAT_UNSAT;
+                if (v == 2) enqueue(lit, GPSAT_REASON_NONE);
+            }
+        }
+        if (propagate() != GPSAT_NO_CONFLICT) return GPSAT_UNSAT;
+        return GPSAT_UNDEF;
+    }
+
+    // Import from slots [from, used) of a pool (fixed 16-word slots, length written last; a slot whose length is
+    // still 0 is being written by another warp and is skipped): the NEWEST clauses of 2..15 literals, at most
+    // share_import_max of them, looking at no more than 64 x 32 slots.  The warp reads 32 slot headers per step.
+    GPSAT_DEV int import_pool(const int *base, int from, int used)
+    {
+        GPSAT_LANE_DECL
+        if (from >= used) return GPSAT_UNDEF;
+        if (used - from > 2048) from = used - 2048;
+        int taken = 0;
+        for (int s0 = used; s0 > from && taken < share_import_max; s0 -= 32) {
+            const int lo = s0 - 32 > from ? s0 - 32 : from;
+            LANEVAR(int, len);
+            LANES
+            {
+                const int sl = s0 - 1 - lane;
+                LV(len) = sl >= lo ? gpsat_ld_cg(base + sl * GPSAT_POOL_SLOT_WORDS) : 0;
+            }
+            unsigned m = BALLOT(LV(len) >= 2 && LV(len) < GPSAT_POOL_SLOT_WORDS);
+            while (m && taken < share_import_max) {
+                const int src = gpsat_ffs(m) - 1;
+                m &= m - 1;
+                if (!import_room()) return propagate() != GPSAT_NO_CONFLICT ? GPSAT_UNSAT : GPSAT_UNDEF;
+                const int sl = s0 - 1 - src;
+                const int st = attach_record(base + sl * GPSAT_POOL_SLOT_WORDS + 1, SHFL(len, src));
+                if (st != GPSAT_UNDEF) return st;
+                taken++;
+            }
+        }
+        if (propagate() != GPSAT_NO_CONFLICT) return GPSAT_UNSAT;
+        return GPSAT_UNDEF;
+    }
+
+    // Import what the two shared pools gained since this job last looked (all of it for a fresh job).
     GPSAT_DEV int pool_import()
     {
         if (!share_learnts) return GPSAT_UNDEF;
         const int cap_slots = pool_cap_words / GPSAT_POOL_SLOT_WORDS;
-        if (pool != nullptr) {   // slots [pool_mark, used): a resumed job only looks at what arrived since it parked
+        {
+            const int st = import_facts();
+            if (st != GPSAT_UNDEF) return st;
+        }
+        if (pool != nullptr) {
             int used = gpsat_ld_volatile(pool_cursor);
             if (used > cap_slots) used = cap_slots;
             const int from = pool_mark < used ? pool_mark : used;
             pool_mark = used;
-            const int st = import_records(pool + from * GPSAT_POOL_SLOT_WORDS, (used - from) * GPSAT_POOL_SLOT_WORDS,
-                                          GPSAT_POOL_SLOT_WORDS);
+            const int st = import_pool(pool, from, used);
             if (st != GPSAT_UNDEF) return st;
         }
         if (xpool != nullptr) {
@@ -805,67 +911,38 @@ struct WarpSolver {
             if (used > cap_slots) used = cap_slots;
             const int from = xpool_mark < used ? xpool_mark : used;
             xpool_mark = used;
-            const int st = import_records(xpool + from * GPSAT_POOL_SLOT_WORDS, (used - from) * GPSAT_POOL_SLOT_WORDS,
-                                          GPSAT_POOL_SLOT_WORDS);
+            const int st = import_pool(xpool, from, used);
             if (st != GPSAT_UNDEF) return st;
         }
         return GPSAT_UNDEF;
     }
 
-    // records = [len, lit0 .. lit(len-1)]: packed back to back (stride 0: hand-off blocks) or one per fixed slot of
-    // `stride` words (the pools; a slot whose length is still 0 is being written by another warp and is skipped)
-    GPSAT_DEV int import_records(const int *pool, int used, int stride)
+    // Hand-off blocks of split cubes: records [len, lit0 .. lit(len-1)] packed back to back in rec[0..used).
+    // Unit records (the parent's level-0 facts) first, then the clauses.
+    GPSAT_DEV int import_records(const int *rec, int used)
     {
-        GPSAT_LANE_DECL
         int at = 0;
         while (at < used) {
-            const int len = gpsat_ld_volatile(pool + at);
-            if (stride == 0 && (len <= 0 || at + 1 + len > used)) break;
+            const int len = gpsat_ld_cg(rec + at);
+            if (len <= 0 || at + 1 + len > used) break;
             if (len == 1) {
-                const int u = gpsat_ld_cg(pool + at + 1);
+                const int u = gpsat_ld_cg(rec + at + 1);
                 const int v = lit_value(u);
                 if (v == 0) return GPSAT_UNSAT;
                 if (v == 2) enqueue(u, GPSAT_REASON_NONE);
             }
-            at += stride ? stride : len + 1;
+            at += len + 1;
         }
         const int end_at = at;
         if (propagate() != GPSAT_NO_CONFLICT) return GPSAT_UNSAT;
         for (at = 0; at < end_at;) {
-            const int len = gpsat_ld_volatile(pool + at);
+            const int len = gpsat_ld_cg(rec + at);
             if (len >= 2 && len <= 32 && len <= lbuf_words) {
-                if ((watch_bot - arena_top) < (arena_words - clause_base) / 2) break;   // keep room for own clauses
-                LANEVAR(int, x);
-                LANEVAR(int, v);
-                LANES
-                {
-                    LV(x) = lane < len ? gpsat_ld_cg(pool + at + 1 + lane) : 0;
-                    LV(v) = lane < len ? lit_value(LV(x)) : 0;
-                }
-                const unsigned in = len == 32 ? 0xffffffffu : ((1u << len) - 1u);
-                const unsigned mt = BALLOT(LV(v) == 1) & in;
-                const unsigned mnf = BALLOT(LV(v) != 0) & in;
-                if (!mt) {
-                    const int nf = gpsat_popc(mnf);
-                    if (nf == 0) return GPSAT_UNSAT;
-                    LANES
-                    {
-                        if (lane < len) {
-                            const bool isnf = (mnf >> lane) & 1u;
-                            const int dst = isnf ? gpsat_popc(mnf & GPSAT_LANEMASK_LT)
-                                                 : nf + gpsat_popc(~mnf & in & GPSAT_LANEMASK_LT);
-                            lbuf[dst] = LV(x);
-                        }
-                    }
-                    SYNCWARP();
-                    if (nf == 1) {
-                        enqueue(lbuf[0], GPSAT_REASON_NONE);
-                    } else if (learn(len) == GPSAT_NO_CONFLICT) {
-                        return GPSAT_JOB_OOM;
-                    }
-                }
+                if (!import_room()) break;
+                const int st = attach_record(rec + at + 1, len);
+                if (st != GPSAT_UNDEF) return st;
             }
-            at += stride ? stride : len + 1;
+            at += len + 1;
         }
         if (propagate() != GPSAT_NO_CONFLICT) return GPSAT_UNSAT;
         return GPSAT_UNDEF;
@@ -1116,7 +1193,7 @@ struct WarpSolver {
                 for (int x = lane; x < 2 * n_vars; x += 32) vs[x] = gpsat_ld_cg(hand + 1 + x);
             }
             SYNCWARP();
-            const int st = import_records(hand + 1 + 2 * n_vars, gpsat_ld_cg(hand), 0);
+            const int st = import_records(hand + 1 + 2 * n_vars, gpsat_ld_cg(hand));
             release_slot();
             if (st != GPSAT_UNDEF) return st;
         }
@@ -1286,11 +1363,13 @@ GPSAT_DEV void gpsat_bind(WarpSolver &S, const gpsat_formula_view &F, const gpsa
     S.max_conflicts = P.max_conflicts;
     S.share_learnts = P.share_learnts;
     S.share_max_len = P.share_max_len;
+    S.share_import_max = P.share_import_max > 0 ? P.share_import_max : 256;
     S.pool = B.pool;
     S.pool_cursor = B.pool_cursor;
     S.pool_cap_words = B.pool_cap_words;
     S.xpool = B.xpool;
     S.xpool_cursor = B.xpool_cursor;
+    S.facts = B.facts;
 }
 
 // Runs one job (an original cube, or a child produced by a split) and folds its outcome into the record of the

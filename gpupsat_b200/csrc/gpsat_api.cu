@@ -155,6 +155,7 @@ struct gpsat {
     DevBuf<int64_t> conflict_clause;
     DevBuf<int32_t> gstate;
     DevBuf<int32_t> pool, pool_cursor, xpool, xpool_cursor;
+    DevBuf<uint8_t> facts;
     DevBuf<int32_t> dq_lits, dq_meta, dq_ctrl, root_pending, root_flag, dq_hand, park;
     std::vector<int32_t> root_pending_h, root_flag_h;
     DevBuf<int32_t> arena;
@@ -179,6 +180,10 @@ const int64_t kPoolSlots = kPoolWords / GPSAT_POOL_SLOT_WORDS;
 
 int ensure_pools(gpsat *h, bool foreign)
 {
+    if (!h->facts.p) {
+        CU(h->facts.ensure((size_t)std::max(h->D.n_vars, 1)));
+        CU(cudaMemsetAsync(h->facts.p, 0, (size_t)std::max(h->D.n_vars, 1), h->stream));
+    }
     if (!h->pool.p) {
         CU(h->pool.ensure((size_t)kPoolWords));
         CU(h->pool_cursor.ensure(4));
@@ -230,7 +235,7 @@ gpsat_solve_params make_params(gpsat *h, int mode, int64_t implied_stride)
     P.max_iterations = h->opts.max_iterations;
     P.stop_on_sat = h->opts.stop_on_sat;
     P.share_learnts = h->opts.share_learnts;
-    P.share_max_len = std::min(h->opts.share_max_len, 32);
+    P.share_max_len = std::min(h->opts.share_max_len, GPSAT_POOL_SLOT_WORDS - 1);
     P.learnt_refs_cap = 16384;
     if (P.learnt_refs_cap < h->D.n_vars + 64) P.learnt_refs_cap = h->D.n_vars + 64;
     P.max_learnts_first = default_max_learnts(h->D.n_clauses, P.learnt_refs_cap, h->D.n_vars);
@@ -241,6 +246,7 @@ gpsat_solve_params make_params(gpsat *h, int mode, int64_t implied_stride)
     P.split_force = 0;
     P.split_gap = h->opts.split_gap > 0 ? h->opts.split_gap : 8;
     P.split_burst = h->opts.split_burst > 0 ? h->opts.split_burst : 4;
+    P.share_import_max = h->opts.share_import_max > 0 ? h->opts.share_import_max : 256;
     return P;
 }
 
@@ -349,6 +355,7 @@ gpsat_run_buffers make_buffers(gpsat *h, int mode, double budget_ms)
     B.pool_cap_words = (int32_t)kPoolWords;
     B.xpool = h->xpool.p;
     B.xpool_cursor = h->xpool_cursor.p;
+    B.facts = h->facts.p;
     B.state_in_smem = h->state_in_smem;
     B.formula_in_smem = h->formula_in_smem;
     B.formula_smem_words = h->formula_smem_words;
@@ -870,6 +877,7 @@ int gpsat_solve_begin(gpsat_t *h)
         CU(cudaMemsetAsync(h->pool_cursor.p, 0, 4 * sizeof(int32_t), h->stream));
         CU(cudaMemsetAsync(h->pool.p, 0, (size_t)kPoolWords * sizeof(int32_t), h->stream));
     }
+    if (h->facts.p) CU(cudaMemsetAsync(h->facts.p, 0, (size_t)std::max(h->D.n_vars, 1), h->stream));
     if (h->xpool.p) {
         CU(cudaMemsetAsync(h->xpool_cursor.p, 0, 4 * sizeof(int32_t), h->stream));
         CU(cudaMemsetAsync(h->xpool.p, 0, (size_t)kPoolWords * sizeof(int32_t), h->stream));
@@ -1017,6 +1025,10 @@ int gpsat_pool_import(gpsat_t *h, const int32_t *buf, int64_t n_words)
                 set_error("pool literal out of range");
                 return GPSAT_E_ARG;
             }
+        if (len == 1) {
+            const uint8_t f = (uint8_t)(1 + (buf[at + 1] & 1));
+            CU(cudaMemcpy(h->facts.p + (buf[at + 1] >> 1), &f, 1, cudaMemcpyHostToDevice));
+        }
         if (len < GPSAT_POOL_SLOT_WORDS) {   // longer clauses do not fit a slot: optional knowledge, dropped
             const size_t o = slots.size();
             slots.resize(o + GPSAT_POOL_SLOT_WORDS, 0);
@@ -1072,7 +1084,7 @@ int gpsat_exchange_unpack(gpsat_t *h, const void *dev_blocks, int32_t n_ranks, i
     int rc = ensure_pools(h, true);
     if (rc != GPSAT_OK) return rc;
     CU(gpsat_kernels::launch_xchg_unpack((const int *)dev_blocks, n_ranks, my_rank, (int)block_words, h->xpool.p,
-                                         h->xpool_cursor.p, (int)kPoolSlots, h->stream));
+                                         h->xpool_cursor.p, (int)kPoolSlots, h->facts.p, h->D.n_vars, h->stream));
     std::vector<int32_t> hdr((size_t)n_ranks * GPSAT_XCHG_HEADER_WORDS);
     CU(cudaMemcpy2DAsync(hdr.data(), GPSAT_XCHG_HEADER_WORDS * sizeof(int32_t), dev_blocks,
                          (size_t)block_words * sizeof(int32_t), GPSAT_XCHG_HEADER_WORDS * sizeof(int32_t), (size_t)n_ranks,

@@ -73,6 +73,7 @@ struct gpsat_solve_params {
     int32_t split_force;         // test hook: split at every restart even when no warp is idle
     int32_t split_gap;           // conflicts a job runs between two rounds of splitting
     int32_t split_burst;         // children handed out per round while warps are idle
+    int32_t share_import_max;    // non-unit clauses a job takes from each shared pool when it starts (newest first)
 };
 
 // word offsets (int32 units) of the per-warp state arrays inside one warp's state block
@@ -101,6 +102,7 @@ struct gpsat_run_buffers {
     int32_t pool_cap_words;
     const int32_t *xpool;          // clauses received from other GPUs (same slot format, may be null)
     const int32_t *xpool_cursor;   // [0] slots used
+    uint8_t *facts;                // n_vars: 0 none, 1 false, 2 true — learnt unit clauses of all GPUs (may be null)
     int32_t state_in_smem;
     int32_t formula_in_smem;       // cl2 / occ2 / ostart staged once per block in front of the warps' state blocks
     int32_t formula_smem_words;    // size of that staging area (multiple of 4 words)

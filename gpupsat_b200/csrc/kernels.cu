@@ -158,7 +158,8 @@ gpsat_xchg_pack_kernel(const int *__restrict__ pool, int *pool_cursor, int pool_
 
 __global__ void __launch_bounds__(256)
 gpsat_xchg_unpack_kernel(const int *__restrict__ blocks, int n_ranks, int my_rank, int block_words,
-                         int *__restrict__ xpool, int *xpool_cursor, int xpool_cap_slots)
+                         int *__restrict__ xpool, int *xpool_cursor, int xpool_cap_slots, unsigned char *facts,
+                         int n_vars)
 {
     // every thread recomputes the (tiny) prefix over ranks; thread 0 publishes the new cursor at the end
     int base = xpool_cursor[0];
@@ -171,6 +172,11 @@ gpsat_xchg_unpack_kernel(const int *__restrict__ blocks, int n_ranks, int my_ran
         const int4 *src = reinterpret_cast<const int4 *>(b + GPSAT_XCHG_HEADER_WORDS);
         int4 *dst = reinterpret_cast<int4 *>(xpool + (size_t)base * GPSAT_POOL_SLOT_WORDS);
         for (int i = (int)threadIdx.x; i < n * (GPSAT_POOL_SLOT_WORDS / 4); i += (int)blockDim.x) dst[i] = src[i];
+        // unit clauses of the other GPU become facts of this one
+        for (int i = (int)threadIdx.x; i < n; i += (int)blockDim.x) {
+            const int *rec = b + GPSAT_XCHG_HEADER_WORDS + (size_t)i * GPSAT_POOL_SLOT_WORDS;
+            if (rec[0] == 1 && facts && rec[1] >= 0 && (rec[1] >> 1) < n_vars) facts[rec[1] >> 1] = (unsigned char)(1 + (rec[1] & 1));
+        }
         base += n;
     }
     __syncthreads();
@@ -227,10 +233,11 @@ cudaError_t launch_xchg_pack(const int *pool, int *pool_cursor, int pool_cap_slo
 }
 
 cudaError_t launch_xchg_unpack(const int *blocks, int n_ranks, int my_rank, int block_words, int *xpool,
-                               int *xpool_cursor, int xpool_cap_slots, cudaStream_t stream)
+                               int *xpool_cursor, int xpool_cap_slots, unsigned char *facts, int n_vars,
+                               cudaStream_t stream)
 {
     gpsat_xchg_unpack_kernel<<<1, 256, 0, stream>>>(blocks, n_ranks, my_rank, block_words, xpool, xpool_cursor,
-                                                    xpool_cap_slots);
+                                                    xpool_cap_slots, facts, n_vars);
     return cudaGetLastError();
 }
 

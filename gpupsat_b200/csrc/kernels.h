@@ -24,7 +24,8 @@ cudaError_t launch_stamp(unsigned long long *t0, cudaStream_t stream);
 cudaError_t launch_xchg_pack(const int *pool, int *pool_cursor, int pool_cap_slots, int *block, int block_words,
                              int rank, int done, int verdict, int jobs_done, cudaStream_t stream);
 cudaError_t launch_xchg_unpack(const int *blocks, int n_ranks, int my_rank, int block_words, int *xpool,
-                               int *xpool_cursor, int xpool_cap_slots, cudaStream_t stream);
+                               int *xpool_cursor, int xpool_cap_slots, unsigned char *facts, int n_vars,
+                               cudaStream_t stream);
 
 // clause evaluation: one thread per (assignment, clause)
 cudaError_t launch_eval_clauses(int32_t n_vars, int32_t n_clauses, const int32_t *coffsets, const int32_t *clits,

@@ -105,7 +105,7 @@ typedef struct gpsat_opts {
     int32_t stop_on_sat;          /* 1: first satisfied cube ends the run (Parallelizer.cu:213-227) */
     int64_t max_conflicts;        /* per job, 0 = none */
     int32_t share_learnts;        /* 1: short 1-UIP clauses go to the per-GPU pool and are imported by later jobs */
-    int32_t share_max_len;        /* longest clause exported to the pool */
+    int32_t share_max_len;        /* longest clause exported to the pool (at most 15: pool slots are 16 words) */
     int32_t warps_per_block;      /* 0 = auto */
     int32_t blocks;               /* 0 = auto (SM count x resident blocks) */
     int64_t arena_words;          /* per-warp learnt-clause arena (int32 words); 0 = auto */
@@ -115,7 +115,8 @@ typedef struct gpsat_opts {
                                      then depend on timing, so parity runs set 0. */
     int32_t split_gap;            /* conflicts a cube runs between two rounds of splitting; 0 = default (8) */
     int32_t split_burst;          /* children handed out per round while warps are idle; 0 = default (4) */
-    int32_t reserved[5];
+    int32_t share_import_max;     /* non-unit shared clauses a cube imports per pool when it starts; 0 = default (256) */
+    int32_t reserved[4];
 } gpsat_opts;
 
 void gpsat_opts_default(gpsat_opts *o);

@@ -23,7 +23,7 @@ class SolveParams(C.Structure):
                 ("share_learnts", C.c_int32), ("share_max_len", C.c_int32), ("max_learnts_first", C.c_int32),
                 ("learnt_refs_cap", C.c_int32), ("max_conflicts", C.c_int64), ("arena_words", C.c_int64),
                 ("implied_stride", C.c_int64), ("dynamic_split", C.c_int32), ("split_force", C.c_int32),
-                ("split_gap", C.c_int32), ("split_burst", C.c_int32)]
+                ("split_gap", C.c_int32), ("split_burst", C.c_int32), ("share_import_max", C.c_int32)]
 
 
 def build(force=False):
@@ -42,7 +42,7 @@ def _p(a):
 def run(n_vars, offsets, lits, cube_offsets, cube_lits, *, mode=0, decision=1, restart_first=100, restart_factor=1.3,
         max_iterations=0, max_conflicts=0, max_learnts_first=None, learnt_refs_cap=16384, arena_words=1 << 19,
         stop_on_sat=True, share_learnts=0, share_max_len=8, pool=None, pool_cursor=None, dynamic_split=0,
-        split_force=0, split_gap=8, split_burst=4, budget_ticks=0):
+        split_force=0, split_gap=8, split_burst=4, budget_ticks=0, share_import_max=256):
     build()
     lib = C.CDLL(SO)
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
@@ -55,7 +55,7 @@ def run(n_vars, offsets, lits, cube_offsets, cube_lits, *, mode=0, decision=1, r
         max_learnts_first = max(min(max(m // 3, 300), learnt_refs_cap - n_vars - 2), 1)
     P = SolveParams(mode, decision, 0, restart_first, restart_factor, max_iterations, 1 if stop_on_sat else 0,
                     share_learnts, share_max_len, max_learnts_first, learnt_refs_cap, max_conflicts, arena_words,
-                    n_vars, dynamic_split, split_force, split_gap, split_burst)
+                    n_vars, dynamic_split, split_force, split_gap, split_burst, share_import_max)
     rec = np.zeros(n_cubes, dtype=RECORD_DTYPE)
     model = np.zeros(max(n_vars, 1), dtype=np.uint8)
     sat_job = C.c_int32(-1)

@@ -52,6 +52,8 @@ extern "C" int gpsat_emu_run(int32_t n_vars, int64_t n_clauses, const int64_t *o
     B.pool = pool;
     B.pool_cursor = pool_cursor;
     B.pool_cap_words = pool_cap_words;
+    std::vector<uint8_t> facts((size_t)(n_vars > 0 ? n_vars : 1), 0);
+    B.facts = facts.data();
     std::memset(records, 0, sizeof(gpsat_job_record) * (size_t)n_cubes);
     std::vector<int32_t> dq_lits((size_t)GPSAT_DQ_CAP * GPSAT_DQ_MAXK, 0), dq_meta((size_t)GPSAT_DQ_CAP * 4, 0);
     for (int i = 0; i < GPSAT_DQ_CAP; i++) dq_meta[4 * (size_t)i + 2] = i;
