@@ -125,6 +125,7 @@ struct WarpSolver {
         const int start = trail_lim[lv];
         LANES
         {
+            GPSAT_NOUNROLL
             for (int i = start + lane; i < trail_size; i += 32) {
                 int v = trail[i] >> 1;
                 val[v] = val0[v];
@@ -151,6 +152,7 @@ struct WarpSolver {
             watch_bot = nptr;
             LANES
             {
+                GPSAT_NOUNROLL
                 for (int i = lane; i < 2 * n; i += 32) arena[nptr + i] = arena[ptr + i];
             }
             SYNCWARP();
@@ -181,6 +183,7 @@ struct WarpSolver {
 
             // (1) original clauses: occurrence slots of f whose watch bit is set
             const int os = gpsat_ld(ostart + f), oe = gpsat_ld(ostart + f + 1);
+            GPSAT_NOUNROLL
             for (int base = os; base < oe; base += 32) {
                 LANEVAR(int, act);    // 0 none, 1 move, 2 unit, 3 conflict
                 LANEVAR(int, alit);   // unit literal, or new occurrence slot for a move
@@ -195,6 +198,7 @@ struct WarpSolver {
                         const gint2 e = gpsat_ld2(occ2 + k);
                         const int s = e.x, len = e.y;
                         int other = -1, other_val = 2, repl = -1, nread = 0;
+                        GPSAT_NOUNROLL
                         for (int i = 0; i < len; ++i) {
                             const gint2 q = gpsat_ld2(cl2 + s + i);
                             nread++;
@@ -261,6 +265,7 @@ struct WarpSolver {
             c_lwatchers += wn;
             int confl = GPSAT_NO_CONFLICT;
             int j = 0;
+            GPSAT_NOUNROLL
             for (int base = 0; base < wn; base += 32) {
                 LANEVAR(int, ecr);
                 LANEVAR(int, ebl);
@@ -309,6 +314,7 @@ struct WarpSolver {
                         continue;
                     }
                     int found = -1;
+                    GPSAT_NOUNROLL
                     for (int b2 = 2; b2 < len && found < 0; b2 += 32) {
                         const unsigned mm = BALLOT((b2 + lane < len) && lit_value(cl[b2 + lane]) != 0);
                         c_lwords += (len - b2) < 32 ? (len - b2) : 32;
@@ -377,6 +383,7 @@ struct WarpSolver {
             const bool orig = confl >= 0;
             const int s = orig ? confl : GPSAT_LEARNT_OFF(confl) + 1;
             const int len = orig ? gpsat_ld2(cl2 + s - 1).x : arena[s - 1];
+            GPSAT_NOUNROLL
             for (int b = 0; b < len; b += 32) {
                 LANEVAR(int, q);
                 LANEVAR(int, kind);   // 1: current level (path), 2: lower level (goes to the clause)
@@ -431,6 +438,7 @@ struct WarpSolver {
             LANES
             {
                 LV(best) = -1;
+                GPSAT_NOUNROLL
                 for (int i = 1 + lane; i < n_out; i += 32) {
                     const long long key = ((long long)level[lbuf[i] >> 1] << 32) | (long long)(0x7fffffff - i);
                     if (key > LV(best)) LV(best) = key;
@@ -452,6 +460,7 @@ struct WarpSolver {
         }
         LANES
         {
+            GPSAT_NOUNROLL
             for (int i = 1 + lane; i < n_out; i += 32) seen[lbuf[i] >> 1] = 0;
         }
         SYNCWARP();
@@ -466,6 +475,7 @@ struct WarpSolver {
         LANES
         {
             LV(part) = 0;
+            GPSAT_NOUNROLL
             for (int i = lane; i < n_out; i += 32)
                 LV(part) += (unsigned long long)(lbuf[i] + 1) * (unsigned long long)(i + 1) * 0x9E3779B97F4A7C15ull;
         }
@@ -484,6 +494,7 @@ struct WarpSolver {
         const int r = arena_top;
         LANES
         {
+            GPSAT_NOUNROLL
             for (int i = lane; i < n_out; i += 32) arena[r + 1 + i] = lbuf[i];
         }
         LANE0
@@ -506,6 +517,7 @@ struct WarpSolver {
         GPSAT_LANE_DECL
         LANES
         {
+            GPSAT_NOUNROLL
             for (int i = lane; i < n_out; i += 32) vs[lbuf[i]] += 1;
         }
         SYNCWARP();
@@ -513,6 +525,7 @@ struct WarpSolver {
         if (vs_clauses % 50 == 0) {
             LANES
             {
+                GPSAT_NOUNROLL
                 for (int x = lane; x < 2 * n_vars; x += 32) vs[x] /= 2;
             }
             SYNCWARP();
@@ -535,6 +548,7 @@ struct WarpSolver {
         const int at = slot * GPSAT_POOL_SLOT_WORDS;
         LANES
         {
+            GPSAT_NOUNROLL
             for (int i = lane; i < n_out; i += 32) pool[at + 1 + i] = lbuf[i];
         }
         SYNCWARP();
@@ -561,11 +575,13 @@ struct WarpSolver {
         // 1. histogram of candidate lengths
         LANES
         {
+            GPSAT_NOUNROLL
             for (int i = lane; i < 64; i += 32) hist[i] = 0;
         }
         SYNCWARP();
         LANES
         {
+            GPSAT_NOUNROLL
             for (int i = lane; i < n_learnts; i += 32) {
                 const int r = refs[i];
                 const int len = arena[r];
@@ -574,11 +590,13 @@ struct WarpSolver {
         }
         SYNCWARP();
         int n_cand = 0;
+        GPSAT_NOUNROLL
         for (int b = 0; b < 64; ++b) n_cand += hist[b];
         const int target = n_cand / 2;
         int thr = 64, partial = 0;
         {
             int acc = 0;
+            GPSAT_NOUNROLL
             for (int b = 63; b >= 3 && acc < target; --b) {
                 const int h = hist[b];
                 if (acc + h >= target) {
@@ -593,6 +611,7 @@ struct WarpSolver {
         // 2. mark (negative header) in age order, 3. compact, relocating reasons of locked clauses
         int kept = 0;
         int top = clause_base;
+        GPSAT_NOUNROLL
         for (int base = 0; base < n_learnts; base += 32) {
             LANEVAR(int, rr);
             LANEVAR(int, ll);
@@ -616,6 +635,7 @@ struct WarpSolver {
             }
             SYNCWARP();
             const int cnt = (n_learnts - base) < 32 ? (n_learnts - base) : 32;
+            GPSAT_NOUNROLL
             for (int t = 0; t < cnt; ++t) {
                 const int r = SHFL(rr, t);
                 const int len = SHFL(ll, t);
@@ -634,6 +654,7 @@ struct WarpSolver {
                     const bool lk = lit_value(x0) == 1 && reason[x0 >> 1] == GPSAT_LEARNT_CREF(r);
                     SYNCWARP();
                     // move down (top < r, ranges may overlap: ascending order, 32 words at a time)
+                    GPSAT_NOUNROLL
                     for (int w = 0; w < len + 1; w += 32) {
                         LANEVAR(int, tmp);
                         LANES
@@ -662,11 +683,13 @@ struct WarpSolver {
         // 4. rebuild watch vectors: count, carve exact vectors from the top of the arena, fill in age order
         LANES
         {
+            GPSAT_NOUNROLL
             for (int x = lane; x < 2 * n_vars; x += 32) lw_size[x] = 0;
         }
         SYNCWARP();
         LANES
         {
+            GPSAT_NOUNROLL
             for (int i = lane; i < n_learnts; i += 32) {
                 const int r = refs[i];
                 gpsat_atomic_add(lw_size + arena[r + 1], 1);
@@ -675,6 +698,7 @@ struct WarpSolver {
         }
         SYNCWARP();
         watch_bot = arena_words;
+        GPSAT_NOUNROLL
         for (int base = 0; base < 2 * n_vars; base += 32) {
             LANEVAR(int, cntv);
             LANEVAR(int, ptrv);
@@ -684,6 +708,7 @@ struct WarpSolver {
                 LV(cntv) = x < 2 * n_vars ? lw_size[x] : 0;
                 LV(ptrv) = 0;
             }
+            GPSAT_NOUNROLL
             for (int t = 0; t < 32; ++t) {
                 const int c = SHFL(cntv, t);
                 if (c > 0) {
@@ -706,6 +731,7 @@ struct WarpSolver {
             oom = 1;
             return;
         }
+        GPSAT_NOUNROLL
         for (int i = 0; i < n_learnts; ++i) {
             const int r = refs[i];
             const int x0 = arena[r + 1], x1 = arena[r + 2];
@@ -725,6 +751,7 @@ struct WarpSolver {
             LANES
             {
                 LV(best) = -1;
+                GPSAT_NOUNROLL
                 for (int v = lane; v < n_vars; v += 32) {
                     if (val[v] != GPSAT_VAL_UNDEF) continue;
                     const long long kp = ((long long)vs[2 * v + 1] << 32) | (long long)(0x7fffffff - 2 * v);
@@ -739,6 +766,7 @@ struct WarpSolver {
             return o ^ 1;
         }
         // shipped rule: topmost free variable, positive polarity
+        GPSAT_NOUNROLL
         for (int base = n_vars - 1; base >= 0; base -= 32) {
             const unsigned m = BALLOT((base - lane >= 0) && val[base - lane] == GPSAT_VAL_UNDEF);
             if (m) return 2 * (base - (gpsat_ffs(m) - 1)) + 1;
@@ -754,12 +782,15 @@ struct WarpSolver {
         GPSAT_LANE_DECL
         LANES
         {
+            GPSAT_NOUNROLL
             for (int v = lane; v < n_vars; v += 32) {
                 val[v] = val0[v];
                 seen[v] = 0;
             }
+            GPSAT_NOUNROLL
             for (int w = lane; w < wbits_words; w += 32) wbits[w] = wbits0[w];
             if (use_learnts && !keep_learnts) {
+                GPSAT_NOUNROLL
                 for (int x = lane; x < 2 * n_vars; x += 32) {
                     vs[x] = vsids0[x];
                     lw_size[x] = 0;
@@ -836,6 +867,7 @@ struct WarpSolver {
     {
         GPSAT_LANE_DECL
         if (facts == nullptr) return GPSAT_UNDEF;
+        GPSAT_NOUNROLL
         for (int v0 = 0; v0 < n_vars; v0 += 32) {
             LANEVAR(int, f);
             LANES
@@ -853,39 +885,67 @@ struct WarpSolver {
                 if (v == 2) enqueue(lit, GPSAT_REASON_NONE);
             }
         }
-        if (propagate() != GPSAT_NO_CONFLICT) return GPSAT_UNSAT;
         return GPSAT_UNDEF;
     }
 
-    // Import from slots [from, used) of a pool (fixed 16-word slots, length written last; a slot whose length is
-    // still 0 is being written by another warp and is skipped): the NEWEST clauses of 2..15 literals, at most
-    // share_import_max of them, looking at no more than 64 x 32 slots.  The warp reads 32 slot headers per step.
-    GPSAT_DEV int import_pool(const int *base, int from, int used)
+    // One importer for both record layouts (one attach site keeps the kernel's code small; nothing here propagates —
+    // the caller's next propagate() does, at the root level):
+    //   stride > 0   pool slots [from, used) of `stride` words, length written last (a slot whose length is still 0 is
+    //                being written by another warp and is skipped): the NEWEST clauses of 2..stride-1 literals, at
+    //                most share_import_max of them, looking at no more than 2048 slots, 32 slot headers per step;
+    //                unit clauses are not taken here, they travel through `facts`
+    //   stride == 0  hand-off block of a split cube: records [len, lits...] packed back to back in words [0, used):
+    //                unit records (the parent's level-0 facts) become facts, every clause is attached
+    GPSAT_DEV int import_stream(const int *base, int from, int used, int stride)
     {
         GPSAT_LANE_DECL
-        if (from >= used) return GPSAT_UNDEF;
-        if (used - from > 2048) from = used - 2048;
-        int taken = 0;
-        for (int s0 = used; s0 > from && taken < share_import_max; s0 -= 32) {
-            const int lo = s0 - 32 > from ? s0 - 32 : from;
-            LANEVAR(int, len);
-            LANES
-            {
-                const int sl = s0 - 1 - lane;
-                LV(len) = sl >= lo ? gpsat_ld_cg(base + sl * GPSAT_POOL_SLOT_WORDS) : 0;
-            }
-            unsigned m = BALLOT(LV(len) >= 2 && LV(len) < GPSAT_POOL_SLOT_WORDS);
-            while (m && taken < share_import_max) {
+        if (stride && used - from > 2048) from = used - 2048;
+        int taken = 0, at = 0, s0 = used, chunk_top = used;
+        unsigned m = 0;
+        LANEVAR(int, len_v);
+        LANES { LV(len_v) = 0; }
+        while (true) {
+            const int *rec;
+            int len;
+            if (stride) {
+                if (taken >= share_import_max) break;
+                if (!m) {
+                    if (s0 <= from) break;
+                    const int lo = s0 - 32 > from ? s0 - 32 : from;
+                    LANES
+                    {
+                        const int sl = s0 - 1 - lane;
+                        LV(len_v) = sl >= lo ? gpsat_ld_cg(base + sl * stride) : 0;
+                    }
+                    m = BALLOT(LV(len_v) >= 2 && LV(len_v) < stride);
+                    chunk_top = s0;
+                    s0 -= 32;
+                    if (!m) continue;
+                }
                 const int src = gpsat_ffs(m) - 1;
                 m &= m - 1;
-                if (!import_room()) return propagate() != GPSAT_NO_CONFLICT ? GPSAT_UNSAT : GPSAT_UNDEF;
-                const int sl = s0 - 1 - src;
-                const int st = attach_record(base + sl * GPSAT_POOL_SLOT_WORDS + 1, SHFL(len, src));
-                if (st != GPSAT_UNDEF) return st;
-                taken++;
+                rec = base + (chunk_top - 1 - src) * stride + 1;
+                len = SHFL(len_v, src);
+            } else {
+                if (at >= used) break;
+                len = gpsat_ld_cg(base + at);
+                if (len <= 0 || at + 1 + len > used) break;
+                rec = base + at + 1;
+                at += len + 1;
+                if (len == 1) {
+                    const int u = gpsat_ld_cg(rec);
+                    const int v = lit_value(u);
+                    if (v == 0) return GPSAT_UNSAT;
+                    if (v == 2) enqueue(u, GPSAT_REASON_NONE);
+                    continue;
+                }
+                if (len > 32 || len > lbuf_words) continue;
             }
+            if (!import_room()) break;
+            const int st = attach_record(rec, len);
+            if (st != GPSAT_UNDEF) return st;
+            taken++;
         }
-        if (propagate() != GPSAT_NO_CONFLICT) return GPSAT_UNSAT;
         return GPSAT_UNDEF;
     }
 
@@ -903,7 +963,7 @@ struct WarpSolver {
             if (used > cap_slots) used = cap_slots;
             const int from = pool_mark < used ? pool_mark : used;
             pool_mark = used;
-            const int st = import_pool(pool, from, used);
+            const int st = import_stream(pool, from, used, GPSAT_POOL_SLOT_WORDS);
             if (st != GPSAT_UNDEF) return st;
         }
         if (xpool != nullptr) {
@@ -911,40 +971,9 @@ struct WarpSolver {
             if (used > cap_slots) used = cap_slots;
             const int from = xpool_mark < used ? xpool_mark : used;
             xpool_mark = used;
-            const int st = import_pool(xpool, from, used);
+            const int st = import_stream(xpool, from, used, GPSAT_POOL_SLOT_WORDS);
             if (st != GPSAT_UNDEF) return st;
         }
-        return GPSAT_UNDEF;
-    }
-
-    // Hand-off blocks of split cubes: records [len, lit0 .. lit(len-1)] packed back to back in rec[0..used).
-    // Unit records (the parent's level-0 facts) first, then the clauses.
-    GPSAT_DEV int import_records(const int *rec, int used)
-    {
-        int at = 0;
-        while (at < used) {
-            const int len = gpsat_ld_cg(rec + at);
-            if (len <= 0 || at + 1 + len > used) break;
-            if (len == 1) {
-                const int u = gpsat_ld_cg(rec + at + 1);
-                const int v = lit_value(u);
-                if (v == 0) return GPSAT_UNSAT;
-                if (v == 2) enqueue(u, GPSAT_REASON_NONE);
-            }
-            at += len + 1;
-        }
-        const int end_at = at;
-        if (propagate() != GPSAT_NO_CONFLICT) return GPSAT_UNSAT;
-        for (at = 0; at < end_at;) {
-            const int len = gpsat_ld_cg(rec + at);
-            if (len >= 2 && len <= 32 && len <= lbuf_words) {
-                if (!import_room()) break;
-                const int st = attach_record(rec + at + 1, len);
-                if (st != GPSAT_UNDEF) return st;
-            }
-            at += len + 1;
-        }
-        if (propagate() != GPSAT_NO_CONFLICT) return GPSAT_UNSAT;
         return GPSAT_UNDEF;
     }
 
@@ -963,6 +992,7 @@ struct WarpSolver {
         const int cap = hand_words - 1 - 2 * n_vars;
         LANES
         {
+            GPSAT_NOUNROLL
             for (int x = lane; x < 2 * n_vars; x += 32) h[1 + x] = vs[x];
         }
         // level-0 facts as unit records
@@ -971,6 +1001,7 @@ struct WarpSolver {
         const int n_units = (2 * n0 <= cap) ? n0 : cap / 2;
         LANES
         {
+            GPSAT_NOUNROLL
             for (int i = lane; i < n_units; i += 32) {
                 rec[2 * i] = 1;
                 rec[2 * i + 1] = trail[i];
@@ -979,6 +1010,7 @@ struct WarpSolver {
         used = 2 * n_units;
         // newest learnt clauses: the arena tail [refs[first] .. arena_top) that fits
         int first = n_learnts;
+        GPSAT_NOUNROLL
         for (int base = 0; base < n_learnts && first == n_learnts; base += 32) {
             const unsigned m = BALLOT((base + lane < n_learnts) && (arena_top - refs[base + lane] <= cap - used));
             if (m) first = base + gpsat_ffs(m) - 1;
@@ -988,6 +1020,7 @@ struct WarpSolver {
             const int nw = arena_top - from;
             LANES
             {
+                GPSAT_NOUNROLL
                 for (int i = lane; i < nw; i += 32) rec[used + i] = arena[from + i];
             }
             used += nw;
@@ -1019,6 +1052,7 @@ struct WarpSolver {
         LANE0
         {
             int pos = gpsat_ld_volatile(dq_ctrl + 0);
+            GPSAT_NOUNROLL
             for (int tries = 0; tries < 64; ++tries) {
                 const int slot = pos & (dq_cap - 1);
                 const int dif = gpsat_ld_volatile(dq_meta + 4 * slot + 2) - pos;
@@ -1047,6 +1081,7 @@ struct WarpSolver {
         GPSAT_LANE_DECL
         LANES
         {
+            GPSAT_NOUNROLL
             for (int i = lane; i < k; i += 32) dq_lits[(long long)slot * GPSAT_DQ_MAXK + i] = cube_buf[i];
         }
         LANE0
@@ -1116,8 +1151,11 @@ struct WarpSolver {
         const int n0 = dlevel > 0 ? trail_lim[0] : trail_size;
         LANES
         {
+            GPSAT_NOUNROLL
             for (int i = lane; i < k; i += 32) park[16 + i] = cube_buf[i];
+            GPSAT_NOUNROLL
             for (int i = lane; i < n0; i += 32) park[16 + GPSAT_DQ_MAXK + i] = trail[i];
+            GPSAT_NOUNROLL
             for (int x = lane; x < 2 * n_vars; x += 32) park[16 + GPSAT_DQ_MAXK + n_vars + x] = vs[x];
         }
         LANE0
@@ -1161,9 +1199,11 @@ struct WarpSolver {
             const int n0 = park[3];
             LANES
             {
+                GPSAT_NOUNROLL
                 for (int x = lane; x < 2 * n_vars; x += 32) vs[x] = park[16 + GPSAT_DQ_MAXK + n_vars + x];
             }
             SYNCWARP();
+            GPSAT_NOUNROLL
             for (int i = 0; i < n0; ++i) {
                 const int u = park[16 + GPSAT_DQ_MAXK + i];
                 const int v = lit_value(u);
@@ -1178,6 +1218,7 @@ struct WarpSolver {
         if (queued_ok) {   // the cube may grow (splits) or be parked (budgeted steps): work on a private copy
             LANES
             {
+                GPSAT_NOUNROLL
                 for (int i = lane; i < k; i += 32) cube_buf[i] = gpsat_ld_cg(cube + i);
             }
             SYNCWARP();
@@ -1190,10 +1231,11 @@ struct WarpSolver {
         if (hand != nullptr) {   // popped from the ring: inherit the parent's counters, facts and newest clauses
             LANES
             {
+                GPSAT_NOUNROLL
                 for (int x = lane; x < 2 * n_vars; x += 32) vs[x] = gpsat_ld_cg(hand + 1 + x);
             }
             SYNCWARP();
-            const int st = import_records(hand + 1 + 2 * n_vars, gpsat_ld_cg(hand));
+            const int st = import_stream(hand + 1 + 2 * n_vars, 0, gpsat_ld_cg(hand), 0);
             release_slot();
             if (st != GPSAT_UNDEF) return st;
         }
@@ -1415,10 +1457,12 @@ GPSAT_DEV void gpsat_run_and_record(WarpSolver &S, int root, const int *cube, in
         // implied literals = trail entries with a reason, cube variables excluded, trail order
         LANES
         {
+            GPSAT_NOUNROLL
             for (int i = lane; i < k; i += 32) S.seen[cube[i] >> 1] = 1;
         }
         SYNCWARP();
         int n_imp = 0;
+        GPSAT_NOUNROLL
         for (int base = 0; base < S.trail_size; base += 32) {
             LANEVAR(int, x);
             LANEVAR(int, take);
@@ -1447,6 +1491,7 @@ GPSAT_DEV void gpsat_run_and_record(WarpSolver &S, int root, const int *cube, in
         SYNCWARP();
         LANES
         {
+            GPSAT_NOUNROLL
             for (int i = lane; i < k; i += 32) S.seen[cube[i] >> 1] = 0;
         }
         if (B.n_implied) {
@@ -1460,6 +1505,7 @@ GPSAT_DEV void gpsat_run_and_record(WarpSolver &S, int root, const int *cube, in
         if (SHFL(won, 0)) {
             LANES
             {
+                GPSAT_NOUNROLL
                 for (int v = lane; v < S.n_vars; v += 32) B.model[v] = (S.val[v] == GPSAT_VAL_FALSE) ? 0 : 1;
             }
             SYNCWARP();
@@ -1514,6 +1560,7 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
                 }
                 if (kind == 3 && P.mode == GPSAT_MODE_SOLVE && P.dynamic_split) {
                     int pos = gpsat_ld_volatile(B.dq_ctrl + 1);
+                    GPSAT_NOUNROLL
                     for (int tries = 0; tries < 8; ++tries) {
                         const int slot = pos & (B.dq_cap - 1);
                         const int dif = gpsat_ld_volatile(B.dq_meta + 4 * slot + 2) - (pos + 1);

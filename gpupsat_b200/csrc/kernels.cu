@@ -11,7 +11,7 @@
 #include "kernels.h"
 #include "cdcl_warp.inl"
 
-#define GPSAT_MAX_THREADS 768   // 24 warps per block: up to 85 registers per thread
+#define GPSAT_MAX_THREADS 640   // 20 warps per block: up to 102 registers per thread
 
 namespace {
 
