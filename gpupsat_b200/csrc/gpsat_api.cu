@@ -140,6 +140,7 @@ struct gpsat {
     DevBuf<uint32_t> valbits;
     DevBuf<int64_t> sweep_counters;
     int uniform3 = 0;
+    int sweep_cluster = 0;   // cluster size used by the last occurrence-mode propagation (0 = HBM-bitmap kernel)
     // cubes
     int32_t n_cubes = 0;
     bool cubes_set = false;
@@ -434,11 +435,11 @@ void fill_stats(gpsat *h, gpsat_stats *s)
     s->jobs_total = h->n_cubes;
     for (int j = 0; j < h->n_cubes; j++) {
         const gpsat_job_record &r = h->records_h[(size_t)j];
-        if (r.status == GPSAT_JOB_NOT_RUN) continue;
+        // counters include cubes that are still open (parked between steps, or cut short by the stop flag)
         if (r.status == GPSAT_SAT) s->jobs_sat++;
         else if (r.status == GPSAT_UNSAT) s->jobs_unsat++;
-        else s->jobs_undef++;
-        if (r.status != GPSAT_JOB_ABORTED) s->jobs_done++;
+        else if (r.status != GPSAT_JOB_NOT_RUN) s->jobs_undef++;
+        if (r.status != GPSAT_JOB_ABORTED && r.status != GPSAT_JOB_NOT_RUN) s->jobs_done++;
         s->decisions += r.decisions;
         s->implications += r.implications;
         s->conflicts += r.conflicts;
@@ -489,14 +490,52 @@ int propagate_all_occurrence(gpsat *h, int32_t *status, int32_t *n_implied, int3
 {
     const size_t nc = (size_t)h->n_cubes;
     if (implied_stride <= 0) implied_stride = h->D.n_vars;       // the implied block doubles as the trail
+    const int32_t val_words = (h->D.n_vars + 15) / 16;
+    // Preferred: one thread-block cluster per job with the assignment bitmap in distributed shared memory (the
+    // smallest cluster whose per-CTA slice is at most 64 KB, so that three CTAs share an SM).  Falls back to the
+    // HBM-bitmap kernel (one warp per job) when even 16 CTAs cannot hold the bitmap.  GPSAT_SWEEP_CLUSTER /
+    // GPSAT_SWEEP_THREADS / GPSAT_SWEEP_SLICE_KB override for experiments (cluster 0 = HBM-bitmap kernel).
+    int cluster = 0, slice_log2 = 4, cthreads = 512;
+    {
+        const char *e_cl = std::getenv("GPSAT_SWEEP_CLUSTER"), *e_th = std::getenv("GPSAT_SWEEP_THREADS"),
+                   *e_kb = std::getenv("GPSAT_SWEEP_SLICE_KB");
+        const int slice_kb = e_kb ? std::atoi(e_kb) : 64;
+        if (e_th) cthreads = std::max(32, std::min(1024, std::atoi(e_th) / 32 * 32));
+        int want = e_cl ? std::atoi(e_cl) : -1;
+        if (want != 0) {
+            for (int cs = (want > 0 ? want : 1); cs <= 16; cs *= 2) {
+                int lg = 4;
+                while (((int64_t)1 << lg) * cs < val_words) lg++;
+                if (((int64_t)4 << lg) <= (int64_t)slice_kb * 1024 || (want > 0 && ((int64_t)4 << lg) <= 200 * 1024)) {
+                    cluster = cs;
+                    slice_log2 = lg;
+                    break;
+                }
+                if (want > 0) break;
+            }
+        }
+    }
     int wpb = h->opts.warps_per_block > 0 ? std::min(h->opts.warps_per_block, 32) : 32;
     int blocks = h->opts.blocks > 0 ? h->opts.blocks : h->prop.multiProcessorCount;   // 1024 threads: 1 block per SM
-    const int64_t need = ((int64_t)nc + wpb - 1) / wpb;
-    if (blocks > need) blocks = (int)std::max<int64_t>(need, 1);
+    if (cluster > 0) {
+        wpb = cthreads / 32;
+        int cap = 0;
+        CU(gpsat_kernels::sweep_cluster_capacity(cluster, cthreads, (size_t)4 << slice_log2, &cap));
+        if (cap < 1) {
+            cluster = 0;   // this cluster shape cannot be scheduled: HBM-bitmap kernel
+            wpb = 32;
+        } else {
+            blocks = h->opts.blocks > 0 ? std::min(h->opts.blocks, cap) : cap;
+            if ((int64_t)blocks > (int64_t)nc) blocks = (int)std::max<size_t>(nc, 1);
+        }
+    }
+    if (cluster == 0) {
+        const int64_t need = ((int64_t)nc + wpb - 1) / wpb;
+        if (blocks > need) blocks = (int)std::max<int64_t>(need, 1);
+    }
     const size_t n_warps = (size_t)blocks * wpb;
-    const int32_t val_words = (h->D.n_vars + 15) / 16;
     CU(h->ctrl.ensure(4));
-    if (h->valbits.n < n_warps * (size_t)val_words) {
+    if (cluster == 0 && h->valbits.n < n_warps * (size_t)val_words) {
         CU(h->valbits.ensure(n_warps * (size_t)val_words));
         CU(cudaMemsetAsync(h->valbits.p, 0, n_warps * (size_t)val_words * sizeof(uint32_t), h->stream));
     }
@@ -531,12 +570,16 @@ int propagate_all_occurrence(gpsat *h, int32_t *status, int32_t *n_implied, int3
     L.next_job = h->ctrl.p;
     L.blocks = blocks;
     L.warps_per_block = wpb;
+    L.cluster_size = cluster;
+    L.slice_log2 = slice_log2;
+    if (cluster > 0) CU(cudaMemsetAsync(h->sweep_counters.p, 0, 2 * nc * sizeof(int64_t), h->stream));
     h->kernel_ms = 0;
     h->kernel_launches = 0;
     h->blocks = blocks;
     h->warps_per_block = wpb;
-    h->smem_bytes = 512;
-    h->state_in_smem = 0;
+    h->smem_bytes = cluster > 0 ? ((size_t)4 << slice_log2) : 512;
+    h->state_in_smem = cluster > 0 ? 1 : 0;
+    h->sweep_cluster = cluster;
     CU(cudaEventRecord(h->ev0, h->stream));
     CU(gpsat_kernels::launch_bcp_sweep(L, h->stream));
     CU(cudaEventRecord(h->ev1, h->stream));

@@ -433,6 +433,249 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_kernel(const SweepArg
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// gpsat_bcp_sweep_cluster_kernel — the same occurrence-list BCP with the job's assignment bitmap held ON CHIP:
+// one thread-block CLUSTER per job, the 2-bit-per-variable bitmap (250 KB at n = 1e6, more than one SM's shared
+// memory) is split across the shared memories of the cluster's CTAs and read / updated through distributed shared
+// memory (mapa + ld/atom.shared::cluster).  The HBM-bitmap kernel above spends 2/3 of its time on the two random
+// 4-byte bitmap gathers per visited entry, each of which costs a 32-byte DRAM sector (ncu: 15x more DRAM traffic
+// than algorithmic bytes); here those gathers never leave the SMs, and HBM/L2 only stream the formula index
+// (ostart + occurrence pairs), which is what the algorithmic byte count charges for.
+//   * all threads of the cluster (cluster_size x blockDim) each own one trail literal per round;
+//   * a round ends with two cluster barriers around a snapshot of (trail length, conflict flag) taken by the
+//     leader, so that every thread sees the same loop bounds;
+//   * units are assigned with a remote atomicOr and appended to the trail (the caller's `implied` block in HBM)
+//     through one atomic on the leader's counter.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t dsm_addr(uint32_t local_addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ uint32_t dsm_ld(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void dsm_st(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t dsm_atom_or(uint32_t addr, uint32_t v)
+{
+    uint32_t o;
+    asm volatile("atom.shared::cluster.or.b32 %0, [%1], %2;" : "=r"(o) : "r"(addr), "r"(v) : "memory");
+    return o;
+}
+__device__ __forceinline__ uint32_t dsm_atom_add(uint32_t addr, uint32_t v)
+{
+    uint32_t o;
+    asm volatile("atom.shared::cluster.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(addr), "r"(v) : "memory");
+    return o;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    __syncwarp();
+    asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_size()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+
+// control words in the leader CTA (rank 0) of the cluster
+enum { CW_COUNT = 0, CW_CONFLICT, CW_CLAUSE, CW_JOB, CW_SNAP_TOTAL, CW_SNAP_CONFLICT, CW_WORDS };
+
+struct ClusterBits {
+    uint32_t base;        // shared-window address of this CTA's slice (same offset in every CTA of the cluster)
+    int slice_log2;       // words per slice = 1 << slice_log2
+    // address of the word holding literal x's variable (16 variables per word)
+    __device__ __forceinline__ uint32_t word_addr(int x) const
+    {
+        const uint32_t w = (uint32_t)x >> 5;
+        return dsm_addr(base + ((w & ((1u << slice_log2) - 1u)) << 2), w >> slice_log2);
+    }
+    __device__ __forceinline__ int value(int x) const   // 1 true, 0 false, 2 unassigned
+    {
+        const uint32_t f = (dsm_ld(word_addr(x)) >> (((x >> 1) & 15) * 2)) & 3u;
+        return (f & 2u) ? (int)((f & 1u) == (uint32_t)(x & 1)) : 2;
+    }
+    __device__ __forceinline__ uint32_t assign(int x) const   // returns the previous 2-bit field (0 = was unassigned)
+    {
+        const int sh = ((x >> 1) & 15) * 2;
+        return (dsm_atom_or(word_addr(x), (2u | (uint32_t)(x & 1)) << sh) >> sh) & 3u;
+    }
+};
+
+__global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_cluster_kernel(const SweepArgs A, const int slice_log2)
+{
+    extern __shared__ __align__(16) uint32_t s_slice[];
+    __shared__ uint32_t s_ctrl[CW_WORDS];
+    const uint32_t rank = cluster_rank(), csize = cluster_size();
+    const int cthreads = (int)(csize * blockDim.x), ctid = (int)(rank * blockDim.x + threadIdx.x);
+    const int slice_words = 1 << slice_log2;
+    ClusterBits bits;
+    bits.base = smem_u32(s_slice);
+    bits.slice_log2 = slice_log2;
+    const uint32_t ctrl0 = dsm_addr(smem_u32(s_ctrl), 0);   // the leader's control words
+
+    while (true) {
+        if (rank == 0 && threadIdx.x == 0) {
+            s_ctrl[CW_JOB] = (uint32_t)atomicAdd(A.next_job, 1);
+            s_ctrl[CW_COUNT] = 0;
+            s_ctrl[CW_CONFLICT] = 0;
+            s_ctrl[CW_CLAUSE] = 0xffffffffu;
+        }
+        {
+            uint4 *z = reinterpret_cast<uint4 *>(s_slice);
+            for (int i = (int)threadIdx.x; i < slice_words / 4; i += (int)blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+        }
+        cluster_sync_all();
+        const int job = (int)dsm_ld(ctrl0 + 4 * CW_JOB);
+        if (job >= A.n_cubes) {        // same value in every thread of the cluster
+            cluster_sync_all();        // nobody leaves while a peer may still be reading its shared memory
+            break;
+        }
+        const long long c0 = A.cube_offsets[job], c1 = A.cube_offsets[job + 1];
+        const int k = (int)(c1 - c0);
+        const int32_t *cube = A.cube_lits + c0;
+        int32_t *imp = A.implied + (long long)job * A.stride;
+
+        // phase 0: the whole cube is assigned up front (VariablesStateHandler::set_assumptions)
+        for (int i = ctid; i < k; i += cthreads) {
+            const int x = __ldg(cube + i);
+            const uint32_t prev = bits.assign(x);
+            if ((prev & 2u) && (prev & 1u) != (uint32_t)(x & 1)) dsm_st(ctrl0 + 4 * CW_CONFLICT, 1u);   // x and ~x
+        }
+        cluster_sync_all();
+        if (rank == 0 && threadIdx.x == 0) {
+            s_ctrl[CW_SNAP_TOTAL] = (uint32_t)k;
+            s_ctrl[CW_SNAP_CONFLICT] = s_ctrl[CW_CONFLICT];
+        }
+        cluster_sync_all();
+
+        long long visited = 0, words = 0;
+        int qhead = 0;
+        while (true) {
+            const int total = (int)dsm_ld(ctrl0 + 4 * CW_SNAP_TOTAL);
+            const int conflict = (int)dsm_ld(ctrl0 + 4 * CW_SNAP_CONFLICT);
+            if (conflict || qhead >= total) break;
+            for (int t = qhead + ctid; t < total; t += cthreads) {
+                const int p = t < k ? __ldg(cube + t) : __ldcg(imp + (t - k));
+                const int f = p ^ 1;
+                const int os = __ldg(A.ostart + f), oe = __ldg(A.ostart + f + 1);
+                for (int e0 = os; e0 < oe; e0 += 4) {
+                    const int cnt = min(4, oe - e0);
+                    if (A.uniform3) {
+                        int2 pr[4];
+                        int va[4], vb[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j < cnt) pr[j] = __ldg(A.occ_pair + e0 + j);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j < cnt) {
+                                va[j] = bits.value(pr[j].x);
+                                vb[j] = bits.value(pr[j].y);
+                            }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j < cnt) {
+                                if (va[j] == 1 || vb[j] == 1) continue;
+                                const int n_undef = (va[j] == 2) + (vb[j] == 2);
+                                if (n_undef > 1) continue;
+                                if (n_undef == 0) {   // every other literal false: conflict
+                                    dsm_st(ctrl0 + 4 * CW_CLAUSE, (uint32_t)__ldg(A.occ_clause + e0 + j));
+                                    dsm_st(ctrl0 + 4 * CW_CONFLICT, 1u);
+                                    continue;
+                                }
+                                const int unit = (va[j] == 2) ? pr[j].x : pr[j].y;
+                                const uint32_t prev = bits.assign(unit);
+                                if (prev == 0) {
+                                    const int pos = (int)dsm_atom_add(ctrl0 + 4 * CW_COUNT, 1u);
+                                    if (pos < A.stride) imp[pos] = unit;
+                                } else if ((prev & 1u) != (uint32_t)(unit & 1)) {   // lost a race against ~unit
+                                    dsm_st(ctrl0 + 4 * CW_CLAUSE, (uint32_t)__ldg(A.occ_clause + e0 + j));
+                                    dsm_st(ctrl0 + 4 * CW_CONFLICT, 1u);
+                                }
+                            }
+                        visited += cnt;
+                        words += 2 * cnt;
+                    } else {
+                        for (int j = 0; j < cnt; ++j) {
+                            const int c = __ldg(A.occ_clause + e0 + j);
+                            const int lb = __ldg(A.coffsets + c), le = __ldg(A.coffsets + c + 1);
+                            int unit = -1, n_undef = 0;
+                            bool sat = false;
+                            for (int i = lb; i < le && !sat; ++i) {
+                                const int x = __ldg(A.clits + i);
+                                words++;
+                                if (x == f) continue;
+                                const int v = bits.value(x);
+                                if (v == 1) sat = true;
+                                else if (v == 2) { n_undef++; unit = x; }
+                            }
+                            visited++;
+                            if (sat || n_undef > 1) continue;
+                            if (n_undef == 0) {
+                                dsm_st(ctrl0 + 4 * CW_CLAUSE, (uint32_t)c);
+                                dsm_st(ctrl0 + 4 * CW_CONFLICT, 1u);
+                                continue;
+                            }
+                            const uint32_t prev = bits.assign(unit);
+                            if (prev == 0) {
+                                const int pos = (int)dsm_atom_add(ctrl0 + 4 * CW_COUNT, 1u);
+                                if (pos < A.stride) imp[pos] = unit;
+                            } else if ((prev & 1u) != (uint32_t)(unit & 1)) {
+                                dsm_st(ctrl0 + 4 * CW_CLAUSE, (uint32_t)c);
+                                dsm_st(ctrl0 + 4 * CW_CONFLICT, 1u);
+                            }
+                        }
+                    }
+                }
+            }
+            __threadfence();          // trail entries written this round are read by other SMs in the next one
+            cluster_sync_all();
+            if (rank == 0 && threadIdx.x == 0) {
+                const int cnt = (int)min((long long)s_ctrl[CW_COUNT], (long long)A.stride);
+                s_ctrl[CW_SNAP_TOTAL] = (uint32_t)(k + cnt);
+                s_ctrl[CW_SNAP_CONFLICT] = s_ctrl[CW_CONFLICT];
+            }
+            cluster_sync_all();
+            qhead = total;
+        }
+        // per-job counters: one pair of global atomics per warp
+        for (int o = 16; o > 0; o >>= 1) {
+            visited += __shfl_xor_sync(0xffffffffu, visited, o);
+            words += __shfl_xor_sync(0xffffffffu, words, o);
+        }
+        if ((threadIdx.x & 31u) == 0 && A.counters) {
+            atomicAdd((unsigned long long *)(A.counters + 2 * job), (unsigned long long)visited);
+            atomicAdd((unsigned long long *)(A.counters + 2 * job + 1), (unsigned long long)words);
+        }
+        if (rank == 0 && threadIdx.x == 0) {
+            const int n_imp = (int)s_ctrl[CW_COUNT];
+            const int conflict = (int)s_ctrl[CW_CONFLICT];
+            A.status[job] = conflict ? GPSAT_UNSAT : (n_imp > A.stride ? GPSAT_JOB_OOM : GPSAT_UNDEF);
+            A.n_implied[job] = n_imp;
+            A.conflict_clause[job] = conflict ? (long long)(int)s_ctrl[CW_CLAUSE] : -1;
+        }
+        cluster_sync_all();   // the leader's control words are re-armed only after everybody is done with them
+    }
+}
+
 }  // namespace
 
 namespace gpsat_kernels {
@@ -460,8 +703,53 @@ cudaError_t launch_bcp_sweep(const SweepLaunch &L, cudaStream_t stream)
     A.conflict_clause = L.conflict_clause;
     A.counters = L.counters;
     A.next_job = L.next_job;
+    if (L.cluster_size > 0) {
+        const size_t smem = (size_t)4 << L.slice_log2;
+        cudaError_t e = cudaFuncSetAttribute(gpsat_bcp_sweep_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (L.cluster_size > 8) {
+            e = cudaFuncSetAttribute(gpsat_bcp_sweep_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e != cudaSuccess) return e;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(L.blocks * L.cluster_size));
+        cfg.blockDim = dim3((unsigned)(L.warps_per_block * 32));
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)L.cluster_size;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, gpsat_bcp_sweep_cluster_kernel, A, (int)L.slice_log2);
+    }
     gpsat_bcp_sweep_kernel<<<L.blocks, L.warps_per_block * 32, 0, stream>>>(A);
     return cudaGetLastError();
+}
+
+// how many clusters of `cluster_size` CTAs (threads, dynamic shared memory as given) can be co-resident on the device
+cudaError_t sweep_cluster_capacity(int cluster_size, int threads, size_t smem, int *clusters)
+{
+    cudaError_t e = cudaFuncSetAttribute(gpsat_bcp_sweep_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (cluster_size > 8) {
+        e = cudaFuncSetAttribute(gpsat_bcp_sweep_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(cluster_size * 1024));
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster_size;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaOccupancyMaxActiveClusters(clusters, gpsat_bcp_sweep_cluster_kernel, &cfg);
 }
 
 }  // namespace gpsat_kernels

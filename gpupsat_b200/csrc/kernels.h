@@ -46,8 +46,11 @@ struct SweepLaunch {
     int64_t *conflict_clause;
     int64_t *counters;
     int32_t *next_job;
-    int blocks, warps_per_block;
+    int blocks, warps_per_block;   // cluster kernel: blocks = number of clusters
+    int cluster_size;              // 0: HBM-bitmap kernel (one warp per job); > 0: one cluster per job, bitmap in distributed shared memory
+    int slice_log2;                // cluster kernel: bitmap words per CTA = 1 << slice_log2
 };
 cudaError_t launch_bcp_sweep(const SweepLaunch &L, cudaStream_t stream);
+cudaError_t sweep_cluster_capacity(int cluster_size, int threads, size_t smem, int *clusters);
 
 }  // namespace gpsat_kernels
