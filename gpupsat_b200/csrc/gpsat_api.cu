@@ -491,15 +491,17 @@ int propagate_all_occurrence(gpsat *h, int32_t *status, int32_t *n_implied, int3
     const size_t nc = (size_t)h->n_cubes;
     if (implied_stride <= 0) implied_stride = h->D.n_vars;       // the implied block doubles as the trail
     const int32_t val_words = (h->D.n_vars + 15) / 16;
-    // Preferred: one thread-block cluster per job with the assignment bitmap in distributed shared memory (the
-    // smallest cluster whose per-CTA slice is at most 64 KB, so that three CTAs share an SM).  Falls back to the
+    // Preferred: one thread-block cluster per job with the assignment bitmap in distributed shared memory: the
+    // smallest cluster whose per-CTA slice is at most 160 KB (n = 1e6: 2 CTAs x 128 KB, one CTA of 1024 threads per
+    // SM — measured faster than 4 x 64 KB or 8 x 32 KB, whose larger share of remote lookups loads the SM-to-SM
+    // network: profiles/r01_c4_sweep_f.json).  Falls back to the
     // HBM-bitmap kernel (one warp per job) when even 16 CTAs cannot hold the bitmap.  GPSAT_SWEEP_CLUSTER /
     // GPSAT_SWEEP_THREADS / GPSAT_SWEEP_SLICE_KB override for experiments (cluster 0 = HBM-bitmap kernel).
-    int cluster = 0, slice_log2 = 4, cthreads = 512;
+    int cluster = 0, slice_log2 = 4, cthreads = 1024;
     {
         const char *e_cl = std::getenv("GPSAT_SWEEP_CLUSTER"), *e_th = std::getenv("GPSAT_SWEEP_THREADS"),
                    *e_kb = std::getenv("GPSAT_SWEEP_SLICE_KB");
-        const int slice_kb = e_kb ? std::atoi(e_kb) : 64;
+        const int slice_kb = e_kb ? std::atoi(e_kb) : 160;
         if (e_th) cthreads = std::max(32, std::min(1024, std::atoi(e_th) / 32 * 32));
         int want = e_cl ? std::atoi(e_cl) : -1;
         if (want != 0) {
