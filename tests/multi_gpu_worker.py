@@ -1,0 +1,47 @@
+"""Worker of tests/test_gpu_multi.py: one process per GPU under torchrun (NCCL).  Solves one instance with the epoch
+loop of gpupsat_b200.multi_gpu and prints a JSON line on rank 0."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import gpupsat_b200 as g  # noqa: E402
+from gpupsat_b200 import multi_gpu as mg  # noqa: E402
+from gpupsat_b200.instances import check_model, random_ksat  # noqa: E402
+
+
+def main():
+    n, m, seed, share_len = (int(x) for x in sys.argv[1:5])
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    offs, lits = random_ksat(n, m, seed)
+    cnf = g.Cnf.from_arrays(offs, lits)
+    pre = cnf.preprocess()
+    cubes = pre.choose_cubes(8 * world, 32)
+    mine = mg.shard_cubes(cubes, rank, world)
+    opts = dict(share_learnts=1, share_max_len=share_len) if share_len else {}
+    with g.Solver(cnf.n_vars, pre.offsets, pre.lits, device=local, **opts) as s:
+        s.set_cubes(mine)
+        verdict, model, stats, info = mg.solve_sharded(s, dist, rank, world, dev, budget_ms=5.0,
+                                                       max_clauses_per_epoch=512)
+        rec = s.job_records()
+    ok = bool(check_model(pre.offsets, pre.lits, model)) if verdict == g.SAT else None
+    closed = torch.tensor([int((rec["status"] == g.UNSAT).sum()), len(rec), stats["foreign_clauses"]], device=dev)
+    dist.all_reduce(closed)
+    if rank == 0:
+        print(json.dumps({"verdict": int(verdict), "model_ok": ok, "epochs": info["epochs"],
+                          "cubes_closed_unsat": int(closed[0]), "cubes": int(closed[1]),
+                          "foreign_clauses_all_ranks": int(closed[2]), "world": world}), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -265,3 +265,59 @@ def test_exchanged_clauses_are_implied():
         assert o.run(np.array([0, ln], dtype=np.int64), neg)["records"]["status"][0] == g.UNSAT
         at += ln + 1
         checked += 1
+
+
+def test_config5_pigeonhole_10_9_unsat():
+    """config 5: PHP(10,9), 90 variables, 415 clauses, 4096 cubes — UNSAT (the reference as shipped answers UNDEF after
+    1000 decisions; its cap-lifted host build needs ~7 minutes on one core for the same verdict)."""
+    offs, lits = pigeonhole(10, 9)
+    cnf, pre = _prep(offs, lits)
+    cubes = pre.choose_cubes(8, 32)
+    assert cubes.shape == (4096, 12)
+    with g.Solver(cnf.n_vars, pre.offsets, pre.lits) as s:
+        s.set_cubes(cubes)
+        verdict, _, stats = s.solve()
+        rec = s.job_records()
+    assert verdict == g.UNSAT
+    assert (rec["status"] == g.UNSAT).all() and stats["jobs_done"] == 4096
+    # the same verdict from a different partition of the search space (k = 7) and from no partition at all
+    with g.Solver(cnf.n_vars, pre.offsets, pre.lits) as s:
+        s.set_cubes(pre.choose_cubes(1, 8))
+        assert s.solve()[0] == g.UNSAT
+
+
+def test_config2_and_larger_unsat_verdicts_and_cube_closure():
+    """config 2 (uf250-1065 seed 0) and uf300-1278 seed 0: UNSAT, every one of the 4096 cubes closed; the per-cube
+    statuses of a 1 % sample are cross-checked by the oracle solving those cubes on the CPU."""
+    for n, m, seed, sample in ((250, 1065, 0, 40), (300, 1278, 0, 6)):
+        offs, lits = random_ksat(n, m, seed)
+        cnf, pre = _prep(offs, lits)
+        cubes = pre.choose_cubes(8, 32)
+        with g.Solver(cnf.n_vars, pre.offsets, pre.lits, stop_on_sat=0) as s:
+            s.set_cubes(cubes)
+            verdict, _, stats = s.solve()
+            rec = s.job_records()
+        assert verdict == g.UNSAT and stats["jobs_done"] == len(cubes)
+        assert (rec["status"] == g.UNSAT).all()
+        pick = np.linspace(0, len(cubes) - 1, sample).astype(int)
+        k = cubes.shape[1]
+        want = Oracle(cnf.n_vars, pre.offsets, pre.lits).run(np.arange(0, sample * k + 1, k, dtype=np.int64),
+                                                              cubes[pick].reshape(-1), stop_on_sat=False)
+        assert (want["records"]["status"] == g.UNSAT).all()
+
+
+def test_sat_instance_model_through_cubes():
+    """a satisfiable uf200 instance through 4096 cubes with early termination: model verifies against the CNF"""
+    found = 0
+    for seed in range(1, 40):
+        offs, lits = random_ksat(200, 820, seed)          # r = 4.1: mostly satisfiable
+        cnf, pre = _prep(offs, lits)
+        with g.Solver(cnf.n_vars, pre.offsets, pre.lits) as s:
+            s.set_cubes(pre.choose_cubes(8, 32))
+            verdict, model, stats = s.solve()
+        if verdict == g.SAT:
+            assert check_model(pre.offsets, pre.lits, model)
+            found += 1
+            if found == 3:
+                break
+    assert found == 3
