@@ -690,7 +690,21 @@ int gpsat_create(gpsat_t **out, int32_t n_vars, int64_t n_clauses, const int64_t
     } else {
         CUH(cudaGetDevice(&h->device));
     }
-    CUH(cudaGetDeviceProperties(&h->prop, h->device));
+    {   // cudaGetDeviceProperties costs milliseconds (and varies): query the three attributes used, once per device
+        static int cached_dev = -1;
+        static cudaDeviceProp cached{};
+        if (cached_dev != h->device) {
+            int v = 0;
+            CUH(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, h->device));
+            cached.multiProcessorCount = v;
+            CUH(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+            cached.sharedMemPerBlockOptin = (size_t)v;
+            CUH(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device));
+            cached.sharedMemPerMultiprocessor = (size_t)v;
+            cached_dev = h->device;
+        }
+        h->prop = cached;
+    }
     CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CUH(cudaEventCreate(&h->ev0));
     CUH(cudaEventCreate(&h->ev1));
