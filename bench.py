@@ -160,7 +160,7 @@ def run_reference_arm(args):
         return
     cnf, pre, cubes = make_workload(args.gpus)
     procs = os.cpu_count() or 1
-    per_step = max(procs * 4, 64)
+    per_step = min(max(procs * 16, 64), 4096)          # ~16 cubes per core and step: a few seconds per step
     offs, lits = pre.offsets, pre.lits
     vals, walls = [], []
     for i in range(args.warmup + args.steps):
