@@ -251,7 +251,7 @@ def run_ours(args):
         extra["dynamic_split"] = int(os.environ["GPSAT_DYNAMIC_SPLIT"])
     for env_name, opt in (("GPSAT_SHARE_LEARNTS", "share_learnts"), ("GPSAT_SPLIT_GAP", "split_gap"),
                           ("GPSAT_SPLIT_BURST", "split_burst"), ("GPSAT_SHARE_MAX_LEN", "share_max_len"),
-                          ("GPSAT_SHARE_IMPORT_MAX", "share_import_max")):
+                          ("GPSAT_SHARE_IMPORT_MAX", "share_import_max"), ("GPSAT_SPLIT_HAND_WORDS", "split_hand_words")):
         if os.environ.get(env_name):
             extra[opt] = int(os.environ[env_name])
     if n_gpus > 1:

@@ -28,7 +28,8 @@ class GpsatOpts(C.Structure):
                 ("stop_on_sat", C.c_int32), ("max_conflicts", C.c_int64), ("share_learnts", C.c_int32),
                 ("share_max_len", C.c_int32), ("warps_per_block", C.c_int32), ("blocks", C.c_int32),
                 ("arena_words", C.c_int64), ("dynamic_split", C.c_int32), ("split_gap", C.c_int32),
-                ("split_burst", C.c_int32), ("share_import_max", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("split_burst", C.c_int32), ("share_import_max", C.c_int32), ("split_hand_words", C.c_int32),
+                ("reserved", C.c_int32 * 3)]
 
 
 class GpsatStats(C.Structure):

@@ -217,6 +217,13 @@ gpsat_formula_view make_view(gpsat *h)
     return F;
 }
 
+// learnt-clause words a split-off cube inherits (plus the level-0 facts, which share the space)
+int32_t hand_clause_words(const gpsat *h)
+{
+    const int32_t w = h->opts.split_hand_words > 0 ? h->opts.split_hand_words : 2048;   // measured best on C2
+    return std::max(w, 2 * h->D.n_vars + 64);
+}
+
 int32_t default_max_learnts(int64_t n_clauses, int32_t refs_cap, int32_t n_vars)
 {
     int64_t v = std::max<int64_t>(n_clauses / 3, 300);
@@ -328,7 +335,7 @@ int ensure_run_buffers(gpsat *h, int mode)
     if (mode == GPSAT_MODE_SOLVE && h->opts.dynamic_split) {
         CU(h->dq_lits.ensure((size_t)GPSAT_DQ_CAP * GPSAT_DQ_MAXK));
         CU(h->dq_meta.ensure((size_t)GPSAT_DQ_CAP * 4));
-        CU(h->dq_hand.ensure((size_t)GPSAT_DQ_CAP * (size_t)(1 + 2 * h->D.n_vars + GPSAT_HAND_CLAUSE_WORDS)));
+        CU(h->dq_hand.ensure((size_t)GPSAT_DQ_CAP * (size_t)(1 + 2 * h->D.n_vars + hand_clause_words(h))));
     }
     if (mode == GPSAT_MODE_SOLVE && h->opts.dynamic_split)
         CU(h->park.ensure(n_warps * (size_t)gpsat_park_words(h->D.n_vars)));
@@ -365,7 +372,7 @@ gpsat_run_buffers make_buffers(gpsat *h, int mode, double budget_ms)
     B.dq_ctrl = h->dq_ctrl.p;
     B.root_pending = h->root_pending.p;
     B.dq_hand = h->dq_hand.p;
-    B.hand_words = 1 + 2 * h->D.n_vars + GPSAT_HAND_CLAUSE_WORDS;
+    B.hand_words = 1 + 2 * h->D.n_vars + hand_clause_words(h);
     B.dq_cap = GPSAT_DQ_CAP;
     B.root_flag = h->root_flag.p;
     B.t0 = h->t0.p;

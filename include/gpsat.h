@@ -116,7 +116,8 @@ typedef struct gpsat_opts {
     int32_t split_gap;            /* conflicts a cube runs between two rounds of splitting; 0 = default (8) */
     int32_t split_burst;          /* children handed out per round while warps are idle; 0 = default (4) */
     int32_t share_import_max;     /* non-unit shared clauses a cube imports per pool when it starts; 0 = default (256) */
-    int32_t reserved[4];
+    int32_t split_hand_words;     /* learnt-clause words a split-off cube inherits from its parent; 0 = default */
+    int32_t reserved[3];
 } gpsat_opts;
 
 void gpsat_opts_default(gpsat_opts *o);
