@@ -45,10 +45,12 @@ struct WarpSolver {
     int *lbuf;
     int lbuf_words;
     int *cube_buf;        // this job's cube when it may grow by splitting (GPSAT_DQ_MAXK literals)
-    // ---- this warp's learnt arena (global): [lw_ptr | lw_size | lw_cap | hist | refs | clauses ->   <- watch vectors]
+    // ---- this warp's learnt arena (global): [lw_head: (ptr, size, cap) per literal | hist | refs | clauses ->   <- watch vectors]
+    // the three words of a watch-vector head share a sector, so one round trip fetches them
     int *arena;
     int arena_words;
-    int *lw_ptr, *lw_size, *lw_cap, *hist, *refs;
+    int *lw_head, *hist, *refs;
+    uint32_t *lwbits;     // per literal: does any learnt clause watch it?  (shared memory; saves the round trip when not)
     int refs_cap;
     int clause_base;
     // ---- warp-uniform scalars
@@ -141,7 +143,7 @@ struct WarpSolver {
     GPSAT_DEV void lw_append(int x, int cref, int blocker)
     {
         GPSAT_LANE_DECL
-        int n = lw_size[x], cap = lw_cap[x], ptr = lw_ptr[x];
+        int n = lw_head[3 * x + 1], cap = lw_head[3 * x + 2], ptr = lw_head[3 * x];
         if (n == cap) {
             const int ncap = cap ? 2 * cap : 4;
             const int nptr = watch_bot - 2 * ncap;
@@ -158,8 +160,8 @@ struct WarpSolver {
             SYNCWARP();
             LANE0
             {
-                lw_ptr[x] = nptr;
-                lw_cap[x] = ncap;
+                lw_head[3 * x] = nptr;
+                lw_head[3 * x + 2] = ncap;
             }
             ptr = nptr;
         }
@@ -167,7 +169,8 @@ struct WarpSolver {
         {
             arena[ptr + 2 * n] = cref;
             arena[ptr + 2 * n + 1] = blocker;
-            lw_size[x] = n + 1;
+            lw_head[3 * x + 1] = n + 1;
+            lwbits[x >> 5] |= 1u << (x & 31);
         }
         SYNCWARP();
     }
@@ -180,6 +183,14 @@ struct WarpSolver {
         while (qhead < trail_size) {
             const int p = trail[qhead++];
             const int f = p ^ 1;
+            // learnt watch vector of f: fetch its head now (one global round trip) so that the latency overlaps the scan
+            // of the original clauses; nothing in part (1) changes it
+            const bool has_lw = use_learnts && ((lwbits[f >> 5] >> (f & 31)) & 1u);
+            int wn = 0, wp = 0;
+            if (has_lw) {
+                wp = lw_head[3 * f];
+                wn = lw_head[3 * f + 1];
+            }
 
             // (1) original clauses: occurrence slots of f whose watch bit is set
             const int os = gpsat_ld(ostart + f), oe = gpsat_ld(ostart + f + 1);
@@ -258,10 +269,7 @@ struct WarpSolver {
             }
 
             // (2) learnt clauses watching f, MiniSat order, the warp cooperating on one clause at a time
-            if (!use_learnts) continue;
-            const int wn = lw_size[f];
             if (wn == 0) continue;
-            const int wp = lw_ptr[f];
             c_lwatchers += wn;
             int confl = GPSAT_NO_CONFLICT;
             int j = 0;
@@ -363,7 +371,11 @@ struct WarpSolver {
                 j += gpsat_popc(km);
                 SYNCWARP();
             }
-            LANE0 { lw_size[f] = j; }
+            LANE0
+            {
+                lw_head[3 * (f) + 1] = j;
+                if (j == 0) lwbits[f >> 5] &= ~(1u << (f & 31));
+            }
             SYNCWARP();
             if (confl != GPSAT_NO_CONFLICT) return confl;
         }
@@ -684,7 +696,9 @@ struct WarpSolver {
         LANES
         {
             GPSAT_NOUNROLL
-            for (int x = lane; x < 2 * n_vars; x += 32) lw_size[x] = 0;
+            for (int x = lane; x < 2 * n_vars; x += 32) lw_head[3 * (x) + 1] = 0;
+            GPSAT_NOUNROLL
+            for (int w = lane; w < (2 * n_vars + 31) / 32; w += 32) lwbits[w] = 0u;
         }
         SYNCWARP();
         LANES
@@ -692,8 +706,8 @@ struct WarpSolver {
             GPSAT_NOUNROLL
             for (int i = lane; i < n_learnts; i += 32) {
                 const int r = refs[i];
-                gpsat_atomic_add(lw_size + arena[r + 1], 1);
-                gpsat_atomic_add(lw_size + arena[r + 2], 1);
+                gpsat_atomic_add(lw_head + 3 * arena[r + 1] + 1, 1);
+                gpsat_atomic_add(lw_head + 3 * arena[r + 2] + 1, 1);
             }
         }
         SYNCWARP();
@@ -705,7 +719,7 @@ struct WarpSolver {
             LANES
             {
                 const int x = base + lane;
-                LV(cntv) = x < 2 * n_vars ? lw_size[x] : 0;
+                LV(cntv) = x < 2 * n_vars ? lw_head[3 * (x) + 1] : 0;
                 LV(ptrv) = 0;
             }
             GPSAT_NOUNROLL
@@ -720,9 +734,9 @@ struct WarpSolver {
             {
                 const int x = base + lane;
                 if (x < 2 * n_vars) {
-                    lw_ptr[x] = LV(ptrv);
-                    lw_cap[x] = LV(cntv) > 0 ? 2 * LV(cntv) + 4 : 0;
-                    lw_size[x] = 0;
+                    lw_head[3 * (x)] = LV(ptrv);
+                    lw_head[3 * (x) + 2] = LV(cntv) > 0 ? 2 * LV(cntv) + 4 : 0;
+                    lw_head[3 * (x) + 1] = 0;
                 }
             }
             SYNCWARP();
@@ -793,10 +807,23 @@ struct WarpSolver {
                 GPSAT_NOUNROLL
                 for (int x = lane; x < 2 * n_vars; x += 32) {
                     vs[x] = vsids0[x];
-                    lw_size[x] = 0;
-                    lw_cap[x] = 0;
-                    lw_ptr[x] = 0;
+                    lw_head[3 * (x) + 1] = 0;
+                    lw_head[3 * (x) + 2] = 0;
+                    lw_head[3 * (x)] = 0;
                 }
+            }
+            // learnt-watch bitmap: empty for a fresh job, rebuilt from the heads when a parked job resumes
+            GPSAT_NOUNROLL
+            for (int w = lane; w < (2 * n_vars + 31) / 32; w += 32) {
+                uint32_t bits = 0u;
+                if (use_learnts && keep_learnts) {
+                    GPSAT_NOUNROLL
+                    for (int b = 0; b < 32; ++b) {
+                        const int x = 32 * w + b;
+                        if (x < 2 * n_vars && lw_head[3 * x + 1] > 0) bits |= 1u << b;
+                    }
+                }
+                lwbits[w] = bits;
             }
             LV(l_watchers) = 0;
             LV(l_words) = 0;
@@ -1390,9 +1417,8 @@ GPSAT_DEV void gpsat_bind(WarpSolver &S, const gpsat_formula_view &F, const gpsa
     S.use_learnts = (P.mode == GPSAT_MODE_SOLVE) ? 1 : 0;
     S.arena = arena;
     S.arena_words = (int)P.arena_words;
-    S.lw_ptr = arena;
-    S.lw_size = arena + 2 * F.n_vars;
-    S.lw_cap = arena + 4 * F.n_vars;
+    S.lw_head = arena;
+    S.lwbits = (uint32_t *)(state + Ly.lwbits);
     S.hist = arena + 6 * F.n_vars;
     S.refs = arena + 6 * F.n_vars + 64;
     S.refs_cap = P.learnt_refs_cap;

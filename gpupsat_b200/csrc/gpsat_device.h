@@ -78,7 +78,7 @@ struct gpsat_solve_params {
 
 // word offsets (int32 units) of the per-warp state arrays inside one warp's state block
 struct gpsat_state_layout {
-    int32_t val, seen, level, reason, trail, trail_lim, wbits, vs, lbuf, cube;
+    int32_t val, seen, level, reason, trail, trail_lim, wbits, vs, lbuf, cube, lwbits;
     int32_t total_words;
     int32_t lbuf_words;
 };
@@ -143,6 +143,7 @@ static inline void gpsat_make_layout(int32_t n_vars, int64_t n_lits, gpsat_state
     ly->lbuf_words = (n + 1) > 64 ? (n + 1) : 64;
     GPSAT_TAKE(lbuf, ly->lbuf_words);
     GPSAT_TAKE(cube, GPSAT_DQ_MAXK);
+    GPSAT_TAKE(lwbits, (2 * n + 31) / 32);
 #undef GPSAT_TAKE
     ly->total_words = at;
 }

@@ -19,6 +19,7 @@
 
 #include <cstring>
 #define GPSAT_DEV inline
+#define GPSAT_DEV_OUTLINE inline
 #define GPSAT_NOUNROLL
 #define GPSAT_LANE_DECL
 #define LANEVAR(T, name) T name[32]
@@ -77,6 +78,7 @@ static inline int gpsat_ld(const int *p) { return *p; }
 #else  // ---- CUDA device build ----
 
 #define GPSAT_DEV __device__ __forceinline__
+#define GPSAT_DEV_OUTLINE __device__ __noinline__
 // every warp of a block is at a different point of a large program: code size (instruction-cache footprint), not
 // loop overhead, is what costs issue slots here, so loops are kept rolled
 #define GPSAT_NOUNROLL _Pragma("unroll 1")
