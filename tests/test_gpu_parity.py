@@ -321,3 +321,55 @@ def test_sat_instance_model_through_cubes():
             if found == 3:
                 break
     assert found == 3
+
+
+def test_edge_cases_ragged_cubes_long_clauses_absent_vars():
+    """clauses longer than a warp, cubes of different lengths (empty, contradictory, touching variables that do not occur
+    in the formula), both modes: every record equals the oracle's"""
+    rng = np.random.default_rng(5)
+    n = 96
+    cl = []
+    for _ in range(60):
+        ln = int(rng.choice([2, 3, 3, 5, 40, 70]))
+        vs = rng.choice(90, size=ln, replace=False)          # variables 90..95 never occur
+        cl.append([int(2 * v + rng.integers(0, 2)) for v in vs])
+    offs = np.cumsum([0] + [len(c) for c in cl]).astype(np.int64)
+    lits = np.array([x for c in cl for x in c], dtype=np.int32)
+    cubes = [[], [1], [1, 0], [3, 4, 9, 11, 20], [2 * v for v in range(30)], [2 * v + 1 for v in range(45)],
+             [2 * 93 + 1, 5], [2 * 95, 2 * 95 + 1]]
+    co = np.cumsum([0] + [len(c) for c in cubes]).astype(np.int64)
+    clits = np.array([x for c in cubes for x in c], dtype=np.int32)
+    o = Oracle(n, offs, lits)
+    with g.Solver(n, offs, lits, stop_on_sat=0, dynamic_split=0) as s:
+        s.set_cubes(cube_offsets=co, cube_lits=clits)
+        got = s.propagate_all()
+        want = o.run(co, clits, mode=1, stop_on_sat=False)
+        _cmp_records(got["records"], want["records"], "ragged propagate")
+        assert np.array_equal(got["implied"], want["implied"])
+        verdict, model, stats = s.solve()
+        rec = s.job_records()
+    want = o.run(co, clits, mode=0, stop_on_sat=False)
+    _cmp_records(rec, want["records"], "ragged solve")
+    assert rec["status"][2] == g.UNSAT and rec["status"][7] == g.UNSAT      # x and ~x in one cube
+    if verdict == g.SAT:
+        assert check_model(offs, lits, model)
+
+
+def test_maximum_cube_count_and_bad_arguments():
+    """MAX_VARS = 15 -> 32768 cubes (Configs.cuh:40): all of them propagate; malformed inputs are refused, not run"""
+    offs, lits = random_ksat(250, 1065, 1)
+    cnf, pre = _prep(offs, lits)
+    cubes = pre.choose_cubes(32, 1024)
+    assert cubes.shape == (32768, 15)
+    with g.Solver(cnf.n_vars, pre.offsets, pre.lits) as s:
+        s.set_cubes(cubes)
+        got = s.propagate_all(want_implied=False)
+        assert set(np.unique(got["status"]).tolist()) <= {g.UNSAT, g.UNDEF}
+        want = Oracle(cnf.n_vars, pre.offsets, pre.lits).run(np.arange(0, 15 * 512 + 1, 15, dtype=np.int64),
+                                                              cubes[:512].reshape(-1), mode=1)
+        assert np.array_equal(got["status"][:512], want["records"]["status"])
+        assert np.array_equal(got["n_implied"][:512], want["n_implied"])
+        with pytest.raises(g.GpsatError):
+            s.set_cubes(np.array([[2 * cnf.n_vars + 4]], dtype=np.int32))          # literal out of range
+    with pytest.raises(g.GpsatError):
+        g.Solver(3, np.array([0, 1, 3], dtype=np.int64), np.array([1, 2, 4], dtype=np.int32))   # unit clause
