@@ -136,7 +136,7 @@ struct gpsat {
     DevBuf<uint32_t> wbits0;
     DevBuf<uint8_t> val0;
     // occurrence-mode BCP (opts.bcp == GPSAT_BCP_OCCURRENCE)
-    DevBuf<int32_t> occ_clause, occ_pair;
+    DevBuf<int32_t> occ_clause, occ_pair, orange;
     DevBuf<uint32_t> valbits;
     DevBuf<int64_t> sweep_counters;
     int uniform3 = 0;
@@ -561,7 +561,7 @@ int propagate_all_occurrence(gpsat *h, int32_t *status, int32_t *n_implied, int3
     L.n_clauses = (int32_t)h->D.n_clauses;
     L.n_cubes = h->n_cubes;
     L.uniform3 = h->uniform3;
-    L.ostart = h->ostart.p;
+    L.ostart = h->orange.p;
     L.occ_clause = h->occ_clause.p;
     L.occ_pair = h->occ_pair.p;
     L.coffsets = h->coffsets.p;
@@ -731,23 +731,39 @@ int gpsat_create(gpsat_t **out, int32_t n_vars, int64_t n_clauses, const int64_t
     CUH(h->coffsets.upload(h->coffsets_h.data(), h->coffsets_h.size(), h->stream));
     CUH(h->clits.upload(lits + base, (size_t)h->D.n_lits, h->stream));
     if (h->opts.bcp == GPSAT_BCP_OCCURRENCE) {
-        // occurrence slot -> clause index, and for pure 3-SAT the two other literals of that clause (no clause
-        // dereference on the hot path)
+        // Occurrence lists for the sweep kernels, PADDED: every literal's list starts at an even entry index and is
+        // padded to an even length with a (-1) sentinel, so that the kernel reads it as 16-byte loads of two entries
+        // and finds (begin, end) of a list with ONE 8-byte load (orange) — half the memory requests per literal of
+        // the plain CSR.  Per entry: the clause index, and for pure 3-SAT the two other literals of that clause (no
+        // clause dereference on the hot path).
         const size_t L = (size_t)h->D.n_lits;
-        std::vector<int32_t> oc(L), op;
+        const size_t n_lit_ids = 2 * (size_t)std::max(n_vars, 0);
         h->uniform3 = (h->D.n_clauses > 0 && h->D.n_lits == 3 * h->D.n_clauses && h->D.max_clause_len == 3) ? 1 : 0;
-        if (h->uniform3) op.resize(2 * L);
-        for (size_t k = 0; k < L; k++) {
-            const int32_t s0 = h->D.occ2[2 * k], len = h->D.occ2[2 * k + 1];
-            oc[k] = h->D.cl2[2 * (size_t)(s0 - 1) + 1];
-            if (h->uniform3) {
-                int w = 0;
-                for (int i = 0; i < len; i++) {
-                    if (h->D.cl2[2 * (size_t)(s0 + i) + 1] == (int32_t)k) continue;
-                    op[2 * k + (w++)] = h->D.cl2[2 * (size_t)(s0 + i)];
+        std::vector<int32_t> orange(2 * n_lit_ids, 0), oc, op;
+        oc.reserve(L + n_lit_ids);
+        if (h->uniform3) op.reserve(2 * (L + n_lit_ids));
+        for (size_t f = 0; f < n_lit_ids; f++) {
+            orange[2 * f] = (int32_t)oc.size();
+            for (int32_t k = h->D.ostart[f]; k < h->D.ostart[f + 1]; k++) {
+                const int32_t s0 = h->D.occ2[2 * (size_t)k], len = h->D.occ2[2 * (size_t)k + 1];
+                oc.push_back(h->D.cl2[2 * (size_t)(s0 - 1) + 1]);
+                if (h->uniform3)
+                    for (int i = 0; i < len; i++) {
+                        if (h->D.cl2[2 * (size_t)(s0 + i) + 1] == k) continue;
+                        op.push_back(h->D.cl2[2 * (size_t)(s0 + i)]);
+                    }
+            }
+            if (oc.size() & 1) {
+                oc.push_back(-1);
+                if (h->uniform3) {
+                    op.push_back(-1);
+                    op.push_back(-1);
                 }
             }
+            orange[2 * f + 1] = (int32_t)oc.size();
         }
+        if (oc.empty()) oc.push_back(-1);
+        CUH(h->orange.upload(orange.data(), orange.size(), h->stream));
         CUH(h->occ_clause.upload(oc.data(), oc.size(), h->stream));
         if (h->uniform3) CUH(h->occ_pair.upload(op.data(), op.size(), h->stream));
         CUH(cudaStreamSynchronize(h->stream));

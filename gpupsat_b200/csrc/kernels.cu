@@ -280,9 +280,10 @@ namespace {
 struct SweepArgs {
     int32_t n_vars, n_clauses, n_cubes;
     int32_t uniform3;                 // every clause has exactly 3 literals: use the (other, other) pair entries
-    const int32_t *ostart;            // 2n+1
-    const int32_t *occ_clause;        // n_lits : clause index per occurrence slot
-    const int2 *occ_pair;             // n_lits : the two other literals of that clause (uniform3 only)
+    const int2 *orange;               // 2n : (begin, end) of a literal's PADDED occurrence list: begin and end are even,
+                                      //      padding entries hold -1
+    const int32_t *occ_clause;        // per entry: clause index
+    const int2 *occ_pair;             // per entry: the two other literals of that clause (uniform3 only)
     const int32_t *coffsets;          // n_clauses+1 (general path)
     const int32_t *clits;             // compact literals
     const int64_t *cube_offsets;
@@ -355,12 +356,14 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_kernel(const SweepArg
             if (t < total) {
                 const int p = t < k ? cube[t] : imp[t - k];
                 const int f = p ^ 1;
-                const int os = __ldg(A.ostart + f), oe = __ldg(A.ostart + f + 1);
+                const int2 rg = __ldg(A.orange + f);
+                const int os = rg.x, oe = rg.y;
                 for (int e = os; e < oe; ++e) {
                     int a, b, c = -1, unit = -1, n_false = 0, n_undef = 0;
                     bool sat = false;
                     if (A.uniform3) {
                         const int2 pr = __ldg(A.occ_pair + e);
+                        if (pr.x < 0) continue;   // padding
                         a = pr.x;
                         b = pr.y;
                         const int va = sw_value(vb, a), vb2 = sw_value(vb, b);
@@ -371,6 +374,7 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_kernel(const SweepArg
                         words += 2;
                     } else {
                         c = __ldg(A.occ_clause + e);
+                        if (c < 0) continue;      // padding
                         const int lb = __ldg(A.coffsets + c), le = __ldg(A.coffsets + c + 1);
                         for (int i = lb; i < le && !sat; ++i) {
                             const int x = __ldg(A.clits + i);
@@ -500,12 +504,28 @@ enum { CW_COUNT = 0, CW_CONFLICT, CW_CLAUSE, CW_JOB, CW_SNAP_TOTAL, CW_SNAP_CONF
 
 struct ClusterBits {
     uint32_t base;        // shared-window address of this CTA's slice (same offset in every CTA of the cluster)
+    uint32_t base0;       // shared::cluster address of rank 0's slice
+    uint32_t stride;      // shared::cluster address distance between consecutive ranks (0: not linear, use mapa)
     int slice_log2;       // words per slice = 1 << slice_log2
+    // `mapa` executes on the XU pipe (16 lanes per SM and cycle): one per lookup kept that pipe 89 % busy and made it
+    // the limiter of the kernel (profiles/r01_sweepc_ncu_f.json).  The cluster window is linear in the rank, so the
+    // remote address is one multiply-add; init() verifies the linearity and falls back to mapa otherwise.
+    __device__ __forceinline__ void init(const void *slice, int log2_words, uint32_t csize)
+    {
+        base = smem_u32(slice);
+        slice_log2 = log2_words;
+        base0 = dsm_addr(base, 0);
+        stride = csize > 1 ? dsm_addr(base, 1) - base0 : 0u;
+        for (uint32_t r = 2; r < csize; ++r)
+            if (dsm_addr(base, r) != base0 + r * stride) stride = 0u;
+        if (csize == 1) stride = 1u;   // any non-zero value: rank is always 0
+    }
     // address of the word holding literal x's variable (16 variables per word)
     __device__ __forceinline__ uint32_t word_addr(int x) const
     {
         const uint32_t w = (uint32_t)x >> 5;
-        return dsm_addr(base + ((w & ((1u << slice_log2) - 1u)) << 2), w >> slice_log2);
+        const uint32_t off = (w & ((1u << slice_log2) - 1u)) << 2, r = w >> slice_log2;
+        return stride ? base0 + r * stride + off : dsm_addr(base + off, r);
     }
     __device__ __forceinline__ int value(int x) const   // 1 true, 0 false, 2 unassigned
     {
@@ -527,8 +547,7 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_cluster_kernel(const 
     const int cthreads = (int)(csize * blockDim.x), ctid = (int)(rank * blockDim.x + threadIdx.x);
     const int slice_words = 1 << slice_log2;
     ClusterBits bits;
-    bits.base = smem_u32(s_slice);
-    bits.slice_log2 = slice_log2;
+    bits.init(s_slice, slice_log2, csize);
     const uint32_t ctrl0 = dsm_addr(smem_u32(s_ctrl), 0);   // the leader's control words
 
     while (true) {
@@ -575,24 +594,35 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_cluster_kernel(const 
             for (int t = qhead + ctid; t < total; t += cthreads) {
                 const int p = t < k ? __ldg(cube + t) : __ldcg(imp + (t - k));
                 const int f = p ^ 1;
-                const int os = __ldg(A.ostart + f), oe = __ldg(A.ostart + f + 1);
+                const int2 rg = __ldg(A.orange + f);
+                const int os = rg.x, oe = rg.y;   // both even: the list is read as 16-byte loads of two entries
                 for (int e0 = os; e0 < oe; e0 += 4) {
                     const int cnt = min(4, oe - e0);
                     if (A.uniform3) {
                         int2 pr[4];
                         int va[4], vb[4];
+                        {
+                            const int4 q0 = __ldg(reinterpret_cast<const int4 *>(A.occ_pair + e0));
+                            pr[0] = make_int2(q0.x, q0.y);
+                            pr[1] = make_int2(q0.z, q0.w);
+                            pr[2] = pr[3] = make_int2(-1, -1);
+                            if (cnt > 2) {
+                                const int4 q1 = __ldg(reinterpret_cast<const int4 *>(A.occ_pair + e0 + 2));
+                                pr[2] = make_int2(q1.x, q1.y);
+                                pr[3] = make_int2(q1.z, q1.w);
+                            }
+                        }
+                        int real = 0;
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            if (j < cnt) pr[j] = __ldg(A.occ_pair + e0 + j);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (j < cnt) {
+                            if (pr[j].x >= 0) {
                                 va[j] = bits.value(pr[j].x);
                                 vb[j] = bits.value(pr[j].y);
+                                real++;
                             }
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            if (j < cnt) {
+                            if (pr[j].x >= 0) {
                                 if (va[j] == 1 || vb[j] == 1) continue;
                                 const int n_undef = (va[j] == 2) + (vb[j] == 2);
                                 if (n_undef > 1) continue;
@@ -611,11 +641,12 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_cluster_kernel(const 
                                     dsm_st(ctrl0 + 4 * CW_CONFLICT, 1u);
                                 }
                             }
-                        visited += cnt;
-                        words += 2 * cnt;
+                        visited += real;
+                        words += 2 * real;
                     } else {
                         for (int j = 0; j < cnt; ++j) {
                             const int c = __ldg(A.occ_clause + e0 + j);
+                            if (c < 0) continue;   // padding
                             const int lb = __ldg(A.coffsets + c), le = __ldg(A.coffsets + c + 1);
                             int unit = -1, n_undef = 0;
                             bool sat = false;
@@ -687,7 +718,7 @@ cudaError_t launch_bcp_sweep(const SweepLaunch &L, cudaStream_t stream)
     A.n_clauses = L.n_clauses;
     A.n_cubes = L.n_cubes;
     A.uniform3 = L.uniform3;
-    A.ostart = L.ostart;
+    A.orange = (const int2 *)L.ostart;
     A.occ_clause = L.occ_clause;
     A.occ_pair = (const int2 *)L.occ_pair;
     A.coffsets = L.coffsets;

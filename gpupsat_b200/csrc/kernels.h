@@ -35,7 +35,8 @@ cudaError_t launch_eval_clauses(int32_t n_vars, int32_t n_clauses, const int32_t
 // BCP by clause evaluation over occurrence lists for large clause databases (warp per job, state in HBM)
 struct SweepLaunch {
     int32_t n_vars, n_clauses, n_cubes, uniform3;
-    const int32_t *ostart, *occ_clause, *occ_pair, *coffsets, *clits;
+    const int32_t *ostart;   // (begin, end) pairs of the padded occurrence lists (int2 per literal)
+    const int32_t *occ_clause, *occ_pair, *coffsets, *clits;
     const int64_t *cube_offsets;
     const int32_t *cube_lits;
     uint32_t *valbits;
