@@ -280,6 +280,7 @@ namespace {
 struct SweepArgs {
     int32_t n_vars, n_clauses, n_cubes;
     int32_t uniform3;                 // every clause has exactly 3 literals: use the (other, other) pair entries
+    int32_t stream_index;             // read the occurrence index with evict-first loads (keeps the value blocks in L2)
     const int2 *orange;               // 2n : (begin, end) of a literal's PADDED occurrence list: begin and end are even,
                                       //      padding entries hold -1
     const int32_t *occ_clause;        // per entry: clause index
@@ -707,6 +708,227 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_cluster_kernel(const 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// gpsat_bcp_sweep_cta_kernel — occurrence-list BCP with ONE CTA per job and a two-level assignment:
+//   A  "assigned" bit per variable in SHARED memory (n/8 bytes: 125 KB at n = 1e6, fits one SM);
+//   V  2-bit (valid, value) field per variable in global memory (this CTA's 250 KB block, L2 resident).
+// A literal is assigned by ONE atomicOr on V — its return value says whether the variable was still free (the
+// authority for "append to the trail exactly once") or already carried the same / the opposite value — followed by
+// setting the A bit.  A lookup first tests A in shared memory: 87 % of the lookups of config 4 hit an unassigned
+// variable and end there; only when A is set is V read (V was written before A, so it is valid by then).
+// Compared with the cluster kernel this removes ALL traffic on the SM-to-SM network (ncu: the cluster kernel moves
+// 32 GB of 32-byte DSMEM sectors per launch for 2-bit lookups and is bound by that network), doubles the number of
+// jobs in flight (148 instead of 74) and turns the per-round cluster barriers into __syncthreads().
+// A stale A bit can only read "unassigned" for a variable assigned during the current round; the literal that made
+// it assigned is processed in a later round (after a barrier) and re-examines the clause, so no unit is lost.
+// ---------------------------------------------------------------------------------------------------------------
+#define GPSAT_SWEEP_CHUNK 8
+struct CtaBits {
+    uint32_t *a;          // shared: assigned bits, a FILTER of 2^k bits indexed by var & mask (exact when 2^k >= n;
+                          // when smaller, a set bit may belong to an aliased variable and V decides)
+    uint32_t *v;          // global: 2-bit fields, 16 variables per word
+    uint32_t mask;
+    __device__ __forceinline__ int value(int x) const   // 1 true, 0 false, 2 unassigned
+    {
+        const int var = x >> 1;
+        const uint32_t fb = (uint32_t)var & mask;
+        if (!((a[fb >> 5] >> (fb & 31)) & 1u)) return 2;
+        const uint32_t f = (__ldcg(v + (var >> 4)) >> ((var & 15) * 2)) & 3u;
+        return (f & 2u) ? (int)((f & 1u) == (uint32_t)(x & 1)) : 2;
+    }
+    __device__ __forceinline__ uint32_t assign(int x) const   // previous 2-bit field (0 = was unassigned)
+    {
+        const int var = x >> 1, sh = (var & 15) * 2;
+        const uint32_t prev = (atomicOr(v + (var >> 4), (2u | (uint32_t)(x & 1)) << sh) >> sh) & 3u;
+        if (prev == 0) {
+            const uint32_t fb = (uint32_t)var & mask;
+            atomicOr(a + (fb >> 5), 1u << (fb & 31));
+        }
+        return prev;
+    }
+};
+
+template <int kThreads, int kBlocksPerSm>
+__global__ void __launch_bounds__(kThreads, kBlocksPerSm) gpsat_bcp_sweep_cta_kernel(const SweepArgs A, const int filter_log2)
+{
+    extern __shared__ __align__(16) uint32_t s_abits[];
+    __shared__ int s_count, s_conflict, s_clause, s_job, s_total, s_stop;
+    const int tid = (int)threadIdx.x, nthreads = (int)blockDim.x;
+    const int a_words = 1 << (filter_log2 - 5);
+    CtaBits bits;
+    bits.a = s_abits;
+    bits.mask = (1u << filter_log2) - 1u;
+    bits.v = A.valbits + (size_t)blockIdx.x * (size_t)A.val_words;
+
+    while (true) {
+        if (tid == 0) {
+            s_job = atomicAdd(A.next_job, 1);
+            s_count = 0;
+            s_conflict = 0;
+            s_clause = -1;
+        }
+        for (int i = tid; i < a_words; i += nthreads) s_abits[i] = 0u;
+        {   // this CTA's V block back to all-unassigned (coalesced 16-byte stores; val_words is a multiple of 4)
+            uint4 *z = reinterpret_cast<uint4 *>(bits.v);
+            for (int i = tid; i < A.val_words / 4; i += nthreads) z[i] = make_uint4(0, 0, 0, 0);
+        }
+        __threadfence();
+        __syncthreads();
+        const int job = s_job;
+        if (job >= A.n_cubes) break;
+        const long long c0 = A.cube_offsets[job], c1 = A.cube_offsets[job + 1];
+        const int k = (int)(c1 - c0);
+        const int32_t *cube = A.cube_lits + c0;
+        int32_t *imp = A.implied + (long long)job * A.stride;
+
+        for (int i0 = tid; i0 < k; i0 += 4 * nthreads) {   // phase 0: the whole cube is assigned up front,
+            int x[4];                                       // four atomics in flight per thread
+            uint32_t prev[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) x[u] = i0 + u * nthreads < k ? __ldg(cube + i0 + u * nthreads) : -1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) prev[u] = x[u] >= 0 ? bits.assign(x[u]) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (x[u] >= 0 && (prev[u] & 2u) && (prev[u] & 1u) != (uint32_t)(x[u] & 1)) s_conflict = 1;   // x and ~x
+        }
+        __syncthreads();
+        if (tid == 0) {
+            s_total = k;
+            s_stop = s_conflict;
+        }
+        __syncthreads();
+
+        long long visited = 0, words = 0;
+        int qhead = 0;
+        while (true) {
+            const int total = s_total;
+            if (s_stop || qhead >= total) break;
+            for (int t = qhead + tid; t < total; t += nthreads) {
+                const int p = t < k ? __ldg(cube + t) : __ldcg(imp + (t - k));
+                const int f = p ^ 1;
+                const int2 rg = A.stream_index ? __ldcs(A.orange + f) : __ldg(A.orange + f);
+                const int os = rg.x, oe = rg.y;   // both even: the list is read as 16-byte loads of two entries
+                for (int e0 = os; e0 < oe; e0 += GPSAT_SWEEP_CHUNK) {
+                    const int cnt = min(GPSAT_SWEEP_CHUNK, oe - e0);
+                    if (A.uniform3) {
+                        // all loads of a chunk are issued before anything depends on them: pairs, then the assigned
+                        // bits (shared), then the value fields (global) — three round trips per chunk, and a chunk of
+                        // 8 entries covers most literals of a 3-SAT formula (6 occurrences on average)
+                        int2 pr[GPSAT_SWEEP_CHUNK];
+                        int va[GPSAT_SWEEP_CHUNK], vb[GPSAT_SWEEP_CHUNK];
+#pragma unroll
+                        for (int j = 0; j < GPSAT_SWEEP_CHUNK; j += 2) {
+                            pr[j] = pr[j + 1] = make_int2(-1, -1);
+                            if (j < cnt) {
+                                const int4 *qp = reinterpret_cast<const int4 *>(A.occ_pair + e0 + j);
+                                const int4 q = A.stream_index ? __ldcs(qp) : __ldg(qp);
+                                pr[j] = make_int2(q.x, q.y);
+                                pr[j + 1] = make_int2(q.z, q.w);
+                            }
+                        }
+                        int real = 0;
+#pragma unroll
+                        for (int j = 0; j < GPSAT_SWEEP_CHUNK; ++j)
+                            if (pr[j].x >= 0) {
+                                va[j] = bits.value(pr[j].x);
+                                vb[j] = bits.value(pr[j].y);
+                                real++;
+                            }
+#pragma unroll
+                        for (int j = 0; j < GPSAT_SWEEP_CHUNK; ++j)
+                            if (pr[j].x >= 0) {
+                                if (va[j] == 1 || vb[j] == 1) continue;
+                                const int n_undef = (va[j] == 2) + (vb[j] == 2);
+                                if (n_undef > 1) continue;
+                                if (n_undef == 0) {   // every other literal false: conflict
+                                    s_clause = __ldg(A.occ_clause + e0 + j);
+                                    s_conflict = 1;
+                                    continue;
+                                }
+                                const int unit = (va[j] == 2) ? pr[j].x : pr[j].y;
+                                const uint32_t prev = bits.assign(unit);
+                                if (prev == 0) {
+                                    const int pos = atomicAdd(&s_count, 1);
+                                    if (pos < A.stride) imp[pos] = unit;
+                                } else if ((prev & 1u) != (uint32_t)(unit & 1)) {   // lost a race against ~unit
+                                    s_clause = __ldg(A.occ_clause + e0 + j);
+                                    s_conflict = 1;
+                                }
+                            }
+                        visited += real;
+                        words += 2 * real;
+                    } else {
+                        for (int j = 0; j < cnt; ++j) {
+                            const int c = __ldg(A.occ_clause + e0 + j);
+                            if (c < 0) continue;   // padding
+                            const int lb = __ldg(A.coffsets + c), le = __ldg(A.coffsets + c + 1);
+                            int unit = -1, n_undef = 0;
+                            bool sat = false;
+                            for (int i = lb; i < le && !sat; ++i) {
+                                const int x = __ldg(A.clits + i);
+                                words++;
+                                if (x == f) continue;
+                                const int v = bits.value(x);
+                                if (v == 1) sat = true;
+                                else if (v == 2) { n_undef++; unit = x; }
+                            }
+                            visited++;
+                            if (sat || n_undef > 1) continue;
+                            if (n_undef == 0) {
+                                s_clause = c;
+                                s_conflict = 1;
+                                continue;
+                            }
+                            const uint32_t prev = bits.assign(unit);
+                            if (prev == 0) {
+                                const int pos = atomicAdd(&s_count, 1);
+                                if (pos < A.stride) imp[pos] = unit;
+                            } else if ((prev & 1u) != (uint32_t)(unit & 1)) {
+                                s_clause = c;
+                                s_conflict = 1;
+                            }
+                        }
+                    }
+                }
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                s_total = k + (int)min((long long)s_count, (long long)A.stride);
+                s_stop = s_conflict;
+            }
+            __syncthreads();
+            qhead = total;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            visited += __shfl_xor_sync(0xffffffffu, visited, o);
+            words += __shfl_xor_sync(0xffffffffu, words, o);
+        }
+        if ((tid & 31) == 0 && A.counters) {
+            atomicAdd((unsigned long long *)(A.counters + 2 * job), (unsigned long long)visited);
+            atomicAdd((unsigned long long *)(A.counters + 2 * job + 1), (unsigned long long)words);
+        }
+        if (tid == 0) {
+            const int n_imp = s_count, conflict = s_conflict;
+            A.status[job] = conflict ? GPSAT_UNSAT : (n_imp > A.stride ? GPSAT_JOB_OOM : GPSAT_UNDEF);
+            A.n_implied[job] = n_imp;
+            A.conflict_clause[job] = conflict ? (long long)s_clause : -1;
+        }
+        __syncthreads();
+    }
+}
+
+typedef void (*cta_sweep_kernel_t)(const SweepArgs, const int);
+// register budgets: 1 CTA x 1024 threads (64 registers), 2 x 768 (42), 2 x 1024 (32)
+cta_sweep_kernel_t pick_cta_sweep(int threads, int per_sm)
+{
+    if (per_sm >= 2 && threads > 768) return gpsat_bcp_sweep_cta_kernel<1024, 2>;
+    if (per_sm >= 2) return gpsat_bcp_sweep_cta_kernel<768, 2>;
+    return gpsat_bcp_sweep_cta_kernel<1024, 1>;
+}
+
 }  // namespace
 
 namespace gpsat_kernels {
@@ -718,6 +940,7 @@ cudaError_t launch_bcp_sweep(const SweepLaunch &L, cudaStream_t stream)
     A.n_clauses = L.n_clauses;
     A.n_cubes = L.n_cubes;
     A.uniform3 = L.uniform3;
+    A.stream_index = L.stream_index;
     A.orange = (const int2 *)L.ostart;
     A.occ_clause = L.occ_clause;
     A.occ_pair = (const int2 *)L.occ_pair;
@@ -734,6 +957,14 @@ cudaError_t launch_bcp_sweep(const SweepLaunch &L, cudaStream_t stream)
     A.conflict_clause = L.conflict_clause;
     A.counters = L.counters;
     A.next_job = L.next_job;
+    if (L.cluster_size < 0) {   // one CTA per job, assigned-bit filter in shared memory, values in this CTA's global block
+        const size_t smem = ((size_t)1 << (L.slice_log2 - 3)) + 16;
+        cta_sweep_kernel_t kfn = pick_cta_sweep(L.warps_per_block * 32, -L.cluster_size);
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kfn<<<L.blocks, L.warps_per_block * 32, smem, stream>>>(A, L.slice_log2);
+        return cudaGetLastError();
+    }
     if (L.cluster_size > 0) {
         const size_t smem = (size_t)4 << L.slice_log2;
         cudaError_t e = cudaFuncSetAttribute(gpsat_bcp_sweep_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -758,6 +989,15 @@ cudaError_t launch_bcp_sweep(const SweepLaunch &L, cudaStream_t stream)
     }
     gpsat_bcp_sweep_kernel<<<L.blocks, L.warps_per_block * 32, 0, stream>>>(A);
     return cudaGetLastError();
+}
+
+cudaError_t sweep_cta_capacity(int filter_log2, int threads, int want_per_sm, int *blocks_per_sm)
+{
+    const size_t smem = ((size_t)1 << (filter_log2 - 3)) + 16;
+    cta_sweep_kernel_t kfn = pick_cta_sweep(threads, want_per_sm);
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kfn, threads, smem);
 }
 
 // how many clusters of `cluster_size` CTAs (threads, dynamic shared memory as given) can be co-resident on the device

@@ -48,10 +48,14 @@ struct SweepLaunch {
     int64_t *counters;
     int32_t *next_job;
     int blocks, warps_per_block;   // cluster kernel: blocks = number of clusters
-    int cluster_size;              // 0: HBM-bitmap kernel (one warp per job); > 0: one cluster per job, bitmap in distributed shared memory
-    int slice_log2;                // cluster kernel: bitmap words per CTA = 1 << slice_log2
+    int stream_index;              // CTA kernel: evict-first loads for the occurrence index
+    int cluster_size;              // 0: HBM-bitmap kernel (one warp per job); > 0: one cluster per job, bitmap in distributed
+                                   // shared memory; < 0: one CTA per job, assigned bits in shared memory + values in global
+    int slice_log2;                // cluster kernel: bitmap words per CTA = 1 << slice_log2; CTA kernel: log2 of the filter bits
+                                   // (cluster_size = -(CTAs per SM the kernel variant is compiled for))
 };
 cudaError_t launch_bcp_sweep(const SweepLaunch &L, cudaStream_t stream);
 cudaError_t sweep_cluster_capacity(int cluster_size, int threads, size_t smem, int *clusters);
+cudaError_t sweep_cta_capacity(int filter_log2, int threads, int want_per_sm, int *blocks_per_sm);
 
 }  // namespace gpsat_kernels
