@@ -399,7 +399,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--epoch-ms", type=float, default=20.0, help="N > 1: kernel budget per exchange epoch")
+    ap.add_argument("--epoch-ms", type=float, default=100.0,
+                    help="N > 1: kernel budget per exchange epoch (a C2 shard finishes inside one epoch; measured at "
+                         "N=2: 20 ms epochs 62 ms/solve, 60 ms or more 39 ms/solve)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -1295,7 +1295,7 @@ struct WarpSolver {
                 if (decision_mode == GPSAT_DECIDE_VSIDS) vsids_learnt(n_out);
                 pool_publish(n_out);
                 if (max_conflicts && c_conflicts >= max_conflicts) return GPSAT_UNDEF;
-                if ((c_conflicts & 31) == 0) {
+                if ((c_conflicts & 7) == 0) {   // every 8 conflicts (< 1 ms): stop flag and step budget
                     if (stop_flag && *stop_flag) return GPSAT_JOB_ABORTED;
                     if (budget_ns && queued_ok) {
                         LANEVAR(int, late_v);
