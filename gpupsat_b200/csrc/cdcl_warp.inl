@@ -1560,7 +1560,7 @@ GPSAT_DEV void gpsat_run_and_record(WarpSolver &S, int root, const int *cube, in
 GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const gpsat_run_buffers &B)
 {
     GPSAT_LANE_DECL
-    int is_idle = 0;
+    int is_idle = 0, idle_spins = 0;
     unsigned long long busy_ns = 0;
     while (true) {
         LANEVAR(int, kind_v);   // 0 exit, 1 original cube, 2 queued child, 3 wait, 4 resume the job this warp parked
@@ -1618,9 +1618,13 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
                 is_idle = 1;
                 LANE0 { gpsat_atomic_add(B.dq_ctrl + 3, 1); }   // one more idle warp
             }
-            gpsat_nanosleep(4000);   // idle warps must not steal issue slots from the busy ones
+            // idle warps must not steal issue slots from the busy ones, nor hammer the queue counters in L2 (in the
+            // tail of a run thousands of them poll the same sector that the splitting warps update): back off to 32 us
+            gpsat_nanosleep(4000u << (idle_spins < 3 ? idle_spins : 3));
+            idle_spins++;
             continue;
         }
+        idle_spins = 0;
         if (is_idle) {
             is_idle = 0;
             LANE0 { gpsat_atomic_add(B.dq_ctrl + 3, -1); }
