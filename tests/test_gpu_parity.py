@@ -373,3 +373,23 @@ def test_maximum_cube_count_and_bad_arguments():
             s.set_cubes(np.array([[2 * cnf.n_vars + 4]], dtype=np.int32))          # literal out of range
     with pytest.raises(g.GpsatError):
         g.Solver(3, np.array([0, 1, 3], dtype=np.int64), np.array([1, 2, 4], dtype=np.int32))   # unit clause
+
+
+def test_state_in_global_memory_path():
+    """formulas whose per-job state does not fit in shared memory (n = 4000) run the <global state> kernel variant:
+    sequential solve bit-exact against the oracle, cube solve returns a verified model"""
+    n, m = 4000, 12000                                  # r = 3.0: satisfiable, solved mostly by propagation
+    offs, lits = random_ksat(n, m, 2)
+    cnf, pre = _prep(offs, lits)
+    with g.Solver(cnf.n_vars, pre.offsets, pre.lits, dynamic_split=0) as s:
+        s.set_cubes(None)
+        verdict, model, stats = s.solve()
+        rec = s.job_records()
+        assert stats["state_in_smem"] == 0
+    want = Oracle(cnf.n_vars, pre.offsets, pre.lits).run(np.array([0, 0]), np.zeros(0))
+    _cmp_records(rec, want["records"], "global-state solve")
+    assert verdict == g.SAT and check_model(pre.offsets, pre.lits, model)
+    with g.Solver(cnf.n_vars, pre.offsets, pre.lits) as s:
+        s.set_cubes(pre.choose_cubes(2, 32))
+        verdict, model, stats = s.solve()
+    assert verdict == g.SAT and check_model(pre.offsets, pre.lits, model)
