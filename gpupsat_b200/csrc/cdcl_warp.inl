@@ -100,6 +100,7 @@ struct WarpSolver {
     GPSAT_DEV void enqueue(int x, int why)
     {
         GPSAT_LANE_DECL
+        SYNCWARP();   // every lane has finished reading val[] (lit_value of the same literal) before lane 0 overwrites it
         LANE0
         {
             int v = x >> 1;
