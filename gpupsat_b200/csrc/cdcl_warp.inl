@@ -974,6 +974,11 @@ struct WarpSolver {
             if (st != GPSAT_UNDEF) return st;
             taken++;
         }
+        // imported clauses do not count towards the job's own learnt-clause budget: otherwise a job that starts with a
+        // few hundred foreign clauses reduces its database at once and keeps doing so (measured on uf300 over 2 GPUs:
+        // twice the conflicts with sharing on)
+        max_learnts += taken;
+        if (max_learnts > refs_cap - n_vars - 2) max_learnts = refs_cap - n_vars - 2;
         return GPSAT_UNDEF;
     }
 
