@@ -25,6 +25,7 @@
 #include "warp_lockstep.h"
 
 struct WarpSolver {
+    int lane_id;          // this thread's lane, read once (see GPSAT_LANE_DECL)
     // ---- read-only formula index (global, L1/L2 resident)
     int n_vars, n_clauses, n_lits, wbits_words;
     const gint2 *cl2;
@@ -1383,6 +1384,9 @@ GPSAT_DEV void gpsat_bind(WarpSolver &S, const gpsat_formula_view &F, const gpsa
 {
     S.park = park;
     S.pool_mark = S.xpool_mark = 0;
+#if !defined(GPSAT_WARP_EMU)
+    S.lane_id = gpsat_read_lane();
+#endif
     S.n_vars = F.n_vars;
     S.n_clauses = F.n_clauses;
     S.n_lits = F.n_lits;
@@ -1451,7 +1455,7 @@ GPSAT_DEV void gpsat_bind(WarpSolver &S, const gpsat_formula_view &F, const gpsa
 GPSAT_DEV void gpsat_run_and_record(WarpSolver &S, int root, const int *cube, int k, const int *hand,
                                     const gpsat_solve_params &P, const gpsat_run_buffers &B, bool resume = false)
 {
-    GPSAT_LANE_DECL
+    GPSAT_LANE_DECL_S
     int confl;
     S.max_learnts = P.max_learnts_first;
     S.root = root;
@@ -1565,7 +1569,7 @@ GPSAT_DEV void gpsat_run_and_record(WarpSolver &S, int root, const int *cube, in
 // long-running cubes split) and leaves when no job is outstanding, the stop flag is up, or the step budget is spent.
 GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const gpsat_run_buffers &B)
 {
-    GPSAT_LANE_DECL
+    GPSAT_LANE_DECL_S
     int is_idle = 0, idle_spins = 0;
     unsigned long long busy_ns = 0;
     while (true) {

@@ -22,6 +22,7 @@
 #define GPSAT_DEV_OUTLINE inline
 #define GPSAT_NOUNROLL
 #define GPSAT_LANE_DECL
+#define GPSAT_LANE_DECL_S
 #define LANEVAR(T, name) T name[32]
 #define LV(name) name[lane]
 #define LANES for (int lane = 0; lane < 32; ++lane)
@@ -82,7 +83,19 @@ static inline int gpsat_ld(const int *p) { return *p; }
 // every warp of a block is at a different point of a large program: code size (instruction-cache footprint), not
 // loop overhead, is what costs issue slots here, so loops are kept rolled
 #define GPSAT_NOUNROLL _Pragma("unroll 1")
-#define GPSAT_LANE_DECL const int lane = (int)(threadIdx.x & 31u);
+// the lane index is read ONCE per thread through a volatile asm (gpsat_read_lane) and carried in a register: the
+// compiler otherwise re-reads %tid.x (S2R, short-scoreboard latency) wherever `lane` is needed — 3 % of the stall
+// samples of the CDCL kernel (profiles/r01_cdcl_lines_h.txt, kernels.cu:38)
+#define GPSAT_LANE_DECL const int lane = gpsat_lane_of(this);
+#define GPSAT_LANE_DECL_S const int lane = S.lane_id;
+__device__ __forceinline__ int gpsat_read_lane()
+{
+    int l;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
+    return l;
+}
+template <class T>
+__device__ __forceinline__ int gpsat_lane_of(const T *s) { return s->lane_id; }
 #define LANEVAR(T, name) T name
 #define LV(name) name
 #define LANES
