@@ -137,7 +137,8 @@ struct gpsat {
     DevBuf<uint8_t> val0;
     // occurrence-mode BCP (opts.bcp == GPSAT_BCP_OCCURRENCE)
     DevBuf<int32_t> occ_clause, occ_pair, orange;
-    DevBuf<uint32_t> valbits, valbits_cta;
+    DevBuf<uint32_t> valbits, valbits_cta, occ_bucket;
+    int32_t tern_state_bytes = 0;
     DevBuf<int64_t> sweep_counters;
     int uniform3 = 0;
     int sweep_cluster = 0;   // cluster size used by the last occurrence-mode propagation (0 = HBM-bitmap kernel)
@@ -505,6 +506,9 @@ int propagate_all_occurrence(gpsat *h, int32_t *status, int32_t *n_implied, int3
     // HBM-bitmap kernel (one warp per job) when even 16 CTAs cannot hold the bitmap.  GPSAT_SWEEP_CLUSTER /
     // GPSAT_SWEEP_THREADS / GPSAT_SWEEP_SLICE_KB override for experiments (cluster 0 = HBM-bitmap kernel).
     int cluster = 0, slice_log2 = 4, cthreads = 1024;
+    // first choice when the database qualifies (gpsat_create built the bucket index): the ternary kernel
+    const bool use_tern = h->tern_state_bytes > 0 && !std::getenv("GPSAT_SWEEP_CLUSTER") &&
+                          !(std::getenv("GPSAT_SWEEP_TERNARY") && std::atoi(std::getenv("GPSAT_SWEEP_TERNARY")) == 0);
     {
         const char *e_cl = std::getenv("GPSAT_SWEEP_CLUSTER"), *e_th = std::getenv("GPSAT_SWEEP_THREADS"),
                    *e_kb = std::getenv("GPSAT_SWEEP_SLICE_KB");
@@ -613,7 +617,7 @@ int propagate_all_occurrence(gpsat *h, int32_t *status, int32_t *n_implied, int3
     L.cluster_size = cluster;
     // measured (C4, 1184 jobs): evict-first index loads 12.9 -> 11.2 ms, L2 persistence of the value blocks 11.0 ms
     L.stream_index = std::getenv("GPSAT_SWEEP_LDCS") ? std::atoi(std::getenv("GPSAT_SWEEP_LDCS")) : 1;
-    if (cluster < 0 && (!std::getenv("GPSAT_SWEEP_PERSIST") || std::atoi(std::getenv("GPSAT_SWEEP_PERSIST")))) {
+    if (cluster < 0 && !use_tern && (!std::getenv("GPSAT_SWEEP_PERSIST") || std::atoi(std::getenv("GPSAT_SWEEP_PERSIST")))) {
         // keep the per-CTA value blocks resident in L2 while the occurrence index streams through it
         const size_t bytes = (size_t)blocks * (size_t)cta_val_words * sizeof(uint32_t);
         int max_win = 0, max_persist = 0;
@@ -631,12 +635,25 @@ int propagate_all_occurrence(gpsat *h, int32_t *status, int32_t *n_implied, int3
         cudaGetLastError();
     }
     L.slice_log2 = slice_log2;
+    if (use_tern) {   // one CTA per SM, whole job state in shared memory: nothing else to size
+        L.bucket = h->occ_bucket.p;
+        L.tern_state_bytes = h->tern_state_bytes;
+        blocks = h->prop.multiProcessorCount;
+        if (h->opts.blocks > 0) blocks = std::min(blocks, h->opts.blocks);
+        if ((int64_t)blocks > (int64_t)nc) blocks = (int)std::max<size_t>(nc, 1);
+        wpb = 32;
+        cluster = -1;
+        L.blocks = blocks;
+        L.warps_per_block = wpb;
+        L.cluster_size = cluster;
+    }
     if (cluster != 0) CU(cudaMemsetAsync(h->sweep_counters.p, 0, 2 * nc * sizeof(int64_t), h->stream));
     h->kernel_ms = 0;
     h->kernel_launches = 0;
     h->blocks = blocks;
     h->warps_per_block = wpb;
-    h->smem_bytes = cluster > 0 ? ((size_t)4 << slice_log2) : cluster < 0 ? ((size_t)1 << (slice_log2 - 3)) : 512;
+    h->smem_bytes = use_tern ? gpsat_kernels::tern_smem_bytes(h->tern_state_bytes)
+                             : cluster > 0 ? ((size_t)4 << slice_log2) : cluster < 0 ? ((size_t)1 << (slice_log2 - 3)) : 512;
     h->state_in_smem = cluster != 0 ? 1 : 0;
     h->sweep_cluster = cluster;
     CU(cudaEventRecord(h->ev0, h->stream));
@@ -816,6 +833,36 @@ int gpsat_create(gpsat_t **out, int32_t n_vars, int64_t n_clauses, const int64_t
         CUH(h->orange.upload(orange.data(), orange.size(), h->stream));
         CUH(h->occ_clause.upload(oc.data(), oc.size(), h->stream));
         if (h->uniform3) CUH(h->occ_pair.upload(op.data(), op.size(), h->stream));
+        // Ternary kernel (gpsat_bcp_sweep_tern_kernel): pure 3-SAT whose literal ids (with those of a sentinel variable
+        // n) fit 21 bits and whose base-3 state (five variables per byte) fits one SM's shared memory beside the
+        // lookup table and the hit queues.  Bucket index: the list packed into its head, one 64-byte bucket per literal
+        // id — word 0 the count, entries 0..4 from bit 32 and 5..10 from bit 256 at 42 bits each, unused entries hold
+        // the sentinel's true literal.  GPSAT_SWEEP_TERNARY=0 keeps the other kernels.
+        const char *e_tn = std::getenv("GPSAT_SWEEP_TERNARY");
+        const int32_t state_bytes = (int32_t)((((int64_t)n_vars + 1 + 4) / 5 + 15) / 16 * 16);
+        h->tern_state_bytes = 0;
+        if (h->uniform3 && n_lit_ids + 2 <= ((size_t)1 << 21) && !(e_tn && std::atoi(e_tn) == 0) &&
+            gpsat_kernels::tern_smem_bytes(state_bytes) + 256 <= h->prop.sharedMemPerBlockOptin) {
+            const uint32_t pad = (uint32_t)n_lit_ids + 1u;   // 2n + 1: the sentinel's positive literal
+            std::vector<uint32_t> bk(16 * (n_lit_ids + 2), 0u);
+            auto put = [](uint32_t *w, int bit, uint32_t v) {
+                w[bit >> 5] |= v << (bit & 31);
+                if ((bit & 31) + 21 > 32) w[(bit >> 5) + 1] |= v >> (32 - (bit & 31));
+            };
+            for (size_t f = 0; f < n_lit_ids + 2; f++) {
+                uint32_t *w = bk.data() + 16 * f;
+                const int32_t os = f < n_lit_ids ? orange[2 * f] : 0;
+                const int32_t cnt = f < n_lit_ids ? h->D.ostart[f + 1] - h->D.ostart[f] : 0;
+                w[0] = (uint32_t)cnt;
+                for (int j = 0; j < 11; j++) {
+                    const int bit = j < 5 ? 32 + 42 * j : 256 + 42 * (j - 5);
+                    put(w, bit, j < cnt ? (uint32_t)op[2 * (size_t)(os + j)] : pad);
+                    put(w, bit + 21, j < cnt ? (uint32_t)op[2 * (size_t)(os + j) + 1] : pad);
+                }
+            }
+            CUH(h->occ_bucket.upload(bk.data(), bk.size(), h->stream));
+            h->tern_state_bytes = state_bytes;
+        }
         CUH(cudaStreamSynchronize(h->stream));
     }
     CUH(cudaStreamSynchronize(h->stream));

@@ -37,6 +37,10 @@ struct SweepLaunch {
     int32_t n_vars, n_clauses, n_cubes, uniform3;
     const int32_t *ostart;   // (begin, end) pairs of the padded occurrence lists (int2 per literal)
     const int32_t *occ_clause, *occ_pair, *coffsets, *clits;
+    // ternary kernel (pure 3-SAT, whole job state in one SM's shared memory): 64-byte bucket per literal id, 2n + 2 of
+    // them (16 words each), and the bytes of base-3 state; nullptr selects the other kernels
+    const uint32_t *bucket = nullptr;
+    int32_t tern_state_bytes = 0;
     const int64_t *cube_offsets;
     const int32_t *cube_lits;
     uint32_t *valbits;
@@ -55,6 +59,7 @@ struct SweepLaunch {
                                    // (cluster_size = -(CTAs per SM the kernel variant is compiled for))
 };
 cudaError_t launch_bcp_sweep(const SweepLaunch &L, cudaStream_t stream);
+size_t tern_smem_bytes(int32_t state_bytes);   // dynamic shared memory of the ternary kernel
 cudaError_t sweep_cluster_capacity(int cluster_size, int threads, size_t smem, int *clusters);
 cudaError_t sweep_cta_capacity(int filter_log2, int threads, int want_per_sm, int *blocks_per_sm);
 

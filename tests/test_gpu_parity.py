@@ -173,6 +173,63 @@ def test_occurrence_bcp_mixed_clause_lengths():
         assert set(got["implied"][j, : got["n_implied"][j]].tolist()) == set(want["implied"][j, : want["n_implied"][j]].tolist())
 
 
+def _hub_3sat(n, m, hubs, hub_occ, seed):
+    """pure 3-SAT with a few literals of very many occurrences (long occurrence lists: the bucket index's overflow
+    path) on top of a uniform random background"""
+    rng = np.random.default_rng(seed)
+    cl = []
+    for _ in range(m):
+        vs = rng.choice(n, size=3, replace=False)
+        cl.append([int(2 * v + rng.integers(0, 2)) for v in vs])
+    for h in range(hubs):
+        for _ in range(hub_occ):
+            vs = rng.choice(np.arange(hubs, n), size=2, replace=False)
+            c = [2 * h + (h & 1)] + [int(2 * v + rng.integers(0, 2)) for v in vs]
+            cl.append([c[i] for i in rng.permutation(3)])
+    offs = np.arange(0, 3 * len(cl) + 1, 3, dtype=np.int64)
+    return offs, np.array([x for c in cl for x in c], dtype=np.int32)
+
+
+@pytest.mark.parametrize("env", [{}, {"GPSAT_SWEEP_TERNARY": "0"}, {"GPSAT_SWEEP_CLUSTER": "2"},
+                                 {"GPSAT_SWEEP_CLUSTER": "0"}])
+def test_occurrence_bcp_index_and_state_layouts(env, monkeypatch):
+    """every large-database kernel — ternary state + bucket index (default for pure 3-SAT), one CTA per job with the
+    filter / global fields, cluster, HBM bitmap — gives the oracle's status and implied sets on an instance whose
+    hub literals have 40 occurrences (bucket overflow path) and whose cubes falsify them"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    n = 600
+    offs, lits = _hub_3sat(n, 2200, 6, 40, 5)
+    rng = np.random.default_rng(6)
+    J, K = 96, 24
+    cubes = np.zeros((J, K), dtype=np.int32)
+    for j in range(J):
+        vs = rng.choice(np.arange(6, n), size=K - 6, replace=False)
+        hub = [2 * h + (1 - (h & 1) if (j >> h) & 1 else int(rng.integers(0, 2))) for h in range(6)]   # often false hubs
+        cubes[j] = np.array(hub + [int(2 * v + rng.integers(0, 2)) for v in vs], dtype=np.int32)
+    co = np.arange(0, cubes.size + 1, K, dtype=np.int64)
+    with g.Solver(n, offs, lits, bcp=g.binding.BCP_OCCURRENCE) as s:
+        s.set_cubes(cubes)
+        got = s.propagate_all()
+    want = Oracle(n, offs, lits).run(co, cubes.reshape(-1), mode=2)
+    occ = np.bincount(lits, minlength=2 * n)
+    assert occ.max() >= 40
+    assert np.array_equal(got["status"], want["records"]["status"])
+    assert (got["status"] == g.UNSAT).any() and (got["status"] == g.UNDEF).any()
+    for j in range(J):
+        mine = set(got["implied"][j, : got["n_implied"][j]].tolist())
+        if got["status"][j] == g.UNDEF:
+            assert mine == set(want["implied"][j, : want["n_implied"][j]].tolist())
+            # every occurrence of the negation of every trail literal was visited exactly once
+            trail = np.concatenate([cubes[j], got["implied"][j, : got["n_implied"][j]]])
+            assert got["records"]["watchers_visited"][j] == occ[trail ^ 1].sum()
+        else:
+            c = got["conflict_clause"][j]
+            assert c >= 0
+            trail = set(cubes[j].tolist()) | mine
+            assert all((x ^ 1) in trail for x in lits[offs[c]: offs[c + 1]])
+
+
 def test_config4_large_database_sample():
     """config 4 at full size: n = 1e6, m = 4e6 planted 3-SAT, 32 jobs x 100k-literal trails; sample of jobs against
     the oracle (implied sets), all jobs conflict-free, implied literals agree with the planted assignment."""
