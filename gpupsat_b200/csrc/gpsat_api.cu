@@ -616,7 +616,7 @@ int propagate_all_occurrence(gpsat *h, int32_t *status, int32_t *n_implied, int3
     L.warps_per_block = wpb;
     L.cluster_size = cluster;
     // measured (C4, 1184 jobs): evict-first index loads 12.9 -> 11.2 ms, L2 persistence of the value blocks 11.0 ms
-    L.stream_index = std::getenv("GPSAT_SWEEP_LDCS") ? std::atoi(std::getenv("GPSAT_SWEEP_LDCS")) : 1;
+    L.stream_index = std::getenv("GPSAT_SWEEP_LDCS") ? std::atoi(std::getenv("GPSAT_SWEEP_LDCS")) : (use_tern ? 2 : 1);
     if (cluster < 0 && !use_tern && (!std::getenv("GPSAT_SWEEP_PERSIST") || std::atoi(std::getenv("GPSAT_SWEEP_PERSIST")))) {
         // keep the per-CTA value blocks resident in L2 while the occurrence index streams through it
         const size_t bytes = (size_t)blocks * (size_t)cta_val_words * sizeof(uint32_t);
@@ -635,9 +635,18 @@ int propagate_all_occurrence(gpsat *h, int32_t *status, int32_t *n_implied, int3
         cudaGetLastError();
     }
     L.slice_log2 = slice_log2;
+    if (const char *e_fg = std::getenv("GPSAT_L2_FETCH")) {   // experiment: L2 fetch granularity hint (32 / 64 / 128)
+        size_t before = 0, after = 0;
+        cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
+        cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(e_fg));
+        cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
+        std::fprintf(stderr, "[gpsat] L2 fetch granularity %zu -> %zu (%s)\n", before, after, cudaGetErrorString(e));
+        cudaGetLastError();
+    }
     if (use_tern) {   // one CTA per SM, whole job state in shared memory: nothing else to size
         L.bucket = h->occ_bucket.p;
         L.tern_state_bytes = h->tern_state_bytes;
+        L.tern_prefetch = std::getenv("GPSAT_SWEEP_PREFETCH") ? std::atoi(std::getenv("GPSAT_SWEEP_PREFETCH")) : 1;
         blocks = h->prop.multiProcessorCount;
         if (h->opts.blocks > 0) blocks = std::min(blocks, h->opts.blocks);
         if ((int64_t)blocks > (int64_t)nc) blocks = (int)std::max<size_t>(nc, 1);

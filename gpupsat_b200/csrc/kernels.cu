@@ -924,15 +924,15 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) gpsat_bcp_sweep_cta_ke
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// gpsat_bcp_sweep_tern_kernel — occurrence-list BCP, one CTA per job, for pure 3-SAT databases of up to ~1.0 M
+// gpsat_bcp_sweep_tern_kernel — occurrence-list BCP, one CTA per job, for pure 3-SAT databases of up to ~1.1 M
 // variables: the WHOLE job state stays in the SM's shared memory and a literal costs one 64-byte memory access.
 //
 // State: base-3 digits, five variables per byte (3^5 = 243 <= 256): 0 unassigned, 1 false, 2 true — n = 1e6 needs
 //   200 KB, which fits one SM where the 2-bit encoding (250 KB) does not.  A lookup is branch-free:
 //   q = x / 10 (one IMAD.HI), byte = S[q], code = LUT[byte * 16 + (x - 10 q)] — the 4 KB table folds digit
 //   extraction and the literal's sign into one load and returns 0 (false), 1 (unassigned) or 4 (true), so that a
-//   clause with other literals (a, b) needs attention iff code(a) + code(b) <= 1.  Assigning is a compare-and-swap
-//   on the 32-bit word that holds the byte; its outcome is the authority for "append to the trail exactly once".
+//   clause with other literals (a, b) needs attention iff code(a) + code(b) <= 1.  Assigning is a compare-and-swap on the 32-bit word that holds the
+//   byte; its outcome is the authority for "append to the trail exactly once".
 //   No global-memory state at all (the CTA kernel above keeps 2-bit fields in L2 behind a shared-memory filter: ncu
 //   showed 38 % of its stall samples on those reads / atomics and 12 of 32 lanes active on average).
 // Index: one 64-byte bucket per literal, the occurrence list packed INTO its head (built by gpsat_create):
@@ -943,97 +943,147 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) gpsat_bcp_sweep_cta_ke
 //   32-byte sector for the 8-byte head plus the sectors an unaligned list straddles).  The 2 % of literals with more
 //   than 11 occurrences (Poisson, mean 6) read entries 11.. from the plain pair list.
 // Warp-uniform control flow: a warp takes 32 trail literals, every lane decodes and looks up all 11 slots of its
-//   bucket with no branch (padding evaluates as "satisfied"); the rare clauses that became unit or conflicting are
-//   compacted with ballots into a per-warp queue in shared memory and resolved by as many lanes as there are hits.
+//   bucket with no branch (padding evaluates as "satisfied"); a clause that became unit or conflicting (one in four
+//   literals has one) is parked in a register and resolved once per batch.  The trail literal is fetched two batches
+//   ahead and the bucket one batch ahead, so the memory round trips overlap the lookups of the batch before.
 // A lookup that misses an assignment made during the current round reads "unassigned"; the literal that was
 // assigned is processed in a later round (after a barrier) and re-examines the clause, so no unit is lost.
 // ---------------------------------------------------------------------------------------------------------------
 #define GPSAT_TERN_LIT_BITS 21
 #define GPSAT_TERN_ENTRIES 11
-#define GPSAT_TERN_QUEUE 192          // hit records per warp: one group of at most 6 entries x 32 lanes
 #define GPSAT_TERN_LUT_BYTES 4096
 
-struct TernState {
-    uint8_t *s8;           // shared: five variables per byte
-    const uint8_t *lut;    // shared: [byte * 16 + 2 * (var % 5) + sign] -> 0 false, 1 unassigned, 4 true
-    __device__ __forceinline__ int code(uint32_t x) const
+struct TernJob {
+    // dynamic shared memory: [LUT 4 KB | state bytes]
+    uint8_t *smem;
+    int32_t *imp;
+    long long stride;
+    int *s_count, *s_conflict, *s_conf_f, *s_conf_j;
+    __device__ __forceinline__ int code(uint32_t x) const   // 0 false, 1 unassigned, 4 true
     {
         const uint32_t q = __umulhi(x, 0x1999999Au);   // x / 10 (exact below 2^30)
-        return lut[(uint32_t)s8[q] * 16u + (x - 10u * q)];
+        return smem[(uint32_t)smem[GPSAT_TERN_LUT_BYTES + q] * 16u + (x - 10u * q)];
     }
     // previous digit of the variable: 0 it was unassigned (and now carries x), 1 it was false, 2 it was true
     __device__ __forceinline__ uint32_t assign(uint32_t x) const
     {
         const uint32_t var = x >> 1, q = var / 5u, r = var - 5u * q, sh = (q & 3u) * 8u;
-        const uint32_t p3 = r == 0 ? 1u : r == 1 ? 3u : r == 2 ? 9u : r == 3 ? 27u : 81u;
-        uint32_t *w = reinterpret_cast<uint32_t *>(s8) + (q >> 2);
+        const uint32_t p3 = r == 4u ? 81u : (0x1B090301u >> (8u * r)) & 255u;   // 1, 3, 9, 27, 81
+        uint32_t *w = reinterpret_cast<uint32_t *>(smem + GPSAT_TERN_LUT_BYTES) + (q >> 2);
         uint32_t old = *reinterpret_cast<volatile uint32_t *>(w);
         while (true) {
-            const uint32_t c = lut[((old >> sh) & 255u) * 16u + 2u * r];   // code of the NEGATIVE literal of var
+            const uint32_t c = smem[((old >> sh) & 255u) * 16u + 2u * r];   // code of the NEGATIVE literal of var
             if (c != 1u) return c == 4u ? 1u : 2u;
             const uint32_t seen = atomicCAS(w, old, old + (((1u + (x & 1u)) * p3) << sh));
             if (seen == old) return 0u;
             old = seen;
         }
     }
+    __device__ __forceinline__ void conflict_at(uint32_t f, int j) const
+    {
+        if (atomicCAS(s_conflict, 0, 1) == 0) {
+            *s_conf_f = (int)f;
+            *s_conf_j = j;
+        }
+    }
+    // entry j of literal f's list, other literals (a, b): evaluate it now and act on it
+    __device__ __forceinline__ void resolve(uint32_t a, uint32_t b, uint32_t f, int j) const
+    {
+        const int ca = code(a), cb = code(b);
+        if (ca + cb > 1) return;
+        if (ca + cb == 0) {   // every other literal false
+            conflict_at(f, j);
+            return;
+        }
+        const uint32_t unit = ca ? a : b;
+        const uint32_t prev = assign(unit);
+        if (prev == 0) {
+            const int pos = atomicAdd(s_count, 1);
+            if (pos < stride) imp[pos] = (int32_t)unit;
+        } else if (prev - 1u != (unit & 1u)) {   // lost a race against ~unit
+            conflict_at(f, j);
+        }
+    }
 };
 
-template <int kOff> __device__ __forceinline__ uint32_t tern_field(const uint32_t (&w)[8])
+template <int kOff> __device__ __forceinline__ uint32_t tern_field(const uint32_t (&w)[16])
 {
     constexpr int wi = kOff >> 5, sh = kOff & 31;
     uint32_t v;
     if constexpr (sh + GPSAT_TERN_LIT_BITS <= 32) v = w[wi] >> sh;
-    else v = __funnelshift_r(w[wi], w[wi + 1 < 8 ? wi + 1 : 7], sh);
+    else v = __funnelshift_r(w[wi], w[wi + 1 < 16 ? wi + 1 : 15], sh);
     return v & ((1u << GPSAT_TERN_LIT_BITS) - 1u);
 }
-
-struct TernWarp {
-    TernState st;
-    uint32_t *queue;       // shared: this warp's hit records
-    int qn;                // records queued (warp-uniform)
-    uint32_t lane, lt_mask;
-    // entry j of this lane's bucket: other literals (a, b); queue it when the clause is unit or conflicting
-    __device__ __forceinline__ void examine(uint32_t a, uint32_t b, int j)
-    {
-        const int ca = st.code(a), cb = st.code(b);
-        const bool hit = ca + cb <= 1;
-        const uint32_t m = __ballot_sync(0xffffffffu, hit);
-        if (hit) {
-            const uint32_t unit = ca ? a : b;   // conflict (both false): b, flagged
-            queue[qn + __popc(m & lt_mask)] = unit | (lane << 21) | ((uint32_t)j << 26) | (ca + cb == 0 ? 1u << 30 : 0u);
-        }
-        qn += __popc(m);
-    }
-    template <int kBase, int kN, int kJ0, int kJ = 0> __device__ __forceinline__ void group(const uint32_t (&w)[8])
-    {
-        if constexpr (kJ < kN) {
-            examine(tern_field<kBase + 42 * kJ>(w), tern_field<kBase + 42 * kJ + 21>(w), kJ0 + kJ);
-            group<kBase, kN, kJ0, kJ + 1>(w);
-        }
-    }
+template <int kJ> struct TernEntry {
+    static constexpr int bit = kJ < 5 ? 32 + 42 * kJ : 256 + 42 * (kJ - 5);
 };
 
+// all 11 entries of a bucket, branch-free: bit j of the result is set when entry j needs attention (unit / conflict)
+template <int kJ = 0>
+__device__ __forceinline__ uint32_t tern_scan(const TernJob &J, const uint32_t (&w)[16])
+{
+    if constexpr (kJ < GPSAT_TERN_ENTRIES) {
+        const int s = J.code(tern_field<TernEntry<kJ>::bit>(w)) + J.code(tern_field<TernEntry<kJ>::bit + 21>(w));
+        return (s <= 1 ? 1u << kJ : 0u) | tern_scan<kJ + 1>(J, w);
+    } else {
+        return 0u;
+    }
+}
+// the two other literals of entry j (run-time j: a select over the 11 compile-time positions)
+template <int kJ = 0>
+__device__ __forceinline__ void tern_pick(const uint32_t (&w)[16], int j, uint32_t &a, uint32_t &b)
+{
+    if constexpr (kJ < GPSAT_TERN_ENTRIES) {
+        if (j == kJ) {
+            a = tern_field<TernEntry<kJ>::bit>(w);
+            b = tern_field<TernEntry<kJ>::bit + 21>(w);
+        }
+        tern_pick<kJ + 1>(w, j, a, b);
+    }
+}
+
+// kind 0: four 16-byte evict-first loads; 1: four 16-byte read-only loads; 2: two 32-byte read-only loads
+__device__ __forceinline__ void tern_load_bucket(const uint4 *bucket, uint32_t f, uint32_t (&w)[16], int kind)
+{
+    const uint4 *bp = bucket + 4 * (size_t)f;
+    if (kind == 2) {
+        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(bp));
+        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]) : "l"(bp + 2));
+        return;
+    }
+    uint4 q0, q1, q2, q3;
+    if (kind == 0) { q0 = __ldcs(bp); q1 = __ldcs(bp + 1); q2 = __ldcs(bp + 2); q3 = __ldcs(bp + 3); }
+    else { q0 = __ldg(bp); q1 = __ldg(bp + 1); q2 = __ldg(bp + 2); q3 = __ldg(bp + 3); }
+    w[0] = q0.x; w[1] = q0.y; w[2] = q0.z; w[3] = q0.w;
+    w[4] = q1.x; w[5] = q1.y; w[6] = q1.z; w[7] = q1.w;
+    w[8] = q2.x; w[9] = q2.y; w[10] = q2.z; w[11] = q2.w;
+    w[12] = q3.x; w[13] = q3.y; w[14] = q3.z; w[15] = q3.w;
+}
+
+template <bool kPrefetch>
 __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_tern_kernel(const SweepArgs A)
 {
-    extern __shared__ __align__(16) uint8_t s_dyn[];   // [state bytes | LUT | per-warp hit queues]
+    extern __shared__ __align__(16) uint8_t s_dyn[];   // [LUT | state bytes]
     __shared__ int s_count, s_conflict, s_conf_f, s_conf_j, s_job, s_total, s_stop;
     const int tid = (int)threadIdx.x, nthreads = (int)blockDim.x;
     const uint32_t lane = (uint32_t)tid & 31u, warp = (uint32_t)tid >> 5;
     const int state_bytes = A.tern_state_bytes;        // multiple of 16
-    uint8_t *lut = s_dyn + state_bytes;
-    TernWarp W;
-    W.st.s8 = s_dyn;
-    W.st.lut = lut;
-    W.queue = reinterpret_cast<uint32_t *>(lut + GPSAT_TERN_LUT_BYTES) + warp * GPSAT_TERN_QUEUE;
-    W.lane = lane;
-    W.lt_mask = (1u << lane) - 1u;
     const uint32_t sentinel_true = 2u * (uint32_t)A.n_vars + 1u;   // literal of the sentinel variable n, always true
+    TernJob J;
+    J.smem = s_dyn;
+    J.stride = A.stride;
+    J.s_count = &s_count;
+    J.s_conflict = &s_conflict;
+    J.s_conf_f = &s_conf_f;
+    J.s_conf_j = &s_conf_j;
 
     for (int i = tid; i < GPSAT_TERN_LUT_BYTES; i += nthreads) {
         const uint32_t byte = (uint32_t)i >> 4, rs = (uint32_t)i & 15u, r = rs >> 1, sgn = rs & 1u;
         const uint32_t p3 = r == 0 ? 1u : r == 1 ? 3u : r == 2 ? 9u : r == 3 ? 27u : 81u;
         const uint32_t digit = r < 5 ? (byte / p3) % 3u : 0u;
-        lut[i] = digit == 0 ? 1 : (digit - 1u == sgn ? 4 : 0);
+        s_dyn[i] = digit == 0 ? 1 : (digit - 1u == sgn ? 4 : 0);
     }
 
     while (true) {
@@ -1043,21 +1093,22 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_tern_kernel(const Swe
             s_conflict = 0;
         }
         {
-            uint4 *z = reinterpret_cast<uint4 *>(s_dyn);
+            uint4 *z = reinterpret_cast<uint4 *>(s_dyn + GPSAT_TERN_LUT_BYTES);
             for (int i = tid; i < state_bytes / 16; i += nthreads) z[i] = make_uint4(0, 0, 0, 0);
         }
         __syncthreads();
-        if (tid == 0) W.st.assign(sentinel_true);
+        if (tid == 0) J.assign(sentinel_true);
         const int job = s_job;
         if (job >= A.n_cubes) break;
         const long long c0 = A.cube_offsets[job], c1 = A.cube_offsets[job + 1];
         const int k = (int)(c1 - c0);
         const int32_t *cube = A.cube_lits + c0;
         int32_t *imp = A.implied + (long long)job * A.stride;
+        J.imp = imp;
 
         for (int i = tid; i < k; i += nthreads) {   // phase 0: the whole cube is assigned up front
             const uint32_t x = (uint32_t)__ldg(cube + i);
-            const uint32_t prev = W.st.assign(x);
+            const uint32_t prev = J.assign(x);
             if (prev && prev - 1u != (x & 1u)) s_conflict = 2;   // x and ~x in the cube: no clause to blame
         }
         __syncthreads();
@@ -1072,75 +1123,51 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_tern_kernel(const Swe
         while (true) {
             const int total = s_total;
             if (s_stop || qhead >= total) break;
-            for (int base = qhead + (int)warp * 32; base < total; base += nthreads) {   // warp-uniform trip count
-                const int t = base + (int)lane;
-                uint32_t f = sentinel_true ^ 1u;   // lanes past the end read the sentinel's all-padding bucket
-                if (t < total) f = (uint32_t)(t < k ? __ldg(cube + t) : __ldcg(imp + (t - k))) ^ 1u;
-                const uint4 *bp = A.bucket + 4 * (size_t)f;
-                uint32_t w0[8], w1[8];
-                {
-                    const uint4 q0 = __ldcs(bp), q1 = __ldcs(bp + 1), q2 = __ldcs(bp + 2), q3 = __ldcs(bp + 3);
-                    w0[0] = q0.x; w0[1] = q0.y; w0[2] = q0.z; w0[3] = q0.w;
-                    w0[4] = q1.x; w0[5] = q1.y; w0[6] = q1.z; w0[7] = q1.w;
-                    w1[0] = q2.x; w1[1] = q2.y; w1[2] = q2.z; w1[3] = q2.w;
-                    w1[4] = q3.x; w1[5] = q3.y; w1[6] = q3.z; w1[7] = q3.w;
+            // the negation of trail literal t, or (past the end) the sentinel's false literal: an all-padding bucket
+            auto trail_f = [&](int t) -> uint32_t {
+                if (t >= total) return sentinel_true ^ 1u;
+                return (uint32_t)(t < k ? __ldg(cube + t) : __ldcg(imp + (t - k))) ^ 1u;
+            };
+            int base = qhead + (int)warp * 32;
+            uint32_t f = trail_f(base + (int)lane), f1 = 0;
+            uint32_t w[16], wn[16];
+            if (kPrefetch) {
+                f1 = trail_f(base + nthreads + (int)lane);
+                tern_load_bucket(A.bucket, f, w, A.stream_index);
+            }
+            for (; base < total; base += nthreads) {   // warp-uniform trip count
+                __syncwarp();   // the lanes that resolved a hit rejoin here, not at the end of the round
+                uint32_t f2 = 0;
+                if (kPrefetch) {
+                    f2 = trail_f(base + 2 * nthreads + (int)lane);
+                    tern_load_bucket(A.bucket, f1, wn, A.stream_index);
+                } else {
+                    tern_load_bucket(A.bucket, f, w, A.stream_index);
                 }
-                const int cnt = (int)w0[0];
+                const int cnt = (int)w[0];
                 visited += cnt;
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    W.qn = 0;
-                    if (half == 0) W.template group<32, 5, 0>(w0);
-                    else W.template group<0, 6, 5>(w1);
-                    if (W.qn == 0) continue;
-                    __syncwarp();
-                    for (int i0 = 0; i0 < W.qn; i0 += 32) {   // resolve the hits, one per lane
-                        const int i = i0 + (int)lane;
-                        const uint32_t rec = i < W.qn ? W.queue[i] : 0u;
-                        const uint32_t src_f = __shfl_sync(0xffffffffu, f, (rec >> 21) & 31u);
-                        bool fresh = false, conflict = (rec >> 30) & 1u;
-                        const uint32_t unit = rec & ((1u << GPSAT_TERN_LIT_BITS) - 1u);
-                        if (i < W.qn && !conflict) {
-                            const uint32_t prev = W.st.assign(unit);
-                            fresh = prev == 0;
-                            conflict = prev && prev - 1u != (unit & 1u);   // lost a race against ~unit
-                        }
-                        const uint32_t fm = __ballot_sync(0xffffffffu, fresh);
-                        if (fm) {
-                            int pos0 = 0;
-                            if (lane == 0) pos0 = atomicAdd(&s_count, __popc(fm));
-                            pos0 = __shfl_sync(0xffffffffu, pos0, 0);
-                            const int pos = pos0 + __popc(fm & W.lt_mask);
-                            if (fresh && pos < A.stride) imp[pos] = (int32_t)unit;
-                        }
-                        if (conflict && atomicCAS(&s_conflict, 0, 1) == 0) {
-                            s_conf_f = (int)src_f;
-                            s_conf_j = (int)((rec >> 26) & 15u);
-                        }
-                    }
-                    __syncwarp();
+                uint32_t hits = tern_scan<0>(J, w);
+                while (hits) {   // one in four literals has an entry that needs attention
+                    const int j = __ffs((int)hits) - 1;
+                    hits &= hits - 1u;
+                    uint32_t a = 0, b = 0;
+                    tern_pick<0>(w, j, a, b);
+                    J.resolve(a, b, f, j);
                 }
                 if (cnt > GPSAT_TERN_ENTRIES) {   // rare: the tail of a long list comes from the plain pair index
                     const int os = __ldg(A.orange + f).x;
                     for (int j = GPSAT_TERN_ENTRIES; j < cnt; ++j) {
                         const int2 q = __ldg(A.occ_pair + os + j);
-                        const int ca = W.st.code((uint32_t)q.x), cb = W.st.code((uint32_t)q.y);
-                        if (ca + cb > 1) continue;
-                        bool conflict = ca + cb == 0;
-                        if (!conflict) {
-                            const uint32_t unit = (uint32_t)(ca ? q.x : q.y);
-                            const uint32_t prev = W.st.assign(unit);
-                            if (prev == 0) {
-                                const int pos = atomicAdd(&s_count, 1);
-                                if (pos < A.stride) imp[pos] = (int32_t)unit;
-                            }
-                            conflict = prev && prev - 1u != (unit & 1u);
-                        }
-                        if (conflict && atomicCAS(&s_conflict, 0, 1) == 0) {
-                            s_conf_f = (int)f;
-                            s_conf_j = j;
-                        }
+                        J.resolve((uint32_t)q.x, (uint32_t)q.y, f, j);
                     }
+                }
+                if (kPrefetch) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) w[i] = wn[i];
+                    f = f1;
+                    f1 = f2;
+                } else {
+                    f = trail_f(base + nthreads + (int)lane);
                 }
             }
             __threadfence();
@@ -1184,7 +1211,7 @@ namespace gpsat_kernels {
 
 size_t tern_smem_bytes(int32_t state_bytes)
 {
-    return (size_t)state_bytes + GPSAT_TERN_LUT_BYTES + (size_t)32 * GPSAT_TERN_QUEUE * sizeof(uint32_t);
+    return (size_t)state_bytes + GPSAT_TERN_LUT_BYTES;
 }
 
 cudaError_t launch_bcp_sweep(const SweepLaunch &L, cudaStream_t stream)
@@ -1215,9 +1242,10 @@ cudaError_t launch_bcp_sweep(const SweepLaunch &L, cudaStream_t stream)
     A.next_job = L.next_job;
     if (L.bucket) {   // ternary kernel: whole job state in shared memory, bucket index
         const size_t smem = tern_smem_bytes(L.tern_state_bytes);
-        cudaError_t e = cudaFuncSetAttribute(gpsat_bcp_sweep_tern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        auto kfn = L.tern_prefetch ? gpsat_bcp_sweep_tern_kernel<true> : gpsat_bcp_sweep_tern_kernel<false>;
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        gpsat_bcp_sweep_tern_kernel<<<L.blocks, 1024, smem, stream>>>(A);
+        kfn<<<L.blocks, 1024, smem, stream>>>(A);
         return cudaGetLastError();
     }
     if (L.cluster_size < 0) {   // one CTA per job, assigned-bit filter in shared memory, values in this CTA's global block
