@@ -189,9 +189,9 @@ def workload_config(n_gpus, cubes, share=0):
 
 def c4_sweep(device_index, peak):
     """Config 4 (the HBM-resident configuration): BCP of 1184 jobs x 100 000-literal trails over a planted 3-SAT
-    database with n = 1e6, m = 4e6, by the one-CTA-per-job sweep kernel (assigned-bit filter in shared memory, value
-    fields in L2-persistent global blocks).  Reported beside the headline because it is the one configuration whose
-    clause database lives in HBM."""
+    database with n = 1e6, m = 4e6, by the one-CTA-per-job ternary sweep kernel (whole job state in shared memory,
+    64-byte bucket index).  Reported beside the headline because it is the one configuration whose clause database
+    lives in HBM."""
     import gpupsat_b200 as g
     from gpupsat_b200.instances import planted_3sat_large, sweep_trails
     n, m, J, L = 1_000_000, 4_000_000, 1184, 100_000
@@ -199,24 +199,33 @@ def c4_sweep(device_index, peak):
     co, cl = sweep_trails(n, J, L, 4, planted)
     with g.Solver(n, offs, lits, bcp=g.binding.BCP_OCCURRENCE, device=device_index) as s:
         s.set_cubes(cube_offsets=co, cube_lits=cl)
-        best = None
-        for r in range(4):
+        times = []
+        for r in range(5):
             got = s.propagate_all(implied_stride=6 * L, want_implied=False)
-            ms = s.last_kernel_ms()
-            if r > 0 and (best is None or ms < best):
-                best = ms
+            if r > 0:
+                times.append(s.last_kernel_ms())       # CUDA events on the library's stream around the one launch
         rec = got["records"]
+    ms = sum(times) / len(times)
     imp = int(got["n_implied"].sum())
     visited, words = int(rec["watchers_visited"].sum()), int(rec["clause_words_read"].sum())
     alg = 8 * visited + 4 * words + 8 * imp
+    traffic, src = None, None
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_sweeptern_ncu_w.json")))
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        traffic = sum(float(d[k]["value"]) * scale[d[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        src = "profiles/r01_sweeptern_ncu_w.json (ncu --set full of this launch)"
+    except Exception:
+        pass
     return {"workload": f"planted 3-SAT n={n} m={m}, {J} jobs x {L}-literal trails, BCP to fixpoint",
-            "kernel": "gpsat_bcp_sweep_cta_kernel", "kernel_ms": best, "implications_per_s": imp / (best * 1e-3),
-            "literals_propagated_per_s": (J * L + imp) / (best * 1e-3),
-            "roofline": {"bound": "hbm", "achieved": alg / (best * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg / (best * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg,
-                         "traffic": 34.23e9, "traffic_source": "profiles/r01_sweepcta_ncu_j.json (ncu --set full): "
-                         "3.07 TB/s of DRAM traffic = 47 % of the measured peak; 32-byte sectors fetched for 8-byte index "
-                         "entries make the traffic 2.5 x the algorithmic bytes"}}
+            "kernel": "gpsat_bcp_sweep_tern_kernel", "kernel_ms": ms, "kernel_ms_min": min(times),
+            "implications_per_s": imp / (ms * 1e-3), "literals_propagated_per_s": (J * L + imp) / (ms * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg,
+                         "traffic": traffic, "traffic_source": src,
+                         "note": "algorithmic bytes = 16 B per occurrence entry visited + 8 B per implication; the bucket "
+                                 "index moves 64 B per literal (a 42-bit entry instead of 16 B), so the DRAM traffic is "
+                                 "below the algorithmic bytes; the kernel is bound by shared-memory lookups (LSU 62 %)"}}
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -646,7 +646,8 @@ int propagate_all_occurrence(gpsat *h, int32_t *status, int32_t *n_implied, int3
     if (use_tern) {   // one CTA per SM, whole job state in shared memory: nothing else to size
         L.bucket = h->occ_bucket.p;
         L.tern_state_bytes = h->tern_state_bytes;
-        L.tern_prefetch = std::getenv("GPSAT_SWEEP_PREFETCH") ? std::atoi(std::getenv("GPSAT_SWEEP_PREFETCH")) : 1;
+        // measured on C4: 5.59 ms without, 5.67 ms with the bucket fetched one batch ahead (the lookups, not memory, bound it)
+        L.tern_prefetch = std::getenv("GPSAT_SWEEP_PREFETCH") ? std::atoi(std::getenv("GPSAT_SWEEP_PREFETCH")) : 0;
         blocks = h->prop.multiProcessorCount;
         if (h->opts.blocks > 0) blocks = std::min(blocks, h->opts.blocks);
         if ((int64_t)blocks > (int64_t)nc) blocks = (int)std::max<size_t>(nc, 1);

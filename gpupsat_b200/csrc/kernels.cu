@@ -929,7 +929,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) gpsat_bcp_sweep_cta_ke
 //
 // State: base-3 digits, five variables per byte (3^5 = 243 <= 256): 0 unassigned, 1 false, 2 true — n = 1e6 needs
 //   200 KB, which fits one SM where the 2-bit encoding (250 KB) does not.  A lookup is branch-free:
-//   q = x / 10 (one IMAD.HI), byte = S[q], code = LUT[byte * 16 + (x - 10 q)] — the 4 KB table folds digit
+//   q = x / 10 (one IMAD.HI), byte = S[q], code = LUT[byte * 20 + (x - 10 q)] — the 5 KB table folds digit
 //   extraction and the literal's sign into one load and returns 0 (false), 1 (unassigned) or 4 (true), so that a
 //   clause with other literals (a, b) needs attention iff code(a) + code(b) <= 1.  Assigning is a compare-and-swap on the 32-bit word that holds the
 //   byte; its outcome is the authority for "append to the trail exactly once".
@@ -951,10 +951,11 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) gpsat_bcp_sweep_cta_ke
 // ---------------------------------------------------------------------------------------------------------------
 #define GPSAT_TERN_LIT_BITS 21
 #define GPSAT_TERN_ENTRIES 11
-#define GPSAT_TERN_LUT_BYTES 4096
+#define GPSAT_TERN_LUT_ROW 20          // bytes per table row: 5 words, odd, so that the few byte values that occur spread over the banks
+#define GPSAT_TERN_LUT_BYTES 5120
 
 struct TernJob {
-    // dynamic shared memory: [LUT 4 KB | state bytes]
+    // dynamic shared memory: [LUT 5 KB | state bytes]
     uint8_t *smem;
     int32_t *imp;
     long long stride;
@@ -962,7 +963,7 @@ struct TernJob {
     __device__ __forceinline__ int code(uint32_t x) const   // 0 false, 1 unassigned, 4 true
     {
         const uint32_t q = __umulhi(x, 0x1999999Au);   // x / 10 (exact below 2^30)
-        return smem[(uint32_t)smem[GPSAT_TERN_LUT_BYTES + q] * 16u + (x - 10u * q)];
+        return smem[(uint32_t)smem[GPSAT_TERN_LUT_BYTES + q] * GPSAT_TERN_LUT_ROW + (x - 10u * q)];
     }
     // previous digit of the variable: 0 it was unassigned (and now carries x), 1 it was false, 2 it was true
     __device__ __forceinline__ uint32_t assign(uint32_t x) const
@@ -972,7 +973,7 @@ struct TernJob {
         uint32_t *w = reinterpret_cast<uint32_t *>(smem + GPSAT_TERN_LUT_BYTES) + (q >> 2);
         uint32_t old = *reinterpret_cast<volatile uint32_t *>(w);
         while (true) {
-            const uint32_t c = smem[((old >> sh) & 255u) * 16u + 2u * r];   // code of the NEGATIVE literal of var
+            const uint32_t c = smem[((old >> sh) & 255u) * GPSAT_TERN_LUT_ROW + 2u * r];   // code of the NEGATIVE literal of var
             if (c != 1u) return c == 4u ? 1u : 2u;
             const uint32_t seen = atomicCAS(w, old, old + (((1u + (x & 1u)) * p3) << sh));
             if (seen == old) return 0u;
@@ -1080,7 +1081,7 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_tern_kernel(const Swe
     J.s_conf_j = &s_conf_j;
 
     for (int i = tid; i < GPSAT_TERN_LUT_BYTES; i += nthreads) {
-        const uint32_t byte = (uint32_t)i >> 4, rs = (uint32_t)i & 15u, r = rs >> 1, sgn = rs & 1u;
+        const uint32_t byte = (uint32_t)i / GPSAT_TERN_LUT_ROW, rs = (uint32_t)i % GPSAT_TERN_LUT_ROW, r = rs >> 1, sgn = rs & 1u;
         const uint32_t p3 = r == 0 ? 1u : r == 1 ? 3u : r == 2 ? 9u : r == 3 ? 27u : 81u;
         const uint32_t digit = r < 5 ? (byte / p3) % 3u : 0u;
         s_dyn[i] = digit == 0 ? 1 : (digit - 1u == sgn ? 4 : 0);
