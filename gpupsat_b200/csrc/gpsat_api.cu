@@ -138,6 +138,7 @@ struct gpsat {
     // occurrence-mode BCP (opts.bcp == GPSAT_BCP_OCCURRENCE)
     DevBuf<int32_t> occ_clause, occ_pair, orange;
     DevBuf<uint32_t> valbits, valbits_cta, occ_bucket;
+    DevBuf<int32_t> cube_lits_sorted;   // ternary sweep kernel: every cube's literals ordered by occurrence-count class
     int32_t tern_state_bytes = 0;
     DevBuf<int64_t> sweep_counters;
     int uniform3 = 0;
@@ -646,6 +647,8 @@ int propagate_all_occurrence(gpsat *h, int32_t *status, int32_t *n_implied, int3
     if (use_tern) {   // one CTA per SM, whole job state in shared memory: nothing else to size
         L.bucket = h->occ_bucket.p;
         L.tern_state_bytes = h->tern_state_bytes;
+        if (h->cube_lits_sorted.p && !(std::getenv("GPSAT_SWEEP_SORT") && std::atoi(std::getenv("GPSAT_SWEEP_SORT")) == 0))
+            L.cube_lits = h->cube_lits_sorted.p;
         // measured on C4: 5.59 ms without, 5.67 ms with the bucket fetched one batch ahead (the lookups, not memory, bound it)
         L.tern_prefetch = std::getenv("GPSAT_SWEEP_PREFETCH") ? std::atoi(std::getenv("GPSAT_SWEEP_PREFETCH")) : 0;
         blocks = h->prop.multiProcessorCount;
@@ -907,6 +910,7 @@ int gpsat_set_cubes(gpsat_t *h, int32_t n_cubes, const int64_t *cube_offsets, co
         set_error("bad arguments");
         return GPSAT_E_ARG;
     }
+    h->cube_lits_sorted.release();
     if (n_cubes == 0) {
         h->n_cubes = 1;
         h->cube_offsets_h.assign(2, 0);
@@ -933,6 +937,25 @@ int gpsat_set_cubes(gpsat_t *h, int32_t n_cubes, const int64_t *cube_offsets, co
             }
         }
         CU(h->cube_lits.upload(cube_lits + base, (size_t)total, h->stream));
+        if (h->tern_state_bytes > 0) {
+            // Ternary sweep kernel: a warp scans the buckets of 32 trail literals in lock step and stops at the longest
+            // list among them, so each cube's literals are grouped by the occurrence count of their negation (<= 5,
+            // <= 8, more — the kernel's three scan lengths).  BCP is confluent: status and implied set do not depend
+            // on the order in which a cube's literals are visited.
+            std::vector<int32_t> sorted((size_t)total);
+            for (int32_t j = 0; j < n_cubes; j++) {
+                const int64_t b = h->cube_offsets_h[(size_t)j], e = h->cube_offsets_h[(size_t)j + 1];
+                int64_t at = b;
+                for (int cls = 0; cls < 3; cls++)
+                    for (int64_t i = b; i < e; i++) {
+                        const int32_t x = cube_lits[base + i], f = x ^ 1;
+                        const int32_t c = h->D.ostart[(size_t)f + 1] - h->D.ostart[(size_t)f];
+                        if ((c <= 5 ? 0 : c <= 8 ? 1 : 2) == cls) sorted[(size_t)at++] = x;
+                    }
+            }
+            CU(h->cube_lits_sorted.upload(sorted.data(), sorted.size(), h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+        }
     }
     CU(h->cube_offsets.upload(h->cube_offsets_h.data(), h->cube_offsets_h.size(), h->stream));
     CU(cudaStreamSynchronize(h->stream));

@@ -1019,13 +1019,14 @@ template <int kJ> struct TernEntry {
     static constexpr int bit = kJ < 5 ? 32 + 42 * kJ : 256 + 42 * (kJ - 5);
 };
 
-// all 11 entries of a bucket, branch-free: bit j of the result is set when entry j needs attention (unit / conflict)
-template <int kJ = 0>
+// entries kJ .. kEnd-1 of a bucket, branch-free: bit j of the result is set when entry j needs attention (unit /
+// conflict)
+template <int kEnd, int kJ = 0>
 __device__ __forceinline__ uint32_t tern_scan(const TernJob &J, const uint32_t (&w)[16])
 {
-    if constexpr (kJ < GPSAT_TERN_ENTRIES) {
+    if constexpr (kJ < kEnd) {
         const int s = J.code(tern_field<TernEntry<kJ>::bit>(w)) + J.code(tern_field<TernEntry<kJ>::bit + 21>(w));
-        return (s <= 1 ? 1u << kJ : 0u) | tern_scan<kJ + 1>(J, w);
+        return (s <= 1 ? 1u << kJ : 0u) | tern_scan<kEnd, kJ + 1>(J, w);
     } else {
         return 0u;
     }
@@ -1147,7 +1148,13 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_tern_kernel(const Swe
                 }
                 const int cnt = (int)w[0];
                 visited += cnt;
-                uint32_t hits = tern_scan<0>(J, w);
+                // the host sorts a cube's literals by occurrence count (gpsat_set_cubes), so most warps hold 32 short
+                // lists and skip the padding of the longer ones
+                const int cmax = __reduce_max_sync(0xffffffffu, cnt);
+                uint32_t hits;
+                if (cmax <= 5) hits = tern_scan<5>(J, w);
+                else if (cmax <= 8) hits = tern_scan<8>(J, w);
+                else hits = tern_scan<GPSAT_TERN_ENTRIES>(J, w);
                 while (hits) {   // one in four literals has an entry that needs attention
                     const int j = __ffs((int)hits) - 1;
                     hits &= hits - 1u;

@@ -190,7 +190,7 @@ def _hub_3sat(n, m, hubs, hub_occ, seed):
     return offs, np.array([x for c in cl for x in c], dtype=np.int32)
 
 
-@pytest.mark.parametrize("env", [{}, {"GPSAT_SWEEP_PREFETCH": "1"}, {"GPSAT_SWEEP_TERNARY": "0"}, {"GPSAT_SWEEP_CLUSTER": "2"},
+@pytest.mark.parametrize("env", [{}, {"GPSAT_SWEEP_PREFETCH": "1"}, {"GPSAT_SWEEP_SORT": "0"}, {"GPSAT_SWEEP_TERNARY": "0"}, {"GPSAT_SWEEP_CLUSTER": "2"},
                                  {"GPSAT_SWEEP_CLUSTER": "0"}])
 def test_occurrence_bcp_index_and_state_layouts(env, monkeypatch):
     """every large-database kernel — ternary state + bucket index (default for pure 3-SAT), one CTA per job with the
