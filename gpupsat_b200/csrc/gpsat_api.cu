@@ -939,19 +939,24 @@ int gpsat_set_cubes(gpsat_t *h, int32_t n_cubes, const int64_t *cube_offsets, co
         CU(h->cube_lits.upload(cube_lits + base, (size_t)total, h->stream));
         if (h->tern_state_bytes > 0) {
             // Ternary sweep kernel: a warp scans the buckets of 32 trail literals in lock step and stops at the longest
-            // list among them, so each cube's literals are grouped by the occurrence count of their negation (<= 5,
-            // <= 8, more — the kernel's three scan lengths).  BCP is confluent: status and implied set do not depend
-            // on the order in which a cube's literals are visited.
+            // list among them, so each cube's literals are ordered by the occurrence count of their negation (counting
+            // sort, stable).  BCP is confluent: status and implied set do not depend on the order in which a cube's
+            // literals are visited.
             std::vector<int32_t> sorted((size_t)total);
+            const int kClasses = 12;   // 0 .. 10 occurrences, 11 and more
             for (int32_t j = 0; j < n_cubes; j++) {
                 const int64_t b = h->cube_offsets_h[(size_t)j], e = h->cube_offsets_h[(size_t)j + 1];
-                int64_t at = b;
-                for (int cls = 0; cls < 3; cls++)
-                    for (int64_t i = b; i < e; i++) {
-                        const int32_t x = cube_lits[base + i], f = x ^ 1;
-                        const int32_t c = h->D.ostart[(size_t)f + 1] - h->D.ostart[(size_t)f];
-                        if ((c <= 5 ? 0 : c <= 8 ? 1 : 2) == cls) sorted[(size_t)at++] = x;
-                    }
+                int64_t at[kClasses + 1] = {0};
+                auto cls = [&](int32_t x) {
+                    const int32_t f = x ^ 1;
+                    return std::min<int32_t>(h->D.ostart[(size_t)f + 1] - h->D.ostart[(size_t)f], kClasses - 1);
+                };
+                for (int64_t i = b; i < e; i++) at[cls(cube_lits[base + i]) + 1]++;
+                for (int c = 0; c < kClasses; c++) at[c + 1] += at[c];
+                for (int64_t i = b; i < e; i++) {
+                    const int32_t x = cube_lits[base + i];
+                    sorted[(size_t)(b + at[cls(x)]++)] = x;
+                }
             }
             CU(h->cube_lits_sorted.upload(sorted.data(), sorted.size(), h->stream));
             CU(cudaStreamSynchronize(h->stream));

@@ -1148,13 +1148,22 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_tern_kernel(const Swe
                 }
                 const int cnt = (int)w[0];
                 visited += cnt;
-                // the host sorts a cube's literals by occurrence count (gpsat_set_cubes), so most warps hold 32 short
-                // lists and skip the padding of the longer ones
+                // the host sorts a cube's literals by occurrence count (gpsat_set_cubes), so the 32 lists of a batch
+                // have nearly the same length and the scan stops at the longest of them instead of visiting padding
                 const int cmax = __reduce_max_sync(0xffffffffu, cnt);
                 uint32_t hits;
-                if (cmax <= 5) hits = tern_scan<5>(J, w);
-                else if (cmax <= 8) hits = tern_scan<8>(J, w);
-                else hits = tern_scan<GPSAT_TERN_ENTRIES>(J, w);
+                switch (cmax) {
+                case 0: hits = 0u; break;
+                case 1: case 2: hits = tern_scan<2>(J, w); break;
+                case 3: hits = tern_scan<3>(J, w); break;
+                case 4: hits = tern_scan<4>(J, w); break;
+                case 5: hits = tern_scan<5>(J, w); break;
+                case 6: hits = tern_scan<6>(J, w); break;
+                case 7: hits = tern_scan<7>(J, w); break;
+                case 8: hits = tern_scan<8>(J, w); break;
+                case 9: hits = tern_scan<9>(J, w); break;
+                default: hits = tern_scan<GPSAT_TERN_ENTRIES>(J, w); break;
+                }
                 while (hits) {   // one in four literals has an entry that needs attention
                     const int j = __ffs((int)hits) - 1;
                     hits &= hits - 1u;
