@@ -138,7 +138,7 @@ struct gpsat {
     // occurrence-mode BCP (opts.bcp == GPSAT_BCP_OCCURRENCE)
     DevBuf<int32_t> occ_clause, occ_pair, orange;
     DevBuf<uint32_t> valbits, valbits_cta, occ_bucket;
-    DevBuf<int32_t> cube_lits_sorted;   // ternary sweep kernel: every cube's literals ordered by occurrence-count class
+    DevBuf<int32_t> cube_lits_sorted, cube_short;   // ternary sweep kernel: every cube's literals ordered by occurrence-count class
     int32_t tern_state_bytes = 0;
     DevBuf<int64_t> sweep_counters;
     int uniform3 = 0;
@@ -648,7 +648,7 @@ int propagate_all_occurrence(gpsat *h, int32_t *status, int32_t *n_implied, int3
         L.bucket = h->occ_bucket.p;
         L.tern_state_bytes = h->tern_state_bytes;
         if (h->cube_lits_sorted.p && !(std::getenv("GPSAT_SWEEP_SORT") && std::atoi(std::getenv("GPSAT_SWEEP_SORT")) == 0))
-            L.cube_lits = h->cube_lits_sorted.p;
+            L.cube_lits = h->cube_lits_sorted.p, L.cube_short = h->cube_short.p;
         // measured on C4: 5.59 ms without, 5.67 ms with the bucket fetched one batch ahead (the lookups, not memory, bound it)
         L.tern_prefetch = std::getenv("GPSAT_SWEEP_PREFETCH") ? std::atoi(std::getenv("GPSAT_SWEEP_PREFETCH")) : 0;
         blocks = h->prop.multiProcessorCount;
@@ -911,6 +911,7 @@ int gpsat_set_cubes(gpsat_t *h, int32_t n_cubes, const int64_t *cube_offsets, co
         return GPSAT_E_ARG;
     }
     h->cube_lits_sorted.release();
+    h->cube_short.release();
     if (n_cubes == 0) {
         h->n_cubes = 1;
         h->cube_offsets_h.assign(2, 0);
@@ -942,7 +943,7 @@ int gpsat_set_cubes(gpsat_t *h, int32_t n_cubes, const int64_t *cube_offsets, co
             // list among them, so each cube's literals are ordered by the occurrence count of their negation (counting
             // sort, stable).  BCP is confluent: status and implied set do not depend on the order in which a cube's
             // literals are visited.
-            std::vector<int32_t> sorted((size_t)total);
+            std::vector<int32_t> sorted((size_t)total), n_short((size_t)n_cubes);
             const int kClasses = 12;   // 0 .. 10 occurrences, 11 and more
             for (int32_t j = 0; j < n_cubes; j++) {
                 const int64_t b = h->cube_offsets_h[(size_t)j], e = h->cube_offsets_h[(size_t)j + 1];
@@ -953,12 +954,14 @@ int gpsat_set_cubes(gpsat_t *h, int32_t n_cubes, const int64_t *cube_offsets, co
                 };
                 for (int64_t i = b; i < e; i++) at[cls(cube_lits[base + i]) + 1]++;
                 for (int c = 0; c < kClasses; c++) at[c + 1] += at[c];
+                n_short[(size_t)j] = (int32_t)at[6];   // literals with at most 5 occurrences: one 32-byte sector each
                 for (int64_t i = b; i < e; i++) {
                     const int32_t x = cube_lits[base + i];
                     sorted[(size_t)(b + at[cls(x)]++)] = x;
                 }
             }
             CU(h->cube_lits_sorted.upload(sorted.data(), sorted.size(), h->stream));
+            CU(h->cube_short.upload(n_short.data(), n_short.size(), h->stream));
             CU(cudaStreamSynchronize(h->stream));
         }
     }

@@ -287,6 +287,7 @@ struct SweepArgs {
     const int2 *occ_pair;             // per entry: the two other literals of that clause (uniform3 only)
     const uint4 *bucket;              // ternary kernel: one 64-byte bucket per literal id (2n + 2 of them)
     int32_t tern_state_bytes;         // ternary kernel: ceil((n + 1) / 5) rounded up to 16
+    const int32_t *cube_short;        // ternary kernel: per cube, how many leading literals have at most 5 occurrences (or null)
     const int32_t *coffsets;          // n_clauses+1 (general path)
     const int32_t *clits;             // compact literals
     const int64_t *cube_offsets;
@@ -1045,12 +1046,14 @@ __device__ __forceinline__ void tern_pick(const uint32_t (&w)[16], int j, uint32
 }
 
 // kind 0: four 16-byte evict-first loads; 1: four 16-byte read-only loads; 2: two 32-byte read-only loads
-__device__ __forceinline__ void tern_load_bucket(const uint4 *bucket, uint32_t f, uint32_t (&w)[16], int kind)
+// first_only (warp-uniform): every list of the batch has at most 5 entries — the second sector is not fetched
+__device__ __forceinline__ void tern_load_bucket(const uint4 *bucket, uint32_t f, uint32_t (&w)[16], int kind, bool first_only)
 {
     const uint4 *bp = bucket + 4 * (size_t)f;
     if (kind == 2) {
         asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(bp));
+        if (first_only) return;
         asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]) : "l"(bp + 2));
         return;
@@ -1105,6 +1108,7 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_tern_kernel(const Swe
         const long long c0 = A.cube_offsets[job], c1 = A.cube_offsets[job + 1];
         const int k = (int)(c1 - c0);
         const int32_t *cube = A.cube_lits + c0;
+        const int n_short = A.cube_short ? __ldg(A.cube_short + job) : 0;
         int32_t *imp = A.implied + (long long)job * A.stride;
         J.imp = imp;
 
@@ -1135,16 +1139,16 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_tern_kernel(const Swe
             uint32_t w[16], wn[16];
             if (kPrefetch) {
                 f1 = trail_f(base + nthreads + (int)lane);
-                tern_load_bucket(A.bucket, f, w, A.stream_index);
+                tern_load_bucket(A.bucket, f, w, A.stream_index, base + 32 <= n_short);
             }
             for (; base < total; base += nthreads) {   // warp-uniform trip count
                 __syncwarp();   // the lanes that resolved a hit rejoin here, not at the end of the round
                 uint32_t f2 = 0;
                 if (kPrefetch) {
                     f2 = trail_f(base + 2 * nthreads + (int)lane);
-                    tern_load_bucket(A.bucket, f1, wn, A.stream_index);
+                    tern_load_bucket(A.bucket, f1, wn, A.stream_index, base + nthreads + 32 <= n_short);
                 } else {
-                    tern_load_bucket(A.bucket, f, w, A.stream_index);
+                    tern_load_bucket(A.bucket, f, w, A.stream_index, base + 32 <= n_short);
                 }
                 const int cnt = (int)w[0];
                 visited += cnt;
@@ -1244,6 +1248,7 @@ cudaError_t launch_bcp_sweep(const SweepLaunch &L, cudaStream_t stream)
     A.occ_pair = (const int2 *)L.occ_pair;
     A.bucket = (const uint4 *)L.bucket;
     A.tern_state_bytes = L.tern_state_bytes;
+    A.cube_short = L.cube_short;
     A.coffsets = L.coffsets;
     A.clits = L.clits;
     A.cube_offsets = L.cube_offsets;

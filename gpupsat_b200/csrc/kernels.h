@@ -41,6 +41,7 @@ struct SweepLaunch {
     // them (16 words each), and the bytes of base-3 state; nullptr selects the other kernels
     const uint32_t *bucket = nullptr;
     int32_t tern_state_bytes = 0;
+    const int32_t *cube_short = nullptr;   // per cube: leading literals (sorted order) whose lists have at most 5 entries
     int tern_prefetch = 0;              // bucket fetched one batch ahead (registers), trail literal two
     const int64_t *cube_offsets;
     const int32_t *cube_lits;
