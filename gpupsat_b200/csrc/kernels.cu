@@ -287,6 +287,7 @@ struct SweepArgs {
     const int2 *occ_pair;             // per entry: the two other literals of that clause (uniform3 only)
     const uint4 *bucket;              // ternary kernel: one 64-byte bucket per literal id (2n + 2 of them)
     int32_t tern_state_bytes;         // ternary kernel: ceil((n + 1) / 5) rounded up to 16
+    int32_t l2_prefetch;              // ternary kernel: prefetch the next batch's buckets into L2
     const int32_t *cube_short;        // ternary kernel: per cube, how many leading literals have at most 5 occurrences (or null)
     const int32_t *coffsets;          // n_clauses+1 (general path)
     const int32_t *clits;             // compact literals
@@ -1135,19 +1136,19 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_tern_kernel(const Swe
                 return (uint32_t)(t < k ? __ldg(cube + t) : __ldcg(imp + (t - k))) ^ 1u;
             };
             int base = qhead + (int)warp * 32;
-            uint32_t f = trail_f(base + (int)lane), f1 = 0;
+            // the trail literal is fetched two batches ahead and (kPrefetch: into registers; otherwise: into L2 with a
+            // prefetch, which costs no register) its bucket one batch ahead
+            uint32_t f = trail_f(base + (int)lane), f1 = trail_f(base + nthreads + (int)lane);
             uint32_t w[16], wn[16];
-            if (kPrefetch) {
-                f1 = trail_f(base + nthreads + (int)lane);
-                tern_load_bucket(A.bucket, f, w, A.stream_index, base + 32 <= n_short);
-            }
+            if (kPrefetch) tern_load_bucket(A.bucket, f, w, A.stream_index, base + 32 <= n_short);
             for (; base < total; base += nthreads) {   // warp-uniform trip count
                 __syncwarp();   // the lanes that resolved a hit rejoin here, not at the end of the round
-                uint32_t f2 = 0;
+                const uint32_t f2 = trail_f(base + 2 * nthreads + (int)lane);
                 if (kPrefetch) {
-                    f2 = trail_f(base + 2 * nthreads + (int)lane);
                     tern_load_bucket(A.bucket, f1, wn, A.stream_index, base + nthreads + 32 <= n_short);
                 } else {
+                    if (A.l2_prefetch && base + nthreads < total)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(A.bucket + 4 * (size_t)f1));
                     tern_load_bucket(A.bucket, f, w, A.stream_index, base + 32 <= n_short);
                 }
                 const int cnt = (int)w[0];
@@ -1185,11 +1186,9 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_tern_kernel(const Swe
                 if (kPrefetch) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) w[i] = wn[i];
-                    f = f1;
-                    f1 = f2;
-                } else {
-                    f = trail_f(base + nthreads + (int)lane);
                 }
+                f = f1;
+                f1 = f2;
             }
             __threadfence();
             __syncthreads();
@@ -1249,6 +1248,7 @@ cudaError_t launch_bcp_sweep(const SweepLaunch &L, cudaStream_t stream)
     A.bucket = (const uint4 *)L.bucket;
     A.tern_state_bytes = L.tern_state_bytes;
     A.cube_short = L.cube_short;
+    A.l2_prefetch = L.l2_prefetch;
     A.coffsets = L.coffsets;
     A.clits = L.clits;
     A.cube_offsets = L.cube_offsets;

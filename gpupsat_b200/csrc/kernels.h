@@ -42,7 +42,8 @@ struct SweepLaunch {
     const uint32_t *bucket = nullptr;
     int32_t tern_state_bytes = 0;
     const int32_t *cube_short = nullptr;   // per cube: leading literals (sorted order) whose lists have at most 5 entries
-    int tern_prefetch = 0;              // bucket fetched one batch ahead (registers), trail literal two
+    int tern_prefetch = 0;
+    int l2_prefetch = 0;                // bucket of the next batch prefetched into L2 (no register cost; no gain measured)              // bucket fetched one batch ahead (registers), trail literal two
     const int64_t *cube_offsets;
     const int32_t *cube_lits;
     uint32_t *valbits;
