@@ -945,6 +945,7 @@ int gpsat_set_cubes(gpsat_t *h, int32_t n_cubes, const int64_t *cube_offsets, co
             // sort, stable).  BCP is confluent: status and implied set do not depend on the order in which a cube's
             // literals are visited.
             std::vector<int32_t> sorted((size_t)total), n_short((size_t)n_cubes);
+            std::vector<int32_t> seen_in((size_t)h->D.n_vars, -1);   // last cube each variable was seen in
             const int kClasses = 12;   // 0 .. 10 occurrences, 11 and more
             for (int32_t j = 0; j < n_cubes; j++) {
                 const int64_t b = h->cube_offsets_h[(size_t)j], e = h->cube_offsets_h[(size_t)j + 1];
@@ -955,7 +956,15 @@ int gpsat_set_cubes(gpsat_t *h, int32_t n_cubes, const int64_t *cube_offsets, co
                 };
                 for (int64_t i = b; i < e; i++) at[cls(cube_lits[base + i]) + 1]++;
                 for (int c = 0; c < kClasses; c++) at[c + 1] += at[c];
-                n_short[(size_t)j] = (int32_t)at[6];   // literals with at most 5 occurrences: one 32-byte sector each
+                // bits 0..29: literals with at most 5 occurrences (one 32-byte sector each); bit 30: no variable occurs
+                // twice in the cube (the kernel then assigns it with plain adds instead of compare-and-swap)
+                bool distinct = (e - b) < ((int64_t)1 << 30);
+                for (int64_t i = b; i < e; i++) {
+                    const int32_t v = cube_lits[base + i] >> 1;
+                    if (seen_in[(size_t)v] == j) distinct = false;
+                    seen_in[(size_t)v] = j;
+                }
+                n_short[(size_t)j] = (int32_t)std::min<int64_t>(at[6], ((int64_t)1 << 30) - 1) | (distinct ? 1 << 30 : 0);
                 for (int64_t i = b; i < e; i++) {
                     const int32_t x = cube_lits[base + i];
                     sorted[(size_t)(b + at[cls(x)]++)] = x;

@@ -1109,14 +1109,35 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_tern_kernel(const Swe
         const long long c0 = A.cube_offsets[job], c1 = A.cube_offsets[job + 1];
         const int k = (int)(c1 - c0);
         const int32_t *cube = A.cube_lits + c0;
-        const int n_short = A.cube_short ? __ldg(A.cube_short + job) : 0;
+        const int cube_info = A.cube_short ? __ldg(A.cube_short + job) : 0;
+        const int n_short = cube_info & 0x3FFFFFFF;
+        const bool distinct = (cube_info >> 30) & 1;   // the host checked: no variable occurs twice in this cube
         int32_t *imp = A.implied + (long long)job * A.stride;
         J.imp = imp;
 
-        for (int i = tid; i < k; i += nthreads) {   // phase 0: the whole cube is assigned up front
-            const uint32_t x = (uint32_t)__ldg(cube + i);
-            const uint32_t prev = J.assign(x);
-            if (prev && prev - 1u != (x & 1u)) s_conflict = 2;   // x and ~x in the cube: no clause to blame
+        // phase 0: the whole cube is assigned up front
+        if (distinct) {
+            // every variable at most once: its digit goes from 0 to 1 or 2 with ONE fire-and-forget shared-memory add
+            // (no carry can reach a neighbour's digit), four loads in flight per thread
+            uint32_t *sw = reinterpret_cast<uint32_t *>(s_dyn + GPSAT_TERN_LUT_BYTES);
+            for (int i0 = tid; i0 < k; i0 += 4 * nthreads) {
+                uint32_t x[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) x[u] = i0 + u * nthreads < k ? (uint32_t)__ldg(cube + i0 + u * nthreads) : 0xFFFFFFFFu;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (x[u] != 0xFFFFFFFFu) {
+                        const uint32_t var = x[u] >> 1, q = var / 5u, r = var - 5u * q;
+                        const uint32_t p3 = r == 4u ? 81u : (0x1B090301u >> (8u * r)) & 255u;
+                        atomicAdd(sw + (q >> 2), ((1u + (x[u] & 1u)) * p3) << ((q & 3u) * 8u));
+                    }
+            }
+        } else {
+            for (int i = tid; i < k; i += nthreads) {
+                const uint32_t x = (uint32_t)__ldg(cube + i);
+                const uint32_t prev = J.assign(x);
+                if (prev && prev - 1u != (x & 1u)) s_conflict = 2;   // x and ~x in the cube: no clause to blame
+            }
         }
         __syncthreads();
         if (tid == 0) {

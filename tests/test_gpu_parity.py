@@ -207,11 +207,14 @@ def test_occurrence_bcp_index_and_state_layouts(env, monkeypatch):
         vs = rng.choice(np.arange(6, n), size=K - 6, replace=False)
         hub = [2 * h + (1 - (h & 1) if (j >> h) & 1 else int(rng.integers(0, 2))) for h in range(6)]   # often false hubs
         cubes[j] = np.array(hub + [int(2 * v + rng.integers(0, 2)) for v in vs], dtype=np.int32)
+    cubes[3, 7] = cubes[3, 6]            # the same literal twice
+    cubes[4, 9] = cubes[4, 8] ^ 1        # x and ~x: refuted without a clause to blame
     co = np.arange(0, cubes.size + 1, K, dtype=np.int64)
     with g.Solver(n, offs, lits, bcp=g.binding.BCP_OCCURRENCE) as s:
         s.set_cubes(cubes)
         got = s.propagate_all()
     want = Oracle(n, offs, lits).run(co, cubes.reshape(-1), mode=2)
+    assert got["status"][4] == g.UNSAT and got["conflict_clause"][4] == -1
     occ = np.bincount(lits, minlength=2 * n)
     assert occ.max() >= 40
     assert np.array_equal(got["status"], want["records"]["status"])
@@ -223,7 +226,7 @@ def test_occurrence_bcp_index_and_state_layouts(env, monkeypatch):
             # every occurrence of the negation of every trail literal was visited exactly once
             trail = np.concatenate([cubes[j], got["implied"][j, : got["n_implied"][j]]])
             assert got["records"]["watchers_visited"][j] == occ[trail ^ 1].sum()
-        else:
+        elif j != 4:
             c = got["conflict_clause"][j]
             assert c >= 0
             trail = set(cubes[j].tolist()) | mine
