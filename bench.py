@@ -94,7 +94,8 @@ def make_workload(n_gpus):
     cnf = g.Cnf.from_arrays(offs, lits)
     pre = cnf.preprocess()
     assert pre.status == g.UNDEF
-    cubes = pre.choose_cubes(8 * n_gpus, 32)          # 10*B*T jobs wanted -> k = 12 + log2(n_gpus)
+    strong = os.environ.get("GPSAT_BENCH_SCALING", "weak") == "strong"
+    cubes = pre.choose_cubes(8 if strong else 8 * n_gpus, 32)   # 10*B*T jobs wanted -> k = 12 (+ log2(n_gpus) when weak)
     return cnf, pre, cubes
 
 

@@ -312,11 +312,13 @@ int plan_geometry(gpsat *h, int mode)
         return GPSAT_E_CUDA;
     }
     int blocks = h->opts.blocks > 0 ? h->opts.blocks : h->prop.multiProcessorCount * occ;
-    // never launch more warps than cubes (each warp owns an arena / state block)
-    const int64_t need = ((int64_t)std::max(h->n_cubes, 1) + w - 1) / w;
+    // no more warps than can find work (each warp owns an arena / state block): one per cube, or — when running cubes
+    // hand sub-cubes to idle warps (dynamic_split) — up to eight per cube, so that a GPU that received fewer cubes than
+    // it has warps (a shard of a multi-GPU run) still fills all its SMs
+    const int64_t takers = (mode == GPSAT_MODE_SOLVE && h->opts.dynamic_split) ? 8 : 1;
+    const int64_t need = (takers * (int64_t)std::max(h->n_cubes, 1) + w - 1) / w;
     if (blocks > need) blocks = (int)need;
     h->blocks = std::max(blocks, 1);
-    (void)mode;
     return GPSAT_OK;
 }
 
