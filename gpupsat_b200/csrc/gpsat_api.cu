@@ -814,69 +814,23 @@ int gpsat_create(gpsat_t **out, int32_t n_vars, int64_t n_clauses, const int64_t
     CUH(h->coffsets.upload(h->coffsets_h.data(), h->coffsets_h.size(), h->stream));
     CUH(h->clits.upload(lits + base, (size_t)h->D.n_lits, h->stream));
     if (h->opts.bcp == GPSAT_BCP_OCCURRENCE) {
-        // Occurrence lists for the sweep kernels, PADDED: every literal's list starts at an even entry index and is
-        // padded to an even length with a (-1) sentinel, so that the kernel reads it as 16-byte loads of two entries
-        // and finds (begin, end) of a list with ONE 8-byte load (orange) — half the memory requests per literal of
-        // the plain CSR.  Per entry: the clause index, and for pure 3-SAT the two other literals of that clause (no
-        // clause dereference on the hot path).
-        const size_t L = (size_t)h->D.n_lits;
-        const size_t n_lit_ids = 2 * (size_t)std::max(n_vars, 0);
-        h->uniform3 = (h->D.n_clauses > 0 && h->D.n_lits == 3 * h->D.n_clauses && h->D.max_clause_len == 3) ? 1 : 0;
-        std::vector<int32_t> orange(2 * n_lit_ids, 0), oc, op;
-        oc.reserve(L + n_lit_ids);
-        if (h->uniform3) op.reserve(2 * (L + n_lit_ids));
-        for (size_t f = 0; f < n_lit_ids; f++) {
-            orange[2 * f] = (int32_t)oc.size();
-            for (int32_t k = h->D.ostart[f]; k < h->D.ostart[f + 1]; k++) {
-                const int32_t s0 = h->D.occ2[2 * (size_t)k], len = h->D.occ2[2 * (size_t)k + 1];
-                oc.push_back(h->D.cl2[2 * (size_t)(s0 - 1) + 1]);
-                if (h->uniform3)
-                    for (int i = 0; i < len; i++) {
-                        if (h->D.cl2[2 * (size_t)(s0 + i) + 1] == k) continue;
-                        op.push_back(h->D.cl2[2 * (size_t)(s0 + i)]);
-                    }
-            }
-            if (oc.size() & 1) {
-                oc.push_back(-1);
-                if (h->uniform3) {
-                    op.push_back(-1);
-                    op.push_back(-1);
-                }
-            }
-            orange[2 * f + 1] = (int32_t)oc.size();
-        }
-        if (oc.empty()) oc.push_back(-1);
-        CUH(h->orange.upload(orange.data(), orange.size(), h->stream));
-        CUH(h->occ_clause.upload(oc.data(), oc.size(), h->stream));
-        if (h->uniform3) CUH(h->occ_pair.upload(op.data(), op.size(), h->stream));
-        // Ternary kernel (gpsat_bcp_sweep_tern_kernel): pure 3-SAT whose literal ids (with those of a sentinel variable
-        // n) fit 21 bits and whose base-3 state (five variables per byte) fits one SM's shared memory beside the
-        // lookup table and the hit queues.  Bucket index: the list packed into its head, one 64-byte bucket per literal
-        // id — word 0 the count, entries 0..4 from bit 32 and 5..10 from bit 256 at 42 bits each, unused entries hold
-        // the sentinel's true literal.  GPSAT_SWEEP_TERNARY=0 keeps the other kernels.
+        // Occurrence index of the sweep kernels (host_formula.cpp: build_sweep_index).  The bucket index and with it the
+        // ternary kernel (gpsat_bcp_sweep_tern_kernel) are used for pure 3-SAT whose literal ids fit 21 bits and whose
+        // base-3 state (five variables per byte) fits one SM's shared memory beside the lookup table;
+        // GPSAT_SWEEP_TERNARY=0 keeps the other kernels.
         const char *e_tn = std::getenv("GPSAT_SWEEP_TERNARY");
         const int32_t state_bytes = (int32_t)((((int64_t)n_vars + 1 + 4) / 5 + 15) / 16 * 16);
+        const bool want_buckets = !(e_tn && std::atoi(e_tn) == 0) &&
+                                  gpsat_kernels::tern_smem_bytes(state_bytes) + 256 <= h->prop.sharedMemPerBlockOptin;
+        gpsat_host::SweepIndex X;
+        gpsat_host::build_sweep_index(h->D, want_buckets, X);
+        h->uniform3 = X.uniform3;
         h->tern_state_bytes = 0;
-        if (h->uniform3 && n_lit_ids + 2 <= ((size_t)1 << 21) && !(e_tn && std::atoi(e_tn) == 0) &&
-            gpsat_kernels::tern_smem_bytes(state_bytes) + 256 <= h->prop.sharedMemPerBlockOptin) {
-            const uint32_t pad = (uint32_t)n_lit_ids + 1u;   // 2n + 1: the sentinel's positive literal
-            std::vector<uint32_t> bk(16 * (n_lit_ids + 2), 0u);
-            auto put = [](uint32_t *w, int bit, uint32_t v) {
-                w[bit >> 5] |= v << (bit & 31);
-                if ((bit & 31) + 21 > 32) w[(bit >> 5) + 1] |= v >> (32 - (bit & 31));
-            };
-            for (size_t f = 0; f < n_lit_ids + 2; f++) {
-                uint32_t *w = bk.data() + 16 * f;
-                const int32_t os = f < n_lit_ids ? orange[2 * f] : 0;
-                const int32_t cnt = f < n_lit_ids ? h->D.ostart[f + 1] - h->D.ostart[f] : 0;
-                w[0] = (uint32_t)cnt;
-                for (int j = 0; j < 11; j++) {
-                    const int bit = j < 5 ? 32 + 42 * j : 256 + 42 * (j - 5);
-                    put(w, bit, j < cnt ? (uint32_t)op[2 * (size_t)(os + j)] : pad);
-                    put(w, bit + 21, j < cnt ? (uint32_t)op[2 * (size_t)(os + j) + 1] : pad);
-                }
-            }
-            CUH(h->occ_bucket.upload(bk.data(), bk.size(), h->stream));
+        CUH(h->orange.upload(X.orange.data(), X.orange.size(), h->stream));
+        CUH(h->occ_clause.upload(X.occ_clause.data(), X.occ_clause.size(), h->stream));
+        if (X.uniform3) CUH(h->occ_pair.upload(X.occ_pair.data(), X.occ_pair.size(), h->stream));
+        if (!X.bucket.empty()) {
+            CUH(h->occ_bucket.upload(X.bucket.data(), X.bucket.size(), h->stream));
             h->tern_state_bytes = state_bytes;
         }
         CUH(cudaStreamSynchronize(h->stream));
@@ -942,36 +896,11 @@ int gpsat_set_cubes(gpsat_t *h, int32_t n_cubes, const int64_t *cube_offsets, co
         }
         CU(h->cube_lits.upload(cube_lits + base, (size_t)total, h->stream));
         if (h->tern_state_bytes > 0) {
-            // Ternary sweep kernel: a warp scans the buckets of 32 trail literals in lock step and stops at the longest
-            // list among them, so each cube's literals are ordered by the occurrence count of their negation (counting
-            // sort, stable).  BCP is confluent: status and implied set do not depend on the order in which a cube's
-            // literals are visited.
-            std::vector<int32_t> sorted((size_t)total), n_short((size_t)n_cubes);
-            std::vector<int32_t> seen_in((size_t)h->D.n_vars, -1);   // last cube each variable was seen in
-            const int kClasses = 12;   // 0 .. 10 occurrences, 11 and more
-            for (int32_t j = 0; j < n_cubes; j++) {
-                const int64_t b = h->cube_offsets_h[(size_t)j], e = h->cube_offsets_h[(size_t)j + 1];
-                int64_t at[kClasses + 1] = {0};
-                auto cls = [&](int32_t x) {
-                    const int32_t f = x ^ 1;
-                    return std::min<int32_t>(h->D.ostart[(size_t)f + 1] - h->D.ostart[(size_t)f], kClasses - 1);
-                };
-                for (int64_t i = b; i < e; i++) at[cls(cube_lits[base + i]) + 1]++;
-                for (int c = 0; c < kClasses; c++) at[c + 1] += at[c];
-                // bits 0..29: literals with at most 5 occurrences (one 32-byte sector each); bit 30: no variable occurs
-                // twice in the cube (the kernel then assigns it with plain adds instead of compare-and-swap)
-                bool distinct = (e - b) < ((int64_t)1 << 30);
-                for (int64_t i = b; i < e; i++) {
-                    const int32_t v = cube_lits[base + i] >> 1;
-                    if (seen_in[(size_t)v] == j) distinct = false;
-                    seen_in[(size_t)v] = j;
-                }
-                n_short[(size_t)j] = (int32_t)std::min<int64_t>(at[6], ((int64_t)1 << 30) - 1) | (distinct ? 1 << 30 : 0);
-                for (int64_t i = b; i < e; i++) {
-                    const int32_t x = cube_lits[base + i];
-                    sorted[(size_t)(b + at[cls(x)]++)] = x;
-                }
-            }
+            // Ternary sweep kernel: every cube's literals ordered by the length of the list they make the kernel visit
+            // (host_formula.cpp: order_cubes_for_sweep).  BCP is confluent: status and implied set do not depend on the
+            // order in which a cube's literals are visited.
+            std::vector<int32_t> sorted, n_short;
+            gpsat_host::order_cubes_for_sweep(h->D, n_cubes, cube_offsets, cube_lits, sorted, n_short);
             CU(h->cube_lits_sorted.upload(sorted.data(), sorted.size(), h->stream));
             CU(h->cube_short.upload(n_short.data(), n_short.size(), h->stream));
             CU(cudaStreamSynchronize(h->stream));

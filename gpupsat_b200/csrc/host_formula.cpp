@@ -493,6 +493,90 @@ int build_device_formula(int32_t n_vars, int64_t n_clauses, const int64_t *offse
     return GPSAT_OK;
 }
 
+void build_sweep_index(const DeviceFormula &D, bool want_buckets, SweepIndex &out)
+{
+    const size_t L = (size_t)D.n_lits;
+    const size_t n_lit_ids = 2 * (size_t)std::max(D.n_vars, 0);
+    out.uniform3 = (D.n_clauses > 0 && D.n_lits == 3 * D.n_clauses && D.max_clause_len == 3) ? 1 : 0;
+    out.orange.assign(2 * n_lit_ids, 0);
+    out.occ_clause.clear();
+    out.occ_pair.clear();
+    out.bucket.clear();
+    out.occ_clause.reserve(L + n_lit_ids);
+    if (out.uniform3) out.occ_pair.reserve(2 * (L + n_lit_ids));
+    for (size_t f = 0; f < n_lit_ids; f++) {
+        out.orange[2 * f] = (int32_t)out.occ_clause.size();
+        for (int32_t k = D.ostart[f]; k < D.ostart[f + 1]; k++) {
+            const int32_t s0 = D.occ2[2 * (size_t)k], len = D.occ2[2 * (size_t)k + 1];
+            out.occ_clause.push_back(D.cl2[2 * (size_t)(s0 - 1) + 1]);
+            if (out.uniform3)
+                for (int i = 0; i < len; i++) {
+                    if (D.cl2[2 * (size_t)(s0 + i) + 1] == k) continue;
+                    out.occ_pair.push_back(D.cl2[2 * (size_t)(s0 + i)]);
+                }
+        }
+        if (out.occ_clause.size() & 1) {
+            out.occ_clause.push_back(-1);
+            if (out.uniform3) {
+                out.occ_pair.push_back(-1);
+                out.occ_pair.push_back(-1);
+            }
+        }
+        out.orange[2 * f + 1] = (int32_t)out.occ_clause.size();
+    }
+    if (out.occ_clause.empty()) out.occ_clause.push_back(-1);
+    if (!want_buckets || !out.uniform3 || n_lit_ids + 2 > ((size_t)1 << kBucketLitBits)) return;
+    const uint32_t pad = (uint32_t)n_lit_ids + 1u;   // 2n + 1: the sentinel's positive literal
+    out.bucket.assign(16 * (n_lit_ids + 2), 0u);
+    auto put = [](uint32_t *w, int bit, uint32_t v) {
+        w[bit >> 5] |= v << (bit & 31);
+        if ((bit & 31) + kBucketLitBits > 32) w[(bit >> 5) + 1] |= v >> (32 - (bit & 31));
+    };
+    for (size_t f = 0; f < n_lit_ids + 2; f++) {
+        uint32_t *w = out.bucket.data() + 16 * f;
+        const int32_t os = f < n_lit_ids ? out.orange[2 * f] : 0;
+        const int32_t cnt = f < n_lit_ids ? D.ostart[f + 1] - D.ostart[f] : 0;
+        w[0] = (uint32_t)cnt;
+        for (int j = 0; j < kBucketEntries; j++) {
+            const int bit = bucket_entry_bit(j);
+            put(w, bit, j < cnt ? (uint32_t)out.occ_pair[2 * (size_t)(os + j)] : pad);
+            put(w, bit + kBucketLitBits, j < cnt ? (uint32_t)out.occ_pair[2 * (size_t)(os + j) + 1] : pad);
+        }
+    }
+}
+
+void order_cubes_for_sweep(const DeviceFormula &D, int32_t n_cubes, const int64_t *cube_offsets, const int32_t *cube_lits,
+                           std::vector<int32_t> &sorted, std::vector<int32_t> &info)
+{
+    const int64_t base = n_cubes > 0 ? cube_offsets[0] : 0;
+    const int64_t total = n_cubes > 0 ? cube_offsets[n_cubes] - base : 0;
+    sorted.assign((size_t)total, 0);
+    info.assign((size_t)std::max(n_cubes, 0), 0);
+    std::vector<int32_t> seen_in((size_t)std::max(D.n_vars, 1), -1);   // last cube each variable was seen in
+    const int kClasses = 12;                                           // 0 .. 10 occurrences, 11 and more
+    auto cls = [&](int32_t x) {
+        const size_t f = (size_t)(x ^ 1);
+        return std::min<int32_t>(D.ostart[f + 1] - D.ostart[f], kClasses - 1);
+    };
+    for (int32_t j = 0; j < n_cubes; j++) {
+        const int64_t b = cube_offsets[j] - base, e = cube_offsets[j + 1] - base;
+        int64_t at[kClasses + 1] = {0};
+        bool distinct = (e - b) < ((int64_t)1 << 30);
+        for (int64_t i = b; i < e; i++) {
+            const int32_t x = cube_lits[base + i];
+            at[cls(x) + 1]++;
+            if (seen_in[(size_t)(x >> 1)] == j) distinct = false;
+            seen_in[(size_t)(x >> 1)] = j;
+        }
+        for (int c = 0; c < kClasses; c++) at[c + 1] += at[c];
+        info[(size_t)j] = (int32_t)std::min<int64_t>(at[6], ((int64_t)1 << 30) - 1) | (distinct ? 1 << 30 : 0);
+        for (int64_t i = b; i < e; i++) {
+            const int32_t x = cube_lits[base + i];
+            sorted[(size_t)(b + at[cls(x)]++)] = x;
+        }
+    }
+}
+
 }  // namespace gpsat_host
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -74,3 +74,37 @@ def run(n_vars, offsets, lits, cube_offsets, cube_lits, *, mode=0, decision=1, r
     return {"launches": launches.value, "records": rec, "sat_job": sat_job.value, "model": model[:n_vars],
             "implied": implied.reshape(n_cubes, n_vars) if n_vars else implied, "n_implied": n_implied,
             "conflict_clause": confl, "pool": pool, "pool_cursor": pool_cursor}
+
+
+def bucket_index(n_vars, offsets, lits):
+    """host-side bucket index of the ternary sweep kernel (host_formula.cpp: build_sweep_index):
+    (bucket words [2n+2, 16], orange [2n, 2]) or None when the database does not qualify"""
+    build()
+    lib = C.CDLL(SO)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    lits = np.ascontiguousarray(lits, dtype=np.int32)
+    bucket = np.zeros((2 * n_vars + 2, 16), dtype=np.uint32)
+    orange = np.zeros((2 * n_vars, 2), dtype=np.int32)
+    n_entries = C.c_int64(0)
+    rc = lib.gpsat_emu_bucket_index(C.c_int32(n_vars), C.c_int64(len(offsets) - 1), _p(offsets), _p(lits), _p(bucket),
+                                    _p(orange), C.byref(n_entries))
+    if rc == 1:
+        return None
+    assert rc == 0
+    return bucket, orange
+
+
+def order_cubes(n_vars, offsets, lits, cube_offsets, cube_lits):
+    """host_formula.cpp: order_cubes_for_sweep -> (sorted literals, info word per cube)"""
+    build()
+    lib = C.CDLL(SO)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    lits = np.ascontiguousarray(lits, dtype=np.int32)
+    co = np.ascontiguousarray(cube_offsets, dtype=np.int64)
+    cl = np.ascontiguousarray(cube_lits, dtype=np.int32)
+    out = np.zeros(max(int(co[-1] - co[0]), 1), dtype=np.int32)
+    info = np.zeros(len(co) - 1, dtype=np.int32)
+    rc = lib.gpsat_emu_order_cubes(C.c_int32(n_vars), C.c_int64(len(offsets) - 1), _p(offsets), _p(lits),
+                                   C.c_int32(len(co) - 1), _p(co), _p(cl), _p(out), _p(info))
+    assert rc == 0
+    return out[: int(co[-1] - co[0])], info

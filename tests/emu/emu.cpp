@@ -88,3 +88,34 @@ extern "C" int gpsat_emu_run(int32_t n_vars, int64_t n_clauses, const int64_t *o
     for (int j = 0; j < n_cubes; j++) records[j].status = gpsat_root_status(root_flag[j], root_pending[j]);
     return 0;
 }
+
+// ---- host-side index of the large-database sweep kernels (host_formula.cpp), exposed for the CPU tests --------------
+extern "C" int gpsat_emu_bucket_index(int32_t n_vars, int64_t n_clauses, const int64_t *offsets, const int32_t *lits,
+                                      uint32_t *bucket /* 16 * (2n + 2) */, int32_t *orange /* 2 * 2n */,
+                                      int64_t *n_entries)
+{
+    gpsat_host::DeviceFormula D;
+    int rc = gpsat_host::build_device_formula(n_vars, n_clauses, offsets, lits, D);
+    if (rc != 0) return rc;
+    gpsat_host::SweepIndex X;
+    gpsat_host::build_sweep_index(D, true, X);
+    if (X.bucket.empty()) return 1;   // database does not qualify for the bucket index
+    std::copy(X.bucket.begin(), X.bucket.end(), bucket);
+    std::copy(X.orange.begin(), X.orange.end(), orange);
+    *n_entries = (int64_t)X.occ_clause.size();
+    return 0;
+}
+
+extern "C" int gpsat_emu_order_cubes(int32_t n_vars, int64_t n_clauses, const int64_t *offsets, const int32_t *lits,
+                                     int32_t n_cubes, const int64_t *cube_offsets, const int32_t *cube_lits,
+                                     int32_t *sorted, int32_t *info)
+{
+    gpsat_host::DeviceFormula D;
+    int rc = gpsat_host::build_device_formula(n_vars, n_clauses, offsets, lits, D);
+    if (rc != 0) return rc;
+    std::vector<int32_t> s, i;
+    gpsat_host::order_cubes_for_sweep(D, n_cubes, cube_offsets, cube_lits, s, i);
+    std::copy(s.begin(), s.end(), sorted);
+    std::copy(i.begin(), i.end(), info);
+    return 0;
+}

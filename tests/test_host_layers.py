@@ -137,3 +137,96 @@ def test_roundtrip_dimacs(tmp_path):
     assert cnf.largest_clause == 3
     v, cnt = np.unique(lits >> 1, return_counts=True)
     assert cnf.most_common_freq == cnt.max()
+
+
+# ---- index of the large-database sweep kernel (host_formula.cpp: build_sweep_index / order_cubes_for_sweep) ----------
+def _decode_bucket(words):
+    """(count, [(a, b)] * 11) of one 64-byte bucket, read the way the kernel does (tern_field in kernels.cu)"""
+    bits = 0
+    for i, w in enumerate(words):
+        bits |= int(w) << (32 * i)
+    entries = []
+    for j in range(11):
+        o = 32 + 42 * j if j < 5 else 256 + 42 * (j - 5)
+        entries.append(((bits >> o) & 0x1FFFFF, (bits >> (o + 21)) & 0x1FFFFF))
+    return int(words[0]), entries
+
+
+def test_bucket_index_holds_every_occurrence_list():
+    from gpupsat_b200.instances import random_ksat
+    from tests.emu import binding as emu
+    n, m = 300, 1300
+    offs, lits = random_ksat(n, m, 3)
+    extra = [[1, 2 * v, 2 * v + 3] for v in range(2, 32)]                     # literal 1 gets a list of 30+ entries
+    lits = np.concatenate([lits, np.array(extra, dtype=np.int32).reshape(-1)])
+    offs = np.arange(0, len(lits) + 1, 3, dtype=np.int64)
+    bucket, orange = emu.bucket_index(n, offs, lits)
+    clauses = lits.reshape(-1, 3)
+    want = {f: [] for f in range(2 * n)}
+    for c in clauses:                                                          # clause order = occurrence order
+        for i in range(3):
+            want[int(c[i])].append(tuple(int(x) for k, x in enumerate(c) if k != i))
+    pad = 2 * n + 1
+    assert max(len(v) for v in want.values()) > 11
+    for f in range(2 * n):
+        cnt, entries = _decode_bucket(bucket[f])
+        assert cnt == len(want[f]) and orange[f, 1] - orange[f, 0] in (cnt, cnt + 1)
+        for j in range(11):
+            assert entries[j] == (want[f][j] if j < cnt else (pad, pad)), (f, j)
+    for f in (2 * n, 2 * n + 1):                                               # the sentinel's buckets: empty, all padding
+        cnt, entries = _decode_bucket(bucket[f])
+        assert cnt == 0 and all(e == (pad, pad) for e in entries)
+    # not pure 3-SAT -> no bucket index
+    assert emu.bucket_index(4, np.array([0, 2, 5]), np.array([0, 3, 1, 4, 6], dtype=np.int32)) is None
+
+
+def test_cube_order_for_the_sweep_kernel():
+    from gpupsat_b200.instances import random_ksat
+    from tests.emu import binding as emu
+    n, m = 300, 1300
+    offs, lits = random_ksat(n, m, 4)
+    occ = np.bincount(lits, minlength=2 * n)
+    rng = np.random.default_rng(0)
+    cubes = [rng.choice(2 * n, size=k, replace=False).astype(np.int32) for k in (40, 1, 0, 77)]
+    cubes[1] = np.array([5], dtype=np.int32)
+    cubes.append(np.array([8, 9, 8, 20], dtype=np.int32))                      # variable 4 three times
+    co = np.cumsum([0] + [len(c) for c in cubes]).astype(np.int64) + 3         # a base offset, as the ABI allows
+    cl = np.concatenate([np.zeros(3, dtype=np.int32)] + cubes)
+    out, info = emu.order_cubes(n, offs, lits, co, cl)
+    at = 0
+    for j, c in enumerate(cubes):
+        got = out[at: at + len(c)]
+        at += len(c)
+        assert sorted(got.tolist()) == sorted(c.tolist())                      # a permutation of the cube
+        cls = np.minimum(occ[got ^ 1], 11)
+        assert (np.diff(cls) >= 0).all()                                       # ordered by the list length of the negation
+        for k in range(12):                                                    # stable inside a class
+            assert got[cls == k].tolist() == [x for x in c.tolist() if min(occ[x ^ 1], 11) == k]
+        assert (info[j] & 0x3FFFFFFF) == int((occ[c ^ 1] <= 5).sum())
+        distinct = len(set((c >> 1).tolist())) == len(c)
+        assert ((info[j] >> 30) & 1) == int(distinct)
+    # random_ksat rejects repeats inside a clause but a random 40-literal cube may hold x and ~x: both cases occurred?
+    assert ((info >> 30) & 1).tolist()[4] == 0
+
+
+def test_ternary_state_arithmetic_of_the_sweep_kernel():
+    """the integer identities gpsat_bcp_sweep_tern_kernel's lookups rest on (kernels.cu: TernJob::code / assign)"""
+    x = np.arange(0, 1 << 21, dtype=np.uint64)
+    assert np.array_equal((x * 0x1999999A) >> 32, x // 10)                     # q = __umulhi(x, 0x1999999A) = x / 10
+    r = np.arange(5)
+    assert [(0x1B090301 >> (8 * int(k))) & 255 if k < 4 else 81 for k in r] == [1, 3, 9, 27, 81]
+    # five base-3 digits per byte never exceed a byte, and adding a digit's weight to a byte whose digit is 0 changes
+    # that digit only (what the add-assigned cubes rely on)
+    assert 2 * (1 + 3 + 9 + 27 + 81) == 242
+    for byte in range(243):
+        digits = [(byte // 3 ** k) % 3 for k in range(5)]
+        for k in range(5):
+            if digits[k] == 0:
+                for d in (1, 2):
+                    nb = byte + d * 3 ** k
+                    assert nb <= 242 and [(nb // 3 ** i) % 3 for i in range(5)] == digits[:k] + [d] + digits[k + 1:]
+    # literal x = 2 var + sign lives in byte x // 10 at table column x % 10 = 2 (var % 5) + sign
+    v = np.arange(0, 1 << 20, dtype=np.int64)
+    for sgn in (0, 1):
+        lit = 2 * v + sgn
+        assert np.array_equal(lit // 10, v // 5) and np.array_equal(lit % 10, 2 * (v % 5) + sgn)
