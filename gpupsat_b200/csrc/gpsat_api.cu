@@ -495,19 +495,23 @@ int32_t run_verdict(gpsat *h, bool *all_done)
     return GPSAT_UNSAT;
 }
 
-// occurrence-list BCP for large clause databases: gpsat_bcp_sweep_kernel, one warp per cube, all state in HBM
+// occurrence-list BCP for large clause databases (GPSAT_BCP_OCCURRENCE): picks and launches one of the sweep kernels
 int propagate_all_occurrence(gpsat *h, int32_t *status, int32_t *n_implied, int32_t *implied, int64_t implied_stride,
                              int64_t *conflict_clause, gpsat_job_record *records)
 {
     const size_t nc = (size_t)h->n_cubes;
     if (implied_stride <= 0) implied_stride = h->D.n_vars;       // the implied block doubles as the trail
     const int32_t val_words = (h->D.n_vars + 15) / 16;
-    // Preferred: one thread-block cluster per job with the assignment bitmap in distributed shared memory: the
-    // smallest cluster whose per-CTA slice is at most 160 KB (n = 1e6: 2 CTAs x 128 KB, one CTA of 1024 threads per
-    // SM — measured faster than 4 x 64 KB or 8 x 32 KB, whose larger share of remote lookups loads the SM-to-SM
-    // network: profiles/r01_c4_sweep_f.json).  Falls back to the
-    // HBM-bitmap kernel (one warp per job) when even 16 CTAs cannot hold the bitmap.  GPSAT_SWEEP_CLUSTER /
-    // GPSAT_SWEEP_THREADS / GPSAT_SWEEP_SLICE_KB override for experiments (cluster 0 = HBM-bitmap kernel).
+    // Kernel choice, best first (measured on C4):
+    //   1. ternary kernel — pure 3-SAT whose base-3 state fits one SM (gpsat_create built the bucket index);
+    //   2. one CTA per job, assigned-bit filter in shared memory + 2-bit values in an L2-resident global block — any
+    //      clause lengths, as long as one bit per variable fits one SM;
+    //   3. one thread-block cluster per job with the 2-bit bitmap in distributed shared memory: the smallest cluster
+    //      whose per-CTA slice is at most 160 KB (measured faster than more, smaller slices, whose larger share of
+    //      remote lookups loads the SM-to-SM network: profiles/r01_c4_sweep_f.json);
+    //   4. HBM-bitmap kernel (one warp per job) when even 16 CTAs cannot hold the bitmap.
+    // GPSAT_SWEEP_TERNARY=0 / GPSAT_SWEEP_CLUSTER / GPSAT_SWEEP_THREADS / GPSAT_SWEEP_SLICE_KB override for
+    // experiments and tests (GPSAT_SWEEP_CLUSTER=0: HBM-bitmap kernel).
     int cluster = 0, slice_log2 = 4, cthreads = 1024;
     // first choice when the database qualifies (gpsat_create built the bucket index): the ternary kernel
     const bool use_tern = h->tern_state_bytes > 0 && !std::getenv("GPSAT_SWEEP_CLUSTER") &&
