@@ -926,28 +926,32 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) gpsat_bcp_sweep_cta_ke
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// gpsat_bcp_sweep_tern_kernel — occurrence-list BCP, one CTA per job, for pure 3-SAT databases of up to ~1.1 M
-// variables: the WHOLE job state stays in the SM's shared memory and a literal costs one 64-byte memory access.
+// gpsat_bcp_sweep_tern_kernel — occurrence-list BCP, one CTA per job, for pure 3-SAT databases of up to ~1.04 M
+// variables: the WHOLE job state stays in the SM's shared memory and a literal costs one 32- or 64-byte memory access.
 //
 // State: base-3 digits, five variables per byte (3^5 = 243 <= 256): 0 unassigned, 1 false, 2 true — n = 1e6 needs
 //   200 KB, which fits one SM where the 2-bit encoding (250 KB) does not.  A lookup is branch-free:
 //   q = x / 10 (one IMAD.HI), byte = S[q], code = LUT[byte * 20 + (x - 10 q)] — the 5 KB table folds digit
 //   extraction and the literal's sign into one load and returns 0 (false), 1 (unassigned) or 4 (true), so that a
-//   clause with other literals (a, b) needs attention iff code(a) + code(b) <= 1.  Assigning is a compare-and-swap on the 32-bit word that holds the
-//   byte; its outcome is the authority for "append to the trail exactly once".
+//   clause with other literals (a, b) needs attention iff code(a) + code(b) <= 1.  Assigning is a compare-and-swap
+//   on the 32-bit word that holds the byte; its outcome is the authority for "append to the trail exactly once"
+//   (a cube without repeated variables is written with plain adds instead).
 //   No global-memory state at all (the CTA kernel above keeps 2-bit fields in L2 behind a shared-memory filter: ncu
 //   showed 38 % of its stall samples on those reads / atomics and 12 of 32 lanes active on average).
-// Index: one 64-byte bucket per literal, the occurrence list packed INTO its head (built by gpsat_create):
+// Index: one 64-byte bucket per literal, the occurrence list packed INTO its head (host_formula.cpp:
+//   build_sweep_index):
 //   word 0            number of occurrences of the literal
 //   bits  32 .. 241   entries 0..4   } 42 bits per entry: the two OTHER literals of the clause, 21 bits each;
 //   bits 256 .. 507   entries 5..10  } unused entries hold the always-true literal of a sentinel variable n
-//   so a literal is ONE round trip of two adjacent sectors instead of head -> list (two dependent round trips, a
-//   32-byte sector for the 8-byte head plus the sectors an unaligned list straddles).  The 2 % of literals with more
-//   than 11 occurrences (Poisson, mean 6) read entries 11.. from the plain pair list.
-// Warp-uniform control flow: a warp takes 32 trail literals, every lane decodes and looks up all 11 slots of its
-//   bucket with no branch (padding evaluates as "satisfied"); a clause that became unit or conflicting (one in four
-//   literals has one) is parked in a register and resolved once per batch.  The trail literal is fetched two batches
-//   ahead and the bucket one batch ahead, so the memory round trips overlap the lookups of the batch before.
+//   so a literal is ONE round trip of one or two adjacent sectors instead of head -> list (two dependent round trips,
+//   a 32-byte sector for the 8-byte head plus the sectors an unaligned list straddles).  The 2 % of literals with
+//   more than 11 occurrences (Poisson, mean 6) read entries 11.. from the plain pair list.
+// Warp-uniform control flow: a warp takes 32 trail literals; every lane decodes and looks its bucket's entries up
+//   with no branch (padding evaluates as "satisfied"), as many entries as the longest list of the batch has (the
+//   host orders a cube's literals by list length, so the lists of a batch are about equally long), and marks the
+//   clauses that became unit or conflicting (one literal in four has one) in a bit mask; the lanes with marks then
+//   resolve them and rejoin the warp at the top of the next batch (__syncwarp).  The trail literal is fetched two
+//   batches ahead.
 // A lookup that misses an assignment made during the current round reads "unassigned"; the literal that was
 // assigned is processed in a later round (after a barrier) and re-examines the clause, so no unit is lost.
 // ---------------------------------------------------------------------------------------------------------------
