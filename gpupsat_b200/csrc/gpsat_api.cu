@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -29,23 +30,28 @@ using gpsat_host::set_error;
         }                                                                                            \
     } while (0)
 
-// Big device buffers (per-warp arenas, hand-off blocks, pools: hundreds of MB) are recycled through a small
-// process-wide cache, so that create/solve/destroy cycles — one per solve in the end-to-end path — do not pay
-// cudaMalloc/cudaFree for them every time.
+// Device buffers are recycled through a process-wide cache, so that create/solve/destroy cycles — one per solve in
+// the end-to-end path — do not pay cudaMalloc/cudaFree every time: the big ones (per-warp arenas, hand-off blocks,
+// pools: hundreds of MB) because allocating them costs milliseconds, the small ones (a few dozen per handle) because
+// cudaFree synchronises the device and, once NCCL has enabled peer access between the GPUs of a box, every
+// cudaMalloc / cudaFree also maps / unmaps the block for the peers (bench.py at N = 8: 7 ms of a 32 ms end-to-end
+// solve went into these calls).
 struct CachedBlock {
     int device;
     void *p;
     size_t bytes;
 };
 std::vector<CachedBlock> g_block_cache;
-const size_t kCacheMinBytes = (size_t)1 << 20;
-const size_t kCacheMaxBlocks = 24;
+std::mutex g_block_cache_mutex;
+const size_t kCacheMaxBlocks = 160;
 
 cudaError_t cached_alloc(void **p, size_t bytes, size_t *got)
 {
     int dev = 0;
     cudaGetDevice(&dev);
-    if (bytes >= kCacheMinBytes) {
+    bytes = (bytes + 255) / 256 * 256;
+    {
+        std::lock_guard<std::mutex> lock(g_block_cache_mutex);
         size_t best = g_block_cache.size();
         for (size_t i = 0; i < g_block_cache.size(); i++) {
             const CachedBlock &b = g_block_cache[i];
@@ -61,7 +67,8 @@ cudaError_t cached_alloc(void **p, size_t bytes, size_t *got)
         }
     }
     cudaError_t e = cudaMalloc(p, bytes);
-    if (e != cudaSuccess && !g_block_cache.empty()) {   // out of memory: drop the cache and retry once
+    if (e != cudaSuccess) {   // out of memory: drop the cache and retry once
+        std::lock_guard<std::mutex> lock(g_block_cache_mutex);
         for (auto &b : g_block_cache) cudaFree(b.p);
         g_block_cache.clear();
         cudaGetLastError();
@@ -74,13 +81,10 @@ cudaError_t cached_alloc(void **p, size_t bytes, size_t *got)
 void cached_free(void *p, size_t bytes)
 {
     if (!p) return;
-    if (bytes < kCacheMinBytes) {
-        cudaFree(p);
-        return;
-    }
     int dev = 0;
     cudaGetDevice(&dev);
-    if (g_block_cache.size() >= kCacheMaxBlocks) {
+    std::lock_guard<std::mutex> lock(g_block_cache_mutex);
+    if (g_block_cache.size() >= kCacheMaxBlocks) {   // evict the block that has been unused for the longest
         cudaFree(g_block_cache.front().p);
         g_block_cache.erase(g_block_cache.begin());
     }
