@@ -11,7 +11,11 @@ offs, lits = random_ksat(250, 1065, 0)
 pre = g.Cnf.from_arrays(offs, lits).preprocess()
 cubes = pre.choose_cubes(8, 32)
 for spec in sys.argv[1:] or [""]:
-    opts = {k: int(v) for k, v in (kv.split("=") for kv in spec.split())}
+    kvs = [kv.split("=") for kv in spec.split()]
+    for k in [k for k in os.environ if k.startswith("GPSAT_") and k != "GPSAT_BENCH_C4"]:
+        del os.environ[k]
+    os.environ.update({k: v for k, v in kvs if k.startswith("GPSAT_")})       # library knobs read through getenv
+    opts = {k: int(v) for k, v in kvs if not k.startswith("GPSAT_")}
     try:
         with g.Solver(250, pre.offsets, pre.lits, **opts) as s:
             s.set_cubes(cubes)
