@@ -46,9 +46,9 @@ def main():
                            "reference_native": run(REF, path, mode, d), "gpupsat_b200": run(OURS, path, mode, d)}
                     rows.append(row)
                     print(json.dumps(row), flush=True)
-    if args.out:
-        json.dump({"what": "reference (native sm_100a build, unmodified kernels) vs gpupsat_b200 CLI on one B200",
-                   "rows": rows}, open(args.out, "w"), indent=1)
+                    if args.out:      # rewritten after every row: a run cut short keeps what it measured
+                        json.dump({"what": "reference (native sm_100a build, unmodified kernels) vs gpupsat_b200 CLI on "
+                                           "one B200", "rows": rows}, open(args.out, "w"), indent=1)
 
 
 if __name__ == "__main__":
