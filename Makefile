@@ -20,8 +20,8 @@ build/host_formula.o: $(CSRC)/host_formula.cpp $(DEPS)
 	@mkdir -p build
 	$(CXX) -std=c++17 -O2 -Wall -fPIC -c $< -o $@
 
-gpupsat_b200/libgpsat.so: build/kernels.o build/gpsat_api.o build/host_formula.o
-	$(NVCC) -shared $(ARCH) -o $@ $^ -cudart shared
+gpupsat_b200/libgpsat.so: build/kernels.o build/gpsat_api.o build/gpsat_multi.o build/host_formula.o
+	$(NVCC) -shared $(ARCH) -o $@ $^ -cudart shared -ldl
 
 gpupsat_b200/gpupsat: $(CSRC)/gpupsat_main.cpp gpupsat_b200/libgpsat.so include/gpsat.h
 	$(CXX) -std=c++17 -O2 -Wall -o $@ $< -Lgpupsat_b200 -lgpsat -Wl,-rpath,'$$ORIGIN'

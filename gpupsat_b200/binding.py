@@ -40,7 +40,7 @@ class GpsatStats(C.Structure):
                [("kernel_ms", C.c_double), ("kernel_launches", C.c_int32), ("blocks", C.c_int32),
                 ("warps_per_block", C.c_int32), ("smem_bytes_per_block", C.c_int32), ("state_in_smem", C.c_int32),
                 ("reserved", C.c_int32), ("splits", C.c_int64), ("warp_busy_frac", C.c_double),
-                ("foreign_clauses", C.c_int64)]
+                ("foreign_clauses", C.c_int64), ("steals", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
@@ -102,6 +102,21 @@ def lib():
                                         C.POINTER(i64), C.POINTER(i64)]
     L.gpsat_debug_ctrl.argtypes = [vp, vp]
     L.gpsat_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.gpsat_mesh_export.argtypes = [vp, vp]
+    L.gpsat_mesh_attach_ipc.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32]
+    L.gpsat_mesh_attach_local.argtypes = [C.POINTER(vp), i32, i32, vp]
+    L.gpsat_mesh_detach.argtypes = [vp]
+    L.gpsat_mesh_result_words.argtypes = [vp]
+    L.gpsat_mesh_result_words.restype = i64
+    L.gpsat_mesh_results_pack.argtypes = [vp, vp, i64]
+    L.gpsat_mesh_results_unpack.argtypes = [vp, vp, i64, C.POINTER(i32), C.POINTER(GpsatStats)]
+    L.gpsat_handle_device.argtypes = [vp]
+    L.gpsat_multi_create.argtypes = [C.POINTER(vp), i32, vp, i32, i64, vp, vp, C.POINTER(GpsatOpts)]
+    L.gpsat_multi_n_gpus.argtypes = [vp]
+    L.gpsat_multi_set_cubes.argtypes = [vp, i32, vp, vp]
+    L.gpsat_multi_solve.argtypes = [vp, C.POINTER(i32), vp, C.POINTER(GpsatStats), C.POINTER(i32)]
+    L.gpsat_multi_job_records.argtypes = [vp, vp, i32]
+    L.gpsat_multi_destroy.argtypes = [vp]
     _lib = L
     return L
 
@@ -232,9 +247,16 @@ class Solver:
 
     def set_cubes(self, cubes=None, cube_offsets=None, cube_lits=None):
         """cubes: (n, k) array, or explicit CSR (cube_offsets, cube_lits); None = the single empty cube."""
+        self.empty_shard = False
         if cubes is not None:
             cubes = np.ascontiguousarray(cubes, dtype=np.int32)
             n, k = cubes.shape
+            if n == 0:
+                # an empty shard (more ranks than cubes) is NOT the single empty cube of sequential mode: this handle
+                # has nothing to solve — solve_begin/step/end answer "done, UNSAT" without a launch
+                self.empty_shard = True
+                self.n_cubes = 0
+                return
             cube_offsets = np.arange(0, n * k + 1, max(k, 1), dtype=np.int64) if k else np.zeros(n + 1, dtype=np.int64)
             cube_lits = cubes.reshape(-1)
         if cube_offsets is None:
@@ -282,16 +304,48 @@ class Solver:
     def last_kernel_ms(self):
         return float(lib().gpsat_last_kernel_ms(self.h))
 
-    def job_records(self):
-        rec = np.zeros(self.n_cubes, dtype=RECORD_DTYPE)
-        _check(lib().gpsat_job_records(self.h, _p(rec), self.n_cubes))
+    def job_records(self, n=None):
+        n = self.n_cubes if n is None else n      # a mesh rank holds records of ALL cubes of all ranks (n = n_roots)
+        rec = np.zeros(n, dtype=RECORD_DTYPE)
+        _check(lib().gpsat_job_records(self.h, _p(rec), n))
         return rec
+
+    # --- mesh: several GPUs as one work pool over NVLink peer memory (include/gpsat.h: gpsat_mesh_*) ---
+    def mesh_export(self):
+        buf = np.zeros(64, dtype=np.uint8)
+        _check(lib().gpsat_mesh_export(self.h, _p(buf)))
+        return buf
+
+    def mesh_attach_ipc(self, n_ranks, rank, handles, n_roots, root_first, root_stride, n_local):
+        handles = np.ascontiguousarray(handles, dtype=np.uint8).reshape(-1)
+        assert handles.size == 64 * n_ranks
+        _check(lib().gpsat_mesh_attach_ipc(self.h, n_ranks, rank, _p(handles), n_roots, root_first, root_stride, n_local))
+        self.n_roots = n_roots
+
+    def mesh_detach(self):
+        _check(lib().gpsat_mesh_detach(self.h))
+
+    def mesh_result_words(self):
+        return int(lib().gpsat_mesh_result_words(self.h))
+
+    def mesh_results_pack(self, block):
+        _check(lib().gpsat_mesh_results_pack(self.h, C.c_void_p(block.data_ptr()), block.numel()))
+
+    def mesh_results_unpack(self, block):
+        verdict, st = C.c_int32(UNDEF), GpsatStats()
+        _check(lib().gpsat_mesh_results_unpack(self.h, C.c_void_p(block.data_ptr()), block.numel(), C.byref(verdict),
+                                               C.byref(st)))
+        return verdict.value, st.as_dict()
 
     # --- epoch API (one process per GPU) ---
     def solve_begin(self):
+        if getattr(self, "empty_shard", False):
+            return
         _check(lib().gpsat_solve_begin(self.h))
 
     def solve_step(self, budget_ms=0.0):
+        if getattr(self, "empty_shard", False):
+            return True, UNSAT
         done, verdict = C.c_int32(0), C.c_int32(UNDEF)
         _check(lib().gpsat_solve_step(self.h, float(budget_ms), C.byref(done), C.byref(verdict)))
         return bool(done.value), verdict.value
@@ -300,6 +354,8 @@ class Solver:
         verdict = C.c_int32(UNDEF)
         model = np.zeros(max(self.n_vars, 1), dtype=np.uint8)
         st = GpsatStats()
+        if getattr(self, "empty_shard", False):
+            return UNSAT, model[: self.n_vars], st.as_dict()
         _check(lib().gpsat_solve_end(self.h, C.byref(verdict), _p(model), C.byref(st)))
         return verdict.value, model[: self.n_vars], st.as_dict()
 
@@ -333,6 +389,71 @@ class Solver:
                                            C.byref(imported), C.byref(jobs)))
         return {"sat_rank": sat.value, "all_done": bool(done.value), "any_undef": bool(undef.value),
                 "imported_clauses": imported.value, "jobs_done": jobs.value}
+
+
+def mesh_attach_local(solvers, n_roots, n_local=None):
+    """In-process mesh over `solvers` (rank r = solvers[r]; cube g of the n_roots cubes belongs to rank g mod len)."""
+    arr = (C.c_void_p * len(solvers))(*[s.h for s in solvers])
+    nl = None if n_local is None else np.ascontiguousarray(n_local, dtype=np.int32)
+    _check(lib().gpsat_mesh_attach_local(arr, len(solvers), n_roots, _p(nl)))
+    for s in solvers:
+        s.n_roots = n_roots
+
+
+class MultiSolver:
+    """gpsat_multi_*: N GPUs of this process as one solver (one host thread per GPU, mesh over NVLink peer memory)."""
+
+    def __init__(self, n_vars, offsets, lits, n_gpus=0, devices=None, **opts):
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self.lits = np.ascontiguousarray(lits, dtype=np.int32)
+        self.n_vars = int(n_vars)
+        self.opts = default_opts(**opts)
+        dv = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+        h = C.c_void_p()
+        _check(lib().gpsat_multi_create(C.byref(h), n_gpus, _p(dv), self.n_vars, len(self.offsets) - 1,
+                                        _p(self.offsets), _p(self.lits), C.byref(self.opts)))
+        self.h = h
+        self.n_gpus = lib().gpsat_multi_n_gpus(h)
+        self.n_cubes = 1
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().gpsat_multi_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_cubes(self, cubes):
+        if cubes is None:
+            _check(lib().gpsat_multi_set_cubes(self.h, 0, None, None))
+            self.n_cubes = 1
+            return
+        cubes = np.ascontiguousarray(cubes, dtype=np.int32)
+        n, k = cubes.shape
+        co = np.arange(0, n * k + 1, max(k, 1), dtype=np.int64) if k else np.zeros(n + 1, dtype=np.int64)
+        cl = cubes.reshape(-1)
+        _check(lib().gpsat_multi_set_cubes(self.h, n, _p(co), _p(cl)))
+        self.n_cubes = n
+
+    def solve(self):
+        verdict, backend = C.c_int32(UNDEF), C.c_int32(0)
+        model = np.zeros(max(self.n_vars, 1), dtype=np.uint8)
+        st = GpsatStats()
+        _check(lib().gpsat_multi_solve(self.h, C.byref(verdict), _p(model), C.byref(st), C.byref(backend)))
+        d = st.as_dict()
+        d["reduce_backend"] = "nccl" if backend.value == 1 else "host"
+        return verdict.value, model[: self.n_vars], d
+
+    def job_records(self):
+        rec = np.zeros(self.n_cubes, dtype=RECORD_DTYPE)
+        _check(lib().gpsat_multi_job_records(self.h, _p(rec), self.n_cubes))
+        return rec
 
 
 def solve_cnf(cnf: Cnf, blocks=32, threads=32, strategy=STRATEGY_DISTRIBUTED, sequential=False, **opts):

@@ -71,6 +71,7 @@ struct WarpSolver {
     int *dq_lits, *dq_meta, *dq_ctrl, *root_pending, *dq_hand;
     int hand_words, dq_cap;
     int rel_slot, rel_seq;                 // queue slot this job was popped from (released once its content is consumed)
+    int mesh_ranks;                        // > 1: other GPUs pop from this GPU's ring (system-scope fences / atomics)
     const unsigned long long *t0;          // budgeted steps: jobs park themselves once now > *t0 + budget_ns
     unsigned long long budget_ns;
     long long c_splits;
@@ -1064,12 +1065,17 @@ struct WarpSolver {
     }
 
     // ---- dynamic queue: a bounded multi-producer multi-consumer ring (per-slot sequence numbers, dq_meta[4*slot+2]).
-    // dq_ctrl: [0] tail (push tickets) [1] head (pop tickets) [2] outstanding jobs [3] idle warps [4] splits in flight.
-    // demand = idle warps - queued children - splits in flight: how many more children would find a taker right now.
+    // dq_ctrl words: GPSAT_DQC_* (gpsat_device.h).
+    // demand = idle warps - queued children - splits in flight (+ what the other GPUs of the mesh advertise as their
+    // unmet demand): how many more children would find a taker right now.
     GPSAT_DEV int demand_hint() const
     {
-        return gpsat_ld_volatile(dq_ctrl + 3) - (gpsat_ld_volatile(dq_ctrl + 0) - gpsat_ld_volatile(dq_ctrl + 1)) -
-               gpsat_ld_volatile(dq_ctrl + 4);
+        int d = gpsat_ld_volatile(dq_ctrl + GPSAT_DQC_IDLE) -
+                (gpsat_ld_volatile(dq_ctrl + GPSAT_DQC_TAIL) - gpsat_ld_volatile(dq_ctrl + GPSAT_DQC_HEAD)) -
+                gpsat_ld_volatile(dq_ctrl + GPSAT_DQC_INFLIGHT);
+        GPSAT_NOUNROLL
+        for (int r = 0; r < mesh_ranks; ++r) d += gpsat_ld_volatile(dq_ctrl + GPSAT_DQC_PEER_IDLE + r);
+        return d;
     }
 
     // reserves a slot for writing; returns it (ticket in `ticket`) or -1 when the ring is full
@@ -1085,13 +1091,13 @@ struct WarpSolver {
         }
         LANE0
         {
-            int pos = gpsat_ld_volatile(dq_ctrl + 0);
+            int pos = gpsat_ld_volatile(dq_ctrl + GPSAT_DQC_TAIL);
             GPSAT_NOUNROLL
             for (int tries = 0; tries < 64; ++tries) {
                 const int slot = pos & (dq_cap - 1);
                 const int dif = gpsat_ld_volatile(dq_meta + 4 * slot + 2) - pos;
                 if (dif == 0) {
-                    const int old = gpsat_atomic_cas(dq_ctrl + 0, pos, pos + 1);
+                    const int old = gpsat_atomic_cas(dq_ctrl + GPSAT_DQC_TAIL, pos, pos + 1);
                     if (old == pos) {
                         LV(slot_v) = slot;
                         LV(pos_v) = pos;
@@ -1101,7 +1107,7 @@ struct WarpSolver {
                 } else if (dif < 0) {
                     break;   // full
                 } else {
-                    pos = gpsat_ld_volatile(dq_ctrl + 0);
+                    pos = gpsat_ld_volatile(dq_ctrl + GPSAT_DQC_TAIL);
                 }
             }
         }
@@ -1124,11 +1130,12 @@ struct WarpSolver {
             dq_meta[4 * slot] = root;
             dq_meta[4 * slot + 1] = extra >= 0 ? k + 1 : k;
             gpsat_atomic_add(root_pending + root, 1);
-            gpsat_atomic_add(dq_ctrl + 2, 1);
+            gpsat_atomic_add(dq_ctrl + GPSAT_DQC_CREATED, 1);
         }
         SYNCWARP();
         write_handoff(slot);
-        gpsat_threadfence();
+        if (mesh_ranks > 1) gpsat_threadfence_sys();   // the taker may be a warp of another GPU
+        else gpsat_threadfence();
         LANE0 { ((volatile int *)dq_meta)[4 * slot + 2] = ticket + 1; }   // publish
         SYNCWARP();
     }
@@ -1154,17 +1161,15 @@ struct WarpSolver {
         LANES { LV(claim_v) = 0; }
         LANE0
         {
-            const int mine = gpsat_atomic_add(dq_ctrl + 4, 1) + 1;   // splits in flight, this one included
-            const int d = gpsat_ld_volatile(dq_ctrl + 3) -
-                          (gpsat_ld_volatile(dq_ctrl + 0) - gpsat_ld_volatile(dq_ctrl + 1)) - mine;
-            LV(claim_v) = (split_force || d >= 0) ? 1 : 0;
+            gpsat_atomic_add(dq_ctrl + GPSAT_DQC_INFLIGHT, 1);   // splits in flight, this one included
+            LV(claim_v) = (split_force || demand_hint() >= 0) ? 1 : 0;
         }
         int slot = -1, ticket = 0, p = -1;
         if (SHFL(claim_v, 0)) {
             p = pick_branch();
             if (p >= 0) slot = dq_acquire(ticket);
         }
-        LANE0 { gpsat_atomic_add(dq_ctrl + 4, -1); }   // from here on the child is counted by tail - head
+        LANE0 { gpsat_atomic_add(dq_ctrl + GPSAT_DQC_INFLIGHT, -1); }   // from here on the child is counted by tail - head
         if (slot < 0) return k;                        // no demand, nothing to branch on, or the ring is full
         LANE0 { cube_buf[k] = p; }
         SYNCWARP();
@@ -1245,7 +1250,9 @@ struct WarpSolver {
                 if (v == 2) enqueue(u, GPSAT_REASON_NONE);
             }
         }
-        const bool queued_ok = mode == GPSAT_MODE_SOLVE && dynamic_split;
+        // a cube that may be split or parked works on a private copy (GPSAT_DQ_MAXK words of the state block, and as
+        // many in the parking block); a longer cube runs in place and can neither split nor park
+        const bool queued_ok = mode == GPSAT_MODE_SOLVE && dynamic_split && k < GPSAT_DQ_MAXK;
         const bool may_split = queued_ok && k + 1 < GPSAT_DQ_MAXK;
         int want_split = 0, burst = 0;
         long long last_split_at = 0;
@@ -1420,6 +1427,7 @@ GPSAT_DEV void gpsat_bind(WarpSolver &S, const gpsat_formula_view &F, const gpsa
     S.dq_hand = B.dq_hand;
     S.hand_words = B.hand_words;
     S.dq_cap = B.dq_cap;
+    S.mesh_ranks = B.mesh_ranks > 1 ? B.mesh_ranks : 0;
     S.rel_slot = -1;
     S.rel_seq = 0;
     S.t0 = B.t0;
@@ -1558,31 +1566,58 @@ GPSAT_DEV void gpsat_run_and_record(WarpSolver &S, int root, const int *cube, in
     {
         if (status != GPSAT_JOB_SUSPENDED) {
             gpsat_atomic_add(B.root_pending + job, -1);
-            gpsat_atomic_add(B.dq_ctrl + 2, -1);
+            gpsat_atomic_add(B.dq_ctrl + GPSAT_DQC_CLOSED, 1);
         }
     }
     SYNCWARP();
 }
 
+// Lane-0 code: takes the oldest child off a ring (this GPU's, or — `sys` — one that warps of several GPUs pop from).
+// Returns the pop ticket, or -1 when the ring is empty (or its next child is still being written).
+GPSAT_DEV int gpsat_ring_pop(int *ctrl, int *meta, int cap, bool sys)
+{
+    int pos = gpsat_ld_volatile(ctrl + GPSAT_DQC_HEAD);
+    GPSAT_NOUNROLL
+    for (int tries = 0; tries < 8; ++tries) {
+        const int slot = pos & (cap - 1);
+        const int dif = gpsat_ld_volatile(meta + 4 * slot + 2) - (pos + 1);
+        if (dif == 0) {
+            const int old = sys ? gpsat_atomic_cas_sys(ctrl + GPSAT_DQC_HEAD, pos, pos + 1)
+                                : gpsat_atomic_cas(ctrl + GPSAT_DQC_HEAD, pos, pos + 1);
+            if (old == pos) return pos;
+            pos = old;
+        } else if (dif < 0) {
+            return -1;
+        } else {
+            pos = gpsat_ld_volatile(ctrl + GPSAT_DQC_HEAD);
+        }
+    }
+    return -1;
+}
+
 // The warp's main loop: original cubes from the atomic cursor (≙ JobsQueue::next_job, SATSolver/JobsQueue.cu:10-32),
-// then children of split cubes from the dynamic queue; a warp with nothing to do advertises itself as idle (so that
-// long-running cubes split) and leaves when no job is outstanding, the stop flag is up, or the step budget is spent.
-GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const gpsat_run_buffers &B)
+// then children of split cubes from this GPU's ring, then — mesh — children queued on the other GPUs of the box, read
+// over NVLink peer memory; a warp with nothing to do advertises itself as idle (so that long-running cubes split) and
+// leaves when no job is open anywhere, the stop flag is up, or the step budget is spent.
+GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const gpsat_run_buffers &B, int *stage)
 {
     GPSAT_LANE_DECL_S
-    int is_idle = 0, idle_spins = 0;
+    int is_idle = 0, idle_spins = 0, rot = 0;
     unsigned long long busy_ns = 0;
+    const bool mesh = B.mesh_ranks > 1;
     while (true) {
-        LANEVAR(int, kind_v);   // 0 exit, 1 original cube, 2 queued child, 3 wait, 4 resume the job this warp parked
+        LANEVAR(int, kind_v);   // 0 exit, 1 original cube, 2 queued child, 3 wait, 4 resume the job this warp parked, 5 child of another GPU
         LANEVAR(int, idx_v);
+        LANEVAR(int, peer_v);
         LANES
         {
             LV(kind_v) = 0;
             LV(idx_v) = 0;
+            LV(peer_v) = 0;
         }
         LANE0
         {
-            int kind = 3, idx = 0;
+            int kind = 3, idx = 0, peer = 0;
             if (gpsat_ld_volatile(B.stop_flag)) {
                 kind = 0;
             } else if (B.budget_ns && gpsat_now_ns() > *B.t0 + B.budget_ns) {
@@ -1595,30 +1630,41 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
                     if (idx < B.n_cubes) kind = 1;
                 }
                 if (kind == 3 && P.mode == GPSAT_MODE_SOLVE && P.dynamic_split) {
-                    int pos = gpsat_ld_volatile(B.dq_ctrl + 1);
-                    GPSAT_NOUNROLL
-                    for (int tries = 0; tries < 8; ++tries) {
-                        const int slot = pos & (B.dq_cap - 1);
-                        const int dif = gpsat_ld_volatile(B.dq_meta + 4 * slot + 2) - (pos + 1);
-                        if (dif == 0) {
-                            const int old = gpsat_atomic_cas(B.dq_ctrl + 1, pos, pos + 1);
-                            if (old == pos) {
-                                idx = pos;
-                                kind = 2;
-                                break;
+                    idx = gpsat_ring_pop(B.dq_ctrl, B.dq_meta, B.dq_cap, mesh);
+                    if (idx >= 0) kind = 2;
+                    if (kind == 3 && mesh && stage != nullptr) {
+                        // children advertised by the other GPUs (their communication warps refresh PEER_QUEUE): claim one
+                        // locally first, so that at most as many warps go out over NVLink as there are children to take
+                        GPSAT_NOUNROLL
+                        for (int t = 0; t < B.mesh_ranks - 1 && kind == 3; ++t) {
+                            const int r = (B.mesh_rank + 1 + (rot + t) % (B.mesh_ranks - 1)) % B.mesh_ranks;
+                            if (gpsat_ld_volatile(B.dq_ctrl + GPSAT_DQC_PEER_QUEUE + r) <= 0) continue;
+                            if (gpsat_atomic_add(B.dq_ctrl + GPSAT_DQC_PEER_QUEUE + r, -1) <= 0) continue;
+                            int *rctrl = (int *)(B.mesh_base[r] + B.mesh_off_ctrl);
+                            int *rmeta = (int *)(B.mesh_base[r] + B.mesh_off_meta);
+                            gpsat_atomic_add(B.dq_ctrl + GPSAT_DQC_REMOTE_TRIES, 1);
+                            idx = gpsat_ring_pop(rctrl, rmeta, B.dq_cap, true);
+                            if (idx >= 0) {
+                                kind = 5;
+                                peer = r;
                             }
-                            pos = old;
-                        } else if (dif < 0) {
-                            break;   // empty (or the next child is still being written)
-                        } else {
-                            pos = gpsat_ld_volatile(B.dq_ctrl + 1);
                         }
+                        rot++;
                     }
                 }
-                if (kind == 3 && gpsat_ld_volatile(B.dq_ctrl + 2) <= 0) kind = 0;   // nothing outstanding anywhere
+                if (kind == 3) {   // nothing to take: is anything still open?
+                    if (gpsat_ld_volatile(B.dq_ctrl + GPSAT_DQC_DONE)) {
+                        kind = 0;
+                    } else if (!mesh) {
+                        // one 8-byte snapshot of (created, closed): equal = no open job, and then none can appear
+                        const unsigned long long cc = gpsat_ld_volatile64(B.dq_ctrl + GPSAT_DQC_CREATED);
+                        if ((unsigned)(cc & 0xffffffffull) == (unsigned)(cc >> 32)) kind = 0;
+                    }
+                }
             }
             LV(kind_v) = kind;
             LV(idx_v) = idx;
+            LV(peer_v) = peer;
         }
         const int kind = SHFL(kind_v, 0);
         const int idx = SHFL(idx_v, 0);
@@ -1626,7 +1672,7 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
         if (kind == 3) {
             if (!is_idle && P.dynamic_split) {
                 is_idle = 1;
-                LANE0 { gpsat_atomic_add(B.dq_ctrl + 3, 1); }   // one more idle warp
+                LANE0 { gpsat_atomic_add(B.dq_ctrl + GPSAT_DQC_IDLE, 1); }   // one more idle warp
             }
             // idle warps must not steal issue slots from the busy ones, nor hammer the queue counters in L2 (in the
             // tail of a run thousands of them poll the same sector that the splitting warps update): back off to 32 us
@@ -1637,15 +1683,15 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
         idle_spins = 0;
         if (is_idle) {
             is_idle = 0;
-            LANE0 { gpsat_atomic_add(B.dq_ctrl + 3, -1); }
+            LANE0 { gpsat_atomic_add(B.dq_ctrl + GPSAT_DQC_IDLE, -1); }
         }
         const unsigned long long t_job = gpsat_now_ns();
         if (kind == 4) {
             gpsat_run_and_record(S, S.park[1], S.park + 16, S.park[2], nullptr, P, B, true);
         } else if (kind == 1) {
             const long long c0 = B.cube_offsets[idx], c1 = B.cube_offsets[idx + 1];
-            gpsat_run_and_record(S, idx, B.cube_lits + c0, (int)(c1 - c0), nullptr, P, B);
-        } else {
+            gpsat_run_and_record(S, B.root_first + idx * B.root_stride, B.cube_lits + c0, (int)(c1 - c0), nullptr, P, B);
+        } else if (kind == 2) {
             const int slot = idx & (B.dq_cap - 1);
             gpsat_threadfence();
             const int root = gpsat_ld_cg(B.dq_meta + 4 * slot);
@@ -1654,12 +1700,40 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
             S.rel_slot = slot;
             S.rel_seq = idx + B.dq_cap;   // the ticket that may write this slot next
             gpsat_run_and_record(S, root, B.dq_lits + (long long)slot * GPSAT_DQ_MAXK, len, hand, P, B);
+        } else {
+            // a child queued on GPU `peer`: copy its cube and hand-off block over NVLink into this warp's staging block
+            // (one bulk copy instead of a dependent remote load per imported clause), free the remote slot, run it here.
+            // The job counts as closed on THIS GPU; its record goes into this GPU's arrays (merged at the end).
+            const int peer = SHFL(peer_v, 0);
+            const int slot = idx & (B.dq_cap - 1);
+            int *rmeta = (int *)(B.mesh_base[peer] + B.mesh_off_meta);
+            const int *rlits = (const int *)(B.mesh_base[peer] + B.mesh_off_lits) + (long long)slot * GPSAT_DQ_MAXK;
+            const int *rhand = (const int *)(B.mesh_base[peer] + B.mesh_off_hand) + (long long)slot * B.hand_words;
+            gpsat_threadfence_sys();
+            const int root = gpsat_ld_cg(rmeta + 4 * slot);
+            const int len = gpsat_ld_cg(rmeta + 4 * slot + 1);
+            int used = gpsat_ld_cg(rhand);
+            if (used < 0 || used > B.hand_words - 1 - 2 * S.n_vars) used = 0;
+            LANES
+            {
+                gpsat_copy_cg(stage, rhand, 1 + 2 * S.n_vars + used, lane);
+                gpsat_copy_cg(stage + B.hand_words, rlits, GPSAT_DQ_MAXK, lane);
+            }
+            SYNCWARP();
+            gpsat_threadfence_sys();
+            LANE0
+            {
+                ((volatile int *)rmeta)[4 * slot + 2] = idx + B.dq_cap;   // the remote slot is free again
+                gpsat_atomic_add(B.dq_ctrl + GPSAT_DQC_STEALS, 1);
+            }
+            SYNCWARP();
+            gpsat_run_and_record(S, root, stage + B.hand_words, len, stage, P, B);
         }
         busy_ns += gpsat_now_ns() - t_job;
     }
     LANE0
     {
-        if (is_idle) gpsat_atomic_add(B.dq_ctrl + 3, -1);
+        if (is_idle) gpsat_atomic_add(B.dq_ctrl + GPSAT_DQC_IDLE, -1);
         if (B.busy_ns) gpsat_atomic_add_ll(B.busy_ns, (long long)busy_ns);   // utilisation = busy / (warps x kernel time)
     }
 }

@@ -45,10 +45,11 @@ std::vector<CachedBlock> g_block_cache;
 std::mutex g_block_cache_mutex;
 const size_t kCacheMaxBlocks = 160;
 
-cudaError_t cached_alloc(void **p, size_t bytes, size_t *got)
+cudaError_t cached_alloc(void **p, size_t bytes, size_t *got, int *device)
 {
     int dev = 0;
     cudaGetDevice(&dev);
+    *device = dev;
     bytes = (bytes + 255) / 256 * 256;
     {
         std::lock_guard<std::mutex> lock(g_block_cache_mutex);
@@ -78,17 +79,15 @@ cudaError_t cached_alloc(void **p, size_t bytes, size_t *got)
     return e;
 }
 
-void cached_free(void *p, size_t bytes)
+void cached_free(void *p, size_t bytes, int dev)
 {
     if (!p) return;
-    int dev = 0;
-    cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lock(g_block_cache_mutex);
     if (g_block_cache.size() >= kCacheMaxBlocks) {   // evict the block that has been unused for the longest
-        cudaFree(g_block_cache.front().p);
+        cudaFree(g_block_cache.front().p);           // cudaFree works on a pointer of any device
         g_block_cache.erase(g_block_cache.begin());
     }
-    g_block_cache.push_back({dev, p, bytes});
+    g_block_cache.push_back({dev, p, bytes});        // the device the block was allocated on, not the current one
 }
 
 template <class T>
@@ -96,10 +95,11 @@ struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
     size_t bytes = 0;
+    int device = 0;
     ~DevBuf() { release(); }
     void release()
     {
-        if (p) cached_free(p, bytes);
+        if (p) cached_free(p, bytes, device);
         p = nullptr;
         n = 0;
         bytes = 0;
@@ -110,7 +110,7 @@ struct DevBuf {
         release();
         void *q = nullptr;
         size_t got = 0;
-        cudaError_t e = cached_alloc(&q, std::max<size_t>(count, 1) * sizeof(T), &got);
+        cudaError_t e = cached_alloc(&q, std::max<size_t>(count, 1) * sizeof(T), &got, &device);
         if (e == cudaSuccess) {
             p = (T *)q;
             n = count;
@@ -149,6 +149,7 @@ struct gpsat {
     int sweep_cluster = 0;   // cluster size used by the last occurrence-mode propagation (0 = HBM-bitmap kernel)
     // cubes
     int32_t n_cubes = 0;
+    int32_t cube_base = 0;             // gpsat_propagate: index of the one cube the narrowed job list starts at
     bool cubes_set = false;
     std::vector<int64_t> cube_offsets_h;
     DevBuf<int64_t> cube_offsets;
@@ -161,10 +162,21 @@ struct gpsat {
     DevBuf<int32_t> implied, n_implied;
     DevBuf<int64_t> conflict_clause;
     DevBuf<int32_t> gstate;
-    DevBuf<int32_t> pool, pool_cursor, xpool, xpool_cursor;
-    DevBuf<uint8_t> facts;
-    DevBuf<int32_t> dq_lits, dq_meta, dq_ctrl, root_pending, root_flag, dq_hand, park;
+    DevBuf<int32_t> pool, pool_cursor;
+    // queue region: control block, ring of split-off cubes with their hand-off blocks, foreign pool, facts — ONE
+    // allocation with the same layout on every rank, so that the other GPUs of a mesh can map it (gpsat_mesh_*)
+    DevBuf<char> region;
+    gpsat_mesh_layout ML{};
+    bool region_full = false;          // false: control block only (propagate-only handles)
+    int32_t hand_words = 0;
+    DevBuf<int32_t> root_pending, root_flag, park, stage;
+    // mesh (several GPUs as one work pool)
+    int32_t mesh_ranks = 1, mesh_rank = 0;
+    char *mesh_base[GPSAT_MESH_MAX_RANKS] = {nullptr};
+    int32_t n_roots = 0, root_first = 0, root_stride = 1;   // records / root_* arrays cover all cubes of all ranks
+    bool mesh_zero_local = false;      // this rank owns no root cube (it only takes children of other GPUs)
     std::vector<int32_t> root_pending_h, root_flag_h;
+    int32_t dq_ctrl_h[GPSAT_DQC_WORDS] = {0};   // control block after the last launch
     DevBuf<int32_t> arena;
     // geometry
     gpsat_state_layout Ly{};
@@ -185,24 +197,68 @@ namespace {
 const int64_t kPoolWords = 1 << 22;   // 16 MB shared learnt pool per GPU (and as much for clauses from other GPUs)
 const int64_t kPoolSlots = kPoolWords / GPSAT_POOL_SLOT_WORDS;
 
+// every entry point runs on the handle's device (several handles on different GPUs may live in one process)
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
+// learnt-clause words a split-off cube inherits (plus the level-0 facts, which share the space)
+int32_t hand_clause_words(const gpsat *h)
+{
+    const int32_t w = h->opts.split_hand_words > 0 ? h->opts.split_hand_words : 2048;   // measured best on C2 (DESIGN.md)
+    return std::max(w, 2 * h->D.n_vars + 64);
+}
+
+int32_t *region_i32(gpsat *h, int64_t off) { return (int32_t *)(h->region.p + off); }
+int32_t *dq_ctrl(gpsat *h) { return region_i32(h, h->ML.ctrl); }
+int32_t *xpool(gpsat *h) { return h->region_full ? region_i32(h, h->ML.xpool) : nullptr; }
+int32_t *xpool_cursor(gpsat *h) { return h->region_full ? region_i32(h, h->ML.xcur) : nullptr; }
+uint8_t *facts(gpsat *h) { return h->region_full ? (uint8_t *)(h->region.p + h->ML.facts) : nullptr; }
+
+// The queue region.  full = ring + hand-off blocks + foreign pool + facts (solve runs, exchange); otherwise only the
+// control block.  A full region is never shrunk back, and a handle attached to a mesh keeps its region for life.
+int ensure_region(gpsat *h, bool full)
+{
+    if (h->region.p && (h->region_full || !full)) return GPSAT_OK;
+    if (h->mesh_ranks > 1) {
+        set_error("the queue region of a handle attached to a mesh cannot change");
+        return GPSAT_E_STATE;
+    }
+    gpsat_mesh_layout m;
+    h->hand_words = (1 + 2 * h->D.n_vars + hand_clause_words(h) + 3) / 4 * 4;
+    if (full) gpsat_make_mesh_layout(h->D.n_vars, h->hand_words, GPSAT_DQ_CAP, kPoolWords, &m);
+    else gpsat_make_mesh_layout(0, 0, 0, 0, &m);
+    h->region.release();
+    CU(h->region.ensure((size_t)m.total));
+    h->ML = m;
+    h->region_full = full;
+    CU(cudaMemsetAsync(h->region.p + m.ctrl, 0, GPSAT_DQC_WORDS * 4, h->stream));
+    if (full) {
+        CU(cudaMemsetAsync(h->region.p + m.xcur, 0, 64, h->stream));
+        CU(cudaMemsetAsync(h->region.p + m.xpool, 0, (size_t)kPoolWords * 4, h->stream));
+        CU(cudaMemsetAsync(h->region.p + m.facts, 0, (size_t)std::max(h->D.n_vars, 1), h->stream));
+    }
+    return GPSAT_OK;
+}
+
 int ensure_pools(gpsat *h, bool foreign)
 {
-    if (!h->facts.p) {
-        CU(h->facts.ensure((size_t)std::max(h->D.n_vars, 1)));
-        CU(cudaMemsetAsync(h->facts.p, 0, (size_t)std::max(h->D.n_vars, 1), h->stream));
-    }
     if (!h->pool.p) {
         CU(h->pool.ensure((size_t)kPoolWords));
         CU(h->pool_cursor.ensure(4));
         CU(cudaMemsetAsync(h->pool_cursor.p, 0, 4 * sizeof(int32_t), h->stream));
         CU(cudaMemsetAsync(h->pool.p, 0, (size_t)kPoolWords * sizeof(int32_t), h->stream));
     }
-    if (foreign && !h->xpool.p) {
-        CU(h->xpool.ensure((size_t)kPoolWords));
-        CU(h->xpool_cursor.ensure(4));
-        CU(cudaMemsetAsync(h->xpool_cursor.p, 0, 4 * sizeof(int32_t), h->stream));
-        CU(cudaMemsetAsync(h->xpool.p, 0, (size_t)kPoolWords * sizeof(int32_t), h->stream));
-    }
+    if (foreign || !h->region_full) return ensure_region(h, true);
     return GPSAT_OK;
 }
 
@@ -221,13 +277,6 @@ gpsat_formula_view make_view(gpsat *h)
     F.vsids0 = h->vsids0.p;
     F.val0 = h->val0.p;
     return F;
-}
-
-// learnt-clause words a split-off cube inherits (plus the level-0 facts, which share the space)
-int32_t hand_clause_words(const gpsat *h)
-{
-    const int32_t w = h->opts.split_hand_words > 0 ? h->opts.split_hand_words : 2048;   // measured best on C2 (DESIGN.md)
-    return std::max(w, 2 * h->D.n_vars + 64);
 }
 
 int32_t default_max_learnts(int64_t n_clauses, int32_t refs_cap, int32_t n_vars)
@@ -321,32 +370,34 @@ int plan_geometry(gpsat *h, int mode)
     // it has warps (a shard of a multi-GPU run) still fills all its SMs
     const int64_t takers = (mode == GPSAT_MODE_SOLVE && h->opts.dynamic_split) ? 8 : 1;
     const int64_t need = (takers * (int64_t)std::max(h->n_cubes, 1) + w - 1) / w;
-    if (blocks > need) blocks = (int)need;
+    // a GPU of a mesh also takes children of the other GPUs: it always launches every warp it can hold
+    if (blocks > need && !(h->mesh_ranks > 1 && mode == GPSAT_MODE_SOLVE)) blocks = (int)need;
     h->blocks = std::max(blocks, 1);
     return GPSAT_OK;
 }
 
+int32_t roots_of(const gpsat *h) { return h->mesh_ranks > 1 ? h->n_roots : std::max(h->n_cubes, 1); }
+
 int ensure_run_buffers(gpsat *h, int mode)
 {
     const size_t n_warps = (size_t)h->blocks * h->warps_per_block;
+    const size_t nr = (size_t)roots_of(h);
+    const bool split = mode == GPSAT_MODE_SOLVE && h->opts.dynamic_split;
     CU(h->ctrl.ensure(4));
     CU(h->t0.ensure(2));   // [0] globaltimer stamp of the launch, [1] summed busy time of the warps
     CU(h->model.ensure((size_t)std::max(h->D.n_vars, 1)));
-    CU(h->records.ensure((size_t)std::max(h->n_cubes, 1)));
+    CU(h->records.ensure(nr));
+    // solve runs always get the full region: the exchange / pool calls of an epoch may come at any time afterwards
+    int rc = ensure_region(h, mode == GPSAT_MODE_SOLVE || h->opts.share_learnts || h->mesh_ranks > 1);
+    if (rc != GPSAT_OK) return rc;
     if (h->opts.share_learnts) {   // the pools exist only when clause sharing is on
-        int rc = ensure_pools(h, false);
+        rc = ensure_pools(h, false);
         if (rc != GPSAT_OK) return rc;
     }
-    CU(h->dq_ctrl.ensure(8));
-    CU(h->root_pending.ensure((size_t)std::max(h->n_cubes, 1)));
-    CU(h->root_flag.ensure((size_t)std::max(h->n_cubes, 1)));
-    if (mode == GPSAT_MODE_SOLVE && h->opts.dynamic_split) {
-        CU(h->dq_lits.ensure((size_t)GPSAT_DQ_CAP * GPSAT_DQ_MAXK));
-        CU(h->dq_meta.ensure((size_t)GPSAT_DQ_CAP * 4));
-        CU(h->dq_hand.ensure((size_t)GPSAT_DQ_CAP * (size_t)(1 + 2 * h->D.n_vars + hand_clause_words(h))));
-    }
-    if (mode == GPSAT_MODE_SOLVE && h->opts.dynamic_split)
-        CU(h->park.ensure(n_warps * (size_t)gpsat_park_words(h->D.n_vars)));
+    CU(h->root_pending.ensure(nr));
+    CU(h->root_flag.ensure(nr));
+    if (split) CU(h->park.ensure(n_warps * (size_t)gpsat_park_words(h->D.n_vars)));
+    if (split && h->mesh_ranks > 1) CU(h->stage.ensure(n_warps * (size_t)(h->hand_words + GPSAT_DQ_MAXK)));
     if (!h->state_in_smem) CU(h->gstate.ensure(n_warps * (size_t)h->Ly.total_words));
     if (mode == GPSAT_MODE_SOLVE) CU(h->arena.ensure(n_warps * (size_t)h->arena_words));
     return GPSAT_OK;
@@ -356,11 +407,12 @@ gpsat_run_buffers make_buffers(gpsat *h, int mode, double budget_ms)
 {
     gpsat_run_buffers B;
     std::memset(&B, 0, sizeof(B));
+    const bool split = mode == GPSAT_MODE_SOLVE && h->opts.dynamic_split && h->region_full;
     B.cube_offsets = h->cube_offsets.p;
     B.cube_lits = h->cube_lits.p;
-    B.n_cubes = h->n_cubes;
+    B.n_cubes = h->mesh_zero_local ? 0 : h->n_cubes;
     B.next_job = h->ctrl.p + 0;
-    B.stop_flag = h->ctrl.p + 1;
+    B.stop_flag = dq_ctrl(h) + GPSAT_DQC_STOP;
     B.sat_job = h->ctrl.p + 2;
     B.model = h->model.p;
     B.records = h->records.p;
@@ -369,48 +421,58 @@ gpsat_run_buffers make_buffers(gpsat *h, int mode, double budget_ms)
     B.pool = h->pool.p;
     B.pool_cursor = h->pool_cursor.p;
     B.pool_cap_words = (int32_t)kPoolWords;
-    B.xpool = h->xpool.p;
-    B.xpool_cursor = h->xpool_cursor.p;
-    B.facts = h->facts.p;
+    B.xpool = xpool(h);
+    B.xpool_cursor = xpool_cursor(h);
+    B.facts = (h->opts.share_learnts || h->mesh_ranks > 1) ? facts(h) : nullptr;
     B.state_in_smem = h->state_in_smem;
     B.formula_in_smem = h->formula_in_smem;
     B.formula_smem_words = h->formula_smem_words;
-    B.dq_lits = h->dq_lits.p;
-    B.dq_meta = h->dq_meta.p;
-    B.dq_ctrl = h->dq_ctrl.p;
+    B.dq_ctrl = dq_ctrl(h);
+    B.dq_lits = split ? region_i32(h, h->ML.lits) : nullptr;
+    B.dq_meta = split ? region_i32(h, h->ML.meta) : nullptr;
+    B.dq_hand = split ? region_i32(h, h->ML.hand) : nullptr;
     B.root_pending = h->root_pending.p;
-    B.dq_hand = h->dq_hand.p;
-    B.hand_words = 1 + 2 * h->D.n_vars + hand_clause_words(h);
+    B.hand_words = h->hand_words;
     B.dq_cap = GPSAT_DQ_CAP;
     B.root_flag = h->root_flag.p;
     B.t0 = h->t0.p;
     B.busy_ns = (long long *)(h->t0.p + 1);
-    B.park = mode == GPSAT_MODE_SOLVE ? h->park.p : nullptr;
+    B.park = split ? h->park.p : nullptr;
     B.park_words = gpsat_park_words(h->D.n_vars);
     B.budget_ns = budget_ms > 0 ? (unsigned long long)(budget_ms * 1e6) : 0ull;
+    B.mesh_ranks = mode == GPSAT_MODE_SOLVE ? h->mesh_ranks : 1;
+    B.mesh_rank = h->mesh_rank;
+    for (int r = 0; r < GPSAT_MESH_MAX_RANKS; r++) B.mesh_base[r] = r < h->mesh_ranks ? h->mesh_base[r] : nullptr;
+    B.mesh_off_ctrl = h->ML.ctrl;
+    B.mesh_off_meta = h->ML.meta;
+    B.mesh_off_lits = h->ML.lits;
+    B.mesh_off_hand = h->ML.hand;
+    B.mesh_off_xcur = h->ML.xcur;
+    B.mesh_off_xpool = h->ML.xpool;
+    B.mesh_off_facts = h->ML.facts;
+    B.stage = (split && h->mesh_ranks > 1) ? h->stage.p : nullptr;
+    B.root_first = h->mesh_ranks > 1 ? h->root_first : 0;
+    B.root_stride = h->mesh_ranks > 1 ? h->root_stride : 1;
+    B.n_roots = roots_of(h);
+    B.xpool_cap_slots = (int32_t)kPoolSlots;
+    B.mesh_n_vars = h->D.n_vars;
     return B;
 }
 
+// queue state, root arrays and run counters of a new run: one small kernel + memsets, nothing from pageable memory
 int reset_ctrl(gpsat *h)
 {
-    const size_t nc = (size_t)std::max(h->n_cubes, 1);
-    const int32_t init[4] = {0, 0, -1, 0};
-    const int32_t dq_init[8] = {0, 0, h->n_cubes, 0, 0, 0, 0, 0};   // tail, head, outstanding jobs, idle warps, splits in flight
-    CU(cudaMemcpyAsync(h->ctrl.p, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->dq_ctrl.p, dq_init, sizeof(dq_init), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemsetAsync(h->records.p, 0, nc * sizeof(gpsat_job_record), h->stream));
-    CU(cudaMemsetAsync(h->t0.p, 0, 2 * sizeof(unsigned long long), h->stream));
+    const size_t nr = (size_t)roots_of(h);
+    const int n_local = h->mesh_zero_local ? 0 : h->n_cubes;
+    CU(cudaMemsetAsync(h->records.p, 0, nr * sizeof(gpsat_job_record), h->stream));
     if (h->park.p) CU(cudaMemsetAsync(h->park.p, 0, h->park.n * sizeof(int32_t), h->stream));
-    CU(cudaMemsetAsync(h->root_flag.p, 0, nc * sizeof(int32_t), h->stream));
-    std::vector<int32_t> ones(nc, 1);
-    CU(cudaMemcpyAsync(h->root_pending.p, ones.data(), nc * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    std::vector<int32_t> meta;
-    if (h->dq_meta.p) {   // ring slots start empty: sequence number = slot index
-        meta.assign((size_t)GPSAT_DQ_CAP * 4, 0);
-        for (int i = 0; i < GPSAT_DQ_CAP; i++) meta[4 * (size_t)i + 2] = i;
-        CU(cudaMemcpyAsync(h->dq_meta.p, meta.data(), meta.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    }
-    CU(cudaStreamSynchronize(h->stream));   // `ones` / `meta` are pageable host memory
+    CU(gpsat_kernels::launch_queue_init(dq_ctrl(h), h->region_full ? region_i32(h, h->ML.meta) : nullptr, GPSAT_DQ_CAP,
+                                        h->root_pending.p, h->root_flag.p, (int)nr, h->mesh_ranks > 1 ? h->root_first : 0,
+                                        h->mesh_ranks > 1 ? h->root_stride : 1, n_local, xpool_cursor(h), facts(h),
+                                        h->D.n_vars, h->ctrl.p, h->t0.p, h->stream));
+    if (h->region_full && (h->opts.share_learnts || h->mesh_ranks > 1))   // foreign slots must read "empty" (length 0)
+        CU(cudaMemsetAsync(xpool(h), 0, (size_t)kPoolWords * sizeof(int32_t), h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return GPSAT_OK;
 }
 
@@ -430,15 +492,17 @@ int launch_timed(gpsat *h, const gpsat_solve_params &P, const gpsat_run_buffers 
 
 int fetch_records(gpsat *h)
 {
-    const size_t nc = (size_t)std::max(h->n_cubes, 1);
+    const size_t nc = (size_t)roots_of(h);
     h->records_h.resize(nc);
     h->root_pending_h.resize(nc);
     h->root_flag_h.resize(nc);
     CU(cudaMemcpyAsync(h->records_h.data(), h->records.p, nc * sizeof(gpsat_job_record), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(h->root_pending_h.data(), h->root_pending.p, nc * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(h->root_flag_h.data(), h->root_flag.p, nc * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->dq_ctrl_h, dq_ctrl(h), sizeof(h->dq_ctrl_h), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    // the status of an original cube is decided by all jobs that descend from it (dynamic splitting)
+    // the status of an original cube is decided by all jobs that descend from it (dynamic splitting); on a mesh rank
+    // these are this GPU's contributions only, merged over ranks by gpsat_mesh_results_*
     for (size_t j = 0; j < nc; j++) h->records_h[j].status = gpsat_root_status(h->root_flag_h[j], h->root_pending_h[j]);
     return GPSAT_OK;
 }
@@ -447,9 +511,10 @@ void fill_stats(gpsat *h, gpsat_stats *s)
 {
     if (!s) return;
     std::memset(s, 0, sizeof(*s));
-    s->jobs_total = h->n_cubes;
-    for (int j = 0; j < h->n_cubes; j++) {
-        const gpsat_job_record &r = h->records_h[(size_t)j];
+    const size_t nc = std::min(h->records_h.size(), (size_t)roots_of(h));
+    s->jobs_total = (int64_t)nc;
+    for (size_t j = 0; j < nc; j++) {
+        const gpsat_job_record &r = h->records_h[j];
         // counters include cubes that are still open (parked between steps, or cut short by the stop flag)
         if (r.status == GPSAT_SAT) s->jobs_sat++;
         else if (r.status == GPSAT_UNSAT) s->jobs_unsat++;
@@ -467,9 +532,9 @@ void fill_stats(gpsat *h, gpsat_stats *s)
     }
     int32_t cur[2] = {0, 0}, xcur[2] = {0, 0};
     if (h->pool_cursor.p) cudaMemcpy(cur, h->pool_cursor.p, sizeof(cur), cudaMemcpyDeviceToHost);
-    if (h->xpool_cursor.p) cudaMemcpy(xcur, h->xpool_cursor.p, sizeof(xcur), cudaMemcpyDeviceToHost);
+    if (xpool_cursor(h)) cudaMemcpy(xcur, xpool_cursor(h), sizeof(xcur), cudaMemcpyDeviceToHost);
     s->pool_clauses = cur[1];
-    s->foreign_clauses = xcur[0];
+    s->foreign_clauses = std::min<int64_t>(xcur[0], kPoolSlots);
     unsigned long long busy = 0;
     if (h->t0.p && h->run_mode == GPSAT_MODE_SOLVE) cudaMemcpy(&busy, h->t0.p + 1, sizeof(busy), cudaMemcpyDeviceToHost);
     const double warp_ms = (double)h->blocks * h->warps_per_block * h->kernel_ms;
@@ -480,14 +545,16 @@ void fill_stats(gpsat *h, gpsat_stats *s)
     s->warps_per_block = h->warps_per_block;
     s->smem_bytes_per_block = (int32_t)h->smem_bytes;
     s->state_in_smem = h->state_in_smem;
+    s->steals = h->dq_ctrl_h[GPSAT_DQC_STEALS];
 }
 
 // verdict of the whole run from the per-job records (≙ Results::get_status after parallel_kernel_retrieve_results)
 int32_t run_verdict(gpsat *h, bool *all_done)
 {
     bool any_sat = false, any_open = false, any_undef = false;
-    for (int j = 0; j < h->n_cubes; j++) {
-        const int st = h->records_h[(size_t)j].status;
+    const size_t nc = std::min(h->records_h.size(), (size_t)roots_of(h));
+    for (size_t j = 0; j < nc; j++) {
+        const int st = h->records_h[j].status;
         if (st == GPSAT_SAT) any_sat = true;
         else if (st == GPSAT_UNSAT) continue;
         else if (st == GPSAT_JOB_NOT_RUN || st == GPSAT_JOB_ABORTED) any_open = true;
@@ -659,7 +726,7 @@ int propagate_all_occurrence(gpsat *h, int32_t *status, int32_t *n_implied, int3
         L.tern_state_bytes = h->tern_state_bytes;
         L.l2_prefetch = std::getenv("GPSAT_SWEEP_L2PF") ? std::atoi(std::getenv("GPSAT_SWEEP_L2PF")) : 0;   // measured: 4.39 ms either way
         if (h->cube_lits_sorted.p && !(std::getenv("GPSAT_SWEEP_SORT") && std::atoi(std::getenv("GPSAT_SWEEP_SORT")) == 0))
-            L.cube_lits = h->cube_lits_sorted.p, L.cube_short = h->cube_short.p;
+            L.cube_lits = h->cube_lits_sorted.p, L.cube_short = h->cube_short.p + h->cube_base;   // per-cube info follows the narrowed job list
         // measured on C4: 5.59 ms without, 5.67 ms with the bucket fetched one batch ahead (the lookups, not memory, bound it)
         L.tern_prefetch = std::getenv("GPSAT_SWEEP_PREFETCH") ? std::atoi(std::getenv("GPSAT_SWEEP_PREFETCH")) : 0;
         blocks = h->prop.multiProcessorCount;
@@ -789,19 +856,22 @@ int gpsat_create(gpsat_t **out, int32_t n_vars, int64_t n_clauses, const int64_t
         CUH(cudaGetDevice(&h->device));
     }
     {   // cudaGetDeviceProperties costs milliseconds (and varies): query the three attributes used, once per device
-        static int cached_dev = -1;
-        static cudaDeviceProp cached{};
-        if (cached_dev != h->device) {
+        static std::mutex attr_mutex;
+        static cudaDeviceProp cached[64];
+        static bool have[64] = {false};
+        std::lock_guard<std::mutex> lock(attr_mutex);
+        const int slot = h->device >= 0 && h->device < 64 ? h->device : 63;
+        if (!have[slot] || slot == 63) {
             int v = 0;
             CUH(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, h->device));
-            cached.multiProcessorCount = v;
+            cached[slot].multiProcessorCount = v;
             CUH(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-            cached.sharedMemPerBlockOptin = (size_t)v;
+            cached[slot].sharedMemPerBlockOptin = (size_t)v;
             CUH(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device));
-            cached.sharedMemPerMultiprocessor = (size_t)v;
-            cached_dev = h->device;
+            cached[slot].sharedMemPerMultiprocessor = (size_t)v;
+            have[slot] = true;
         }
-        h->prop = cached;
+        h->prop = cached[slot];
     }
     CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CUH(cudaEventCreate(&h->ev0));
@@ -875,8 +945,10 @@ int gpsat_set_cubes(gpsat_t *h, int32_t n_cubes, const int64_t *cube_offsets, co
         set_error("bad arguments");
         return GPSAT_E_ARG;
     }
+    DeviceGuard guard(h->device);
     h->cube_lits_sorted.release();
     h->cube_short.release();
+    h->mesh_zero_local = false;
     if (n_cubes == 0) {
         h->n_cubes = 1;
         h->cube_offsets_h.assign(2, 0);
@@ -933,6 +1005,7 @@ int gpsat_propagate_all(gpsat_t *h, int32_t *status, int32_t *n_implied, int32_t
         set_error("bad arguments");
         return GPSAT_E_ARG;
     }
+    DeviceGuard guard(h->device);
     int rc = ensure_cubes(h);
     if (rc != GPSAT_OK) return rc;
     if (h->opts.bcp == GPSAT_BCP_OCCURRENCE)
@@ -991,12 +1064,14 @@ int gpsat_propagate(gpsat_t *h, int32_t cube, int32_t *status, int32_t *implied,
     int64_t *saved_off = h->cube_offsets.p;
     h->cube_offsets.p = saved_off + cube;
     h->n_cubes = 1;
+    h->cube_base = cube;
     std::vector<int32_t> imp((size_t)std::max(h->D.n_vars, 1));
     int32_t st = GPSAT_UNDEF, n = 0;
     int64_t cc = -1;
     rc = gpsat_propagate_all(h, &st, &n, implied ? imp.data() : nullptr, h->D.n_vars, &cc, nullptr);
     h->cube_offsets.p = saved_off;
     h->n_cubes = saved_n;
+    h->cube_base = 0;
     if (rc != GPSAT_OK) return rc;
     if (status) *status = st;
     if (n_implied) *n_implied = n;
@@ -1012,6 +1087,7 @@ int gpsat_eval_clauses(gpsat_t *h, int32_t n_assignments, const uint8_t *assignm
         set_error("bad arguments");
         return GPSAT_E_ARG;
     }
+    DeviceGuard guard(h->device);
     const size_t na = (size_t)n_assignments, nv = (size_t)h->D.n_vars, nc = (size_t)h->D.n_clauses;
     if (na == 0 || nc == 0) return GPSAT_OK;
     DevBuf<uint8_t> d_as;
@@ -1033,24 +1109,21 @@ int gpsat_solve_begin(gpsat_t *h)
         set_error("null handle");
         return GPSAT_E_ARG;
     }
+    DeviceGuard guard(h->device);
     int rc = ensure_cubes(h);
     if (rc != GPSAT_OK) return rc;
     rc = plan_geometry(h, GPSAT_MODE_SOLVE);
     if (rc != GPSAT_OK) return rc;
     rc = ensure_run_buffers(h, GPSAT_MODE_SOLVE);
     if (rc != GPSAT_OK) return rc;
-    rc = reset_ctrl(h);
-    if (rc != GPSAT_OK) return rc;
     // every solve starts without shared knowledge: clauses of an earlier run on this handle would be cached work
+    // (reset_ctrl clears the foreign pool, its cursor and the facts)
     if (h->pool.p) {
         CU(cudaMemsetAsync(h->pool_cursor.p, 0, 4 * sizeof(int32_t), h->stream));
         CU(cudaMemsetAsync(h->pool.p, 0, (size_t)kPoolWords * sizeof(int32_t), h->stream));
     }
-    if (h->facts.p) CU(cudaMemsetAsync(h->facts.p, 0, (size_t)std::max(h->D.n_vars, 1), h->stream));
-    if (h->xpool.p) {
-        CU(cudaMemsetAsync(h->xpool_cursor.p, 0, 4 * sizeof(int32_t), h->stream));
-        CU(cudaMemsetAsync(h->xpool.p, 0, (size_t)kPoolWords * sizeof(int32_t), h->stream));
-    }
+    rc = reset_ctrl(h);
+    if (rc != GPSAT_OK) return rc;
     h->kernel_ms = 0;
     h->kernel_launches = 0;
     h->run_mode = GPSAT_MODE_SOLVE;
@@ -1064,6 +1137,7 @@ int gpsat_solve_step(gpsat_t *h, double budget_ms, int32_t *done, int32_t *verdi
         set_error("gpsat_solve_step without gpsat_solve_begin");
         return GPSAT_E_STATE;
     }
+    DeviceGuard guard(h->device);
     gpsat_solve_params P = make_params(h, GPSAT_MODE_SOLVE, 0);
     gpsat_run_buffers B = make_buffers(h, GPSAT_MODE_SOLVE, budget_ms);
     int rc = launch_timed(h, P, B);
@@ -1071,10 +1145,14 @@ int gpsat_solve_step(gpsat_t *h, double budget_ms, int32_t *done, int32_t *verdi
     rc = fetch_records(h);
     if (rc != GPSAT_OK) return rc;
     bool all_done = false;
-    const int32_t v = run_verdict(h, &all_done);
-    int32_t ctrl[3] = {0, 0, -1};
-    CU(cudaMemcpy(ctrl, h->ctrl.p, sizeof(ctrl), cudaMemcpyDeviceToHost));
-    const bool stopped = ctrl[1] != 0;
+    int32_t v = run_verdict(h, &all_done);
+    const bool stopped = h->dq_ctrl_h[GPSAT_DQC_STOP] != 0;
+    if (h->mesh_ranks > 1) {
+        // this rank sees only its own contributions: "done" is the mesh-wide termination flag of the communication warp
+        // (or the stop flag), the verdict is decided by gpsat_mesh_results_* / gpsat_multi_solve over all ranks
+        all_done = h->dq_ctrl_h[GPSAT_DQC_DONE] != 0;
+        if (v != GPSAT_SAT) v = GPSAT_UNDEF;
+    }
     if (done) *done = (all_done || stopped || (v == GPSAT_SAT && h->opts.stop_on_sat)) ? 1 : 0;
     if (verdict) *verdict = v;
     return GPSAT_OK;
@@ -1086,8 +1164,9 @@ int gpsat_solve_end(gpsat_t *h, int32_t *verdict, uint8_t *model, gpsat_stats *s
         set_error("gpsat_solve_end without gpsat_solve_begin");
         return GPSAT_E_STATE;
     }
+    DeviceGuard guard(h->device);
     h->solving = false;
-    if (h->records_h.size() < (size_t)h->n_cubes) {
+    if (h->records_h.size() < (size_t)roots_of(h)) {
         int rc = fetch_records(h);
         if (rc != GPSAT_OK) return rc;
     }
@@ -1114,12 +1193,13 @@ int gpsat_solve(gpsat_t *h, int32_t *verdict, uint8_t *model, gpsat_stats *stats
 
 int gpsat_request_stop(gpsat_t *h)
 {
-    if (!h || !h->ctrl.p) {
+    if (!h || !h->region.p) {
         set_error("no run in progress");
         return GPSAT_E_STATE;
     }
+    DeviceGuard guard(h->device);
     const int32_t two = 2;
-    CU(cudaMemcpy(h->ctrl.p + 1, &two, sizeof(two), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dq_ctrl(h) + GPSAT_DQC_STOP, &two, sizeof(two), cudaMemcpyHostToDevice));
     return GPSAT_OK;
 }
 
@@ -1131,11 +1211,12 @@ int gpsat_job_records(gpsat_t *h, gpsat_job_record *records, int32_t cap)
         set_error("bad arguments");
         return GPSAT_E_ARG;
     }
-    if (cap < h->n_cubes || h->records_h.size() < (size_t)h->n_cubes) {
+    const int32_t nr = roots_of(h);
+    if (cap < nr || h->records_h.size() < (size_t)nr) {
         set_error("record buffer too small or no run yet");
         return GPSAT_E_CAPACITY;
     }
-    std::memcpy(records, h->records_h.data(), (size_t)h->n_cubes * sizeof(gpsat_job_record));
+    std::memcpy(records, h->records_h.data(), (size_t)nr * sizeof(gpsat_job_record));
     return GPSAT_OK;
 }
 
@@ -1145,6 +1226,7 @@ int gpsat_pool_export(gpsat_t *h, int32_t *buf, int64_t cap_words, int64_t *n_wo
         set_error("bad arguments");
         return GPSAT_E_ARG;
     }
+    DeviceGuard guard(h->device);
     *n_words = 0;
     if (!h->pool.p) return GPSAT_OK;
     int32_t cur[4] = {0, 0, 0, 0};
@@ -1178,6 +1260,7 @@ int gpsat_pool_import(gpsat_t *h, const int32_t *buf, int64_t n_words)
         set_error("bad arguments");
         return GPSAT_E_ARG;
     }
+    DeviceGuard guard(h->device);
     if (n_words == 0) return GPSAT_OK;
     int rc = ensure_pools(h, true);
     if (rc != GPSAT_OK) return rc;
@@ -1196,7 +1279,7 @@ int gpsat_pool_import(gpsat_t *h, const int32_t *buf, int64_t n_words)
             }
         if (len == 1) {
             const uint8_t f = (uint8_t)(1 + (buf[at + 1] & 1));
-            CU(cudaMemcpy(h->facts.p + (buf[at + 1] >> 1), &f, 1, cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(facts(h) + (buf[at + 1] >> 1), &f, 1, cudaMemcpyHostToDevice));
         }
         if (len < GPSAT_POOL_SLOT_WORDS) {   // longer clauses do not fit a slot: optional knowledge, dropped
             const size_t o = slots.size();
@@ -1206,14 +1289,14 @@ int gpsat_pool_import(gpsat_t *h, const int32_t *buf, int64_t n_words)
         at += 1 + len;
     }
     int32_t cur[4] = {0, 0, 0, 0};
-    CU(cudaMemcpy(cur, h->xpool_cursor.p, sizeof(cur), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(cur, xpool_cursor(h), sizeof(cur), cudaMemcpyDeviceToHost));
     const int64_t n_slots = (int64_t)slots.size() / GPSAT_POOL_SLOT_WORDS;
     if (n_slots == 0 || cur[0] + n_slots > kPoolSlots) return GPSAT_OK;   // pool full: foreign clauses are optional
-    CU(cudaMemcpy(h->xpool.p + (int64_t)cur[0] * GPSAT_POOL_SLOT_WORDS, slots.data(), slots.size() * sizeof(int32_t),
+    CU(cudaMemcpy(xpool(h) + (int64_t)cur[0] * GPSAT_POOL_SLOT_WORDS, slots.data(), slots.size() * sizeof(int32_t),
                   cudaMemcpyHostToDevice));
     cur[0] += (int32_t)n_slots;
     cur[1] += (int32_t)n_slots;
-    CU(cudaMemcpy(h->xpool_cursor.p, cur, sizeof(cur), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(xpool_cursor(h), cur, sizeof(cur), cudaMemcpyHostToDevice));
     return GPSAT_OK;
 }
 
@@ -1228,10 +1311,11 @@ int gpsat_exchange_pack(gpsat_t *h, void *dev_block, int64_t block_words, int32_
         set_error("bad arguments");
         return GPSAT_E_ARG;
     }
+    DeviceGuard guard(h->device);
     int rc = ensure_pools(h, true);
     if (rc != GPSAT_OK) return rc;
     int64_t jobs_done = 0;
-    for (size_t j = 0; j < h->records_h.size() && j < (size_t)h->n_cubes; j++) {
+    for (size_t j = 0; j < h->records_h.size() && j < (size_t)roots_of(h); j++) {
         const int st = h->records_h[j].status;
         jobs_done += (st == GPSAT_SAT || st == GPSAT_UNSAT || st == GPSAT_UNDEF) ? 1 : 0;
     }
@@ -1250,10 +1334,11 @@ int gpsat_exchange_unpack(gpsat_t *h, const void *dev_blocks, int32_t n_ranks, i
         set_error("bad arguments");
         return GPSAT_E_ARG;
     }
+    DeviceGuard guard(h->device);
     int rc = ensure_pools(h, true);
     if (rc != GPSAT_OK) return rc;
-    CU(gpsat_kernels::launch_xchg_unpack((const int *)dev_blocks, n_ranks, my_rank, (int)block_words, h->xpool.p,
-                                         h->xpool_cursor.p, (int)kPoolSlots, h->facts.p, h->D.n_vars, h->stream));
+    CU(gpsat_kernels::launch_xchg_unpack((const int *)dev_blocks, n_ranks, my_rank, (int)block_words, xpool(h),
+                                         xpool_cursor(h), (int)kPoolSlots, facts(h), h->D.n_vars, h->stream));
     std::vector<int32_t> hdr((size_t)n_ranks * GPSAT_XCHG_HEADER_WORDS);
     CU(cudaMemcpy2DAsync(hdr.data(), GPSAT_XCHG_HEADER_WORDS * sizeof(int32_t), dev_blocks,
                          (size_t)block_words * sizeof(int32_t), GPSAT_XCHG_HEADER_WORDS * sizeof(int32_t), (size_t)n_ranks,
@@ -1283,13 +1368,26 @@ int gpsat_exchange_unpack(gpsat_t *h, const void *dev_blocks, int32_t n_ranks, i
 
 int gpsat_debug_ctrl(gpsat_t *h, int32_t *out16)
 {
-    if (!h || !out16 || !h->ctrl.p || !h->dq_ctrl.p) {
+    if (!h || !out16 || !h->ctrl.p || !h->region.p) {
         set_error("no run buffers");
         return GPSAT_E_STATE;
     }
+    DeviceGuard guard(h->device);
     // cudaMemcpy on the legacy stream does not wait for the handle's non-blocking stream: usable while a kernel runs
     CU(cudaMemcpy(out16, h->ctrl.p, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(out16 + 4, h->dq_ctrl.p, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    {   // [4] tail [5] head [6] open jobs [7] idle warps [8] splits in flight [9] done [10] steals [11] stop flag
+        int32_t c[GPSAT_DQC_WORDS];
+        CU(cudaMemcpy(c, dq_ctrl(h), sizeof(c), cudaMemcpyDeviceToHost));
+        out16[4] = c[GPSAT_DQC_TAIL];
+        out16[5] = c[GPSAT_DQC_HEAD];
+        out16[6] = c[GPSAT_DQC_CREATED] - c[GPSAT_DQC_CLOSED];
+        out16[7] = c[GPSAT_DQC_IDLE];
+        out16[8] = c[GPSAT_DQC_INFLIGHT];
+        out16[9] = c[GPSAT_DQC_DONE];
+        out16[10] = c[GPSAT_DQC_STEALS];
+        out16[11] = c[GPSAT_DQC_STOP];
+        out16[1] = c[GPSAT_DQC_STOP];
+    }
     unsigned long long t[2] = {0, 0};
     CU(cudaMemcpy(t, h->t0.p, sizeof(t), cudaMemcpyDeviceToHost));
     out16[12] = (int32_t)(t[0] & 0x7fffffff);
@@ -1307,9 +1405,223 @@ int gpsat_device_ptrs(gpsat_t *h, void **pool_words, void **pool_cursor, void **
     }
     if (pool_words) *pool_words = h->pool.p;
     if (pool_cursor) *pool_cursor = h->pool_cursor.p;
-    if (stop_flag) *stop_flag = h->ctrl.p ? (void *)(h->ctrl.p + 1) : nullptr;
+    if (stop_flag) *stop_flag = h->region.p ? (void *)(dq_ctrl(h) + GPSAT_DQC_STOP) : nullptr;
     if (stream) *stream = (void *)h->stream;
     return GPSAT_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Mesh: the GPUs of one box as ONE work pool over NVLink peer memory (no reference equivalent: the reference is
+// single-GPU).  Every rank maps the queue regions of the others; the communication warp inside the
+// solve kernel (kernels.cu: gpsat_comm_loop) and the stealing path of the warp loop do the rest.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct IpcMapping {
+    unsigned char handle[64];
+    void *p;
+};
+std::vector<IpcMapping> g_ipc_open;   // peer regions stay mapped for the life of the process (regions are recycled
+std::mutex g_ipc_mutex;               // through the block cache, so the same few handles come back every solve)
+
+int mesh_prepare(gpsat *h)
+{
+    if (h->opts.bcp != GPSAT_BCP_WATCHED || !h->opts.dynamic_split) {
+        set_error("a mesh needs the watched-literal solver with dynamic_split = 1");
+        return GPSAT_E_ARG;
+    }
+    if (h->mesh_ranks > 1) return GPSAT_OK;
+    return ensure_region(h, true);
+}
+
+int mesh_set(gpsat *h, int32_t n_ranks, int32_t rank, char *const *bases, int32_t n_roots, int32_t root_first,
+             int32_t root_stride, int32_t n_local)
+{
+    if (n_ranks < 1 || n_ranks > GPSAT_MESH_MAX_RANKS || rank < 0 || rank >= n_ranks || n_roots < 1 || root_stride < 1 ||
+        n_local < 0 || (n_local > 0 && (int64_t)root_first + (int64_t)(n_local - 1) * root_stride >= n_roots)) {
+        set_error("bad mesh arguments");
+        return GPSAT_E_ARG;
+    }
+    if (n_local > 0 && (!h->cubes_set || h->n_cubes != n_local)) {
+        set_error("mesh: n_local differs from the cubes set on this handle");
+        return GPSAT_E_STATE;
+    }
+    h->mesh_ranks = n_ranks;
+    h->mesh_rank = rank;
+    for (int r = 0; r < GPSAT_MESH_MAX_RANKS; r++) h->mesh_base[r] = r < n_ranks ? bases[r] : nullptr;
+    h->mesh_base[rank] = h->region.p;
+    h->n_roots = n_roots;
+    h->root_first = root_first;
+    h->root_stride = root_stride;
+    h->mesh_zero_local = n_local == 0;
+    if (n_local == 0) {
+        h->n_cubes = 1;   // the job list stays the default empty cube, but the kernel is told that this rank owns none
+        h->cube_offsets_h.assign(2, 0);
+        CU(h->cube_offsets.upload(h->cube_offsets_h.data(), h->cube_offsets_h.size(), h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        h->cubes_set = true;
+    }
+    h->records_h.clear();
+    return GPSAT_OK;
+}
+}  // namespace
+
+int gpsat_mesh_export(gpsat_t *h, void *ipc_handle)
+{
+    if (!h || !ipc_handle) {
+        set_error("bad arguments");
+        return GPSAT_E_ARG;
+    }
+    DeviceGuard guard(h->device);
+    int rc = mesh_prepare(h);
+    if (rc != GPSAT_OK) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == GPSAT_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    cudaIpcMemHandle_t mh;
+    CU(cudaIpcGetMemHandle(&mh, h->region.p));
+    std::memcpy(ipc_handle, &mh, sizeof(mh));
+    return GPSAT_OK;
+}
+
+int gpsat_mesh_attach_ipc(gpsat_t *h, int32_t n_ranks, int32_t rank, const void *ipc_handles, int32_t n_roots,
+                          int32_t root_first, int32_t root_stride, int32_t n_local)
+{
+    if (!h || !ipc_handles || n_ranks < 1 || n_ranks > GPSAT_MESH_MAX_RANKS || rank < 0 || rank >= n_ranks) {
+        set_error("bad arguments");
+        return GPSAT_E_ARG;
+    }
+    DeviceGuard guard(h->device);
+    int rc = mesh_prepare(h);
+    if (rc != GPSAT_OK) return rc;
+    char *bases[GPSAT_MESH_MAX_RANKS] = {nullptr};
+    for (int r = 0; r < n_ranks; r++) {
+        if (r == rank) continue;
+        const unsigned char *hb = (const unsigned char *)ipc_handles + (size_t)r * GPSAT_IPC_HANDLE_BYTES;
+        std::lock_guard<std::mutex> lock(g_ipc_mutex);
+        void *p = nullptr;
+        for (const auto &m : g_ipc_open)
+            if (std::memcmp(m.handle, hb, GPSAT_IPC_HANDLE_BYTES) == 0) p = m.p;
+        if (!p) {
+            cudaIpcMemHandle_t mh;
+            std::memcpy(&mh, hb, sizeof(mh));
+            CU(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+            IpcMapping m;
+            std::memcpy(m.handle, hb, GPSAT_IPC_HANDLE_BYTES);
+            m.p = p;
+            g_ipc_open.push_back(m);
+        }
+        bases[r] = (char *)p;
+    }
+    return mesh_set(h, n_ranks, rank, bases, n_roots, root_first, root_stride, n_local);
+}
+
+int gpsat_mesh_attach_local(gpsat_t *const *handles, int32_t n_ranks, int32_t n_roots, const int32_t *n_local)
+{
+    if (!handles || n_ranks < 1 || n_ranks > GPSAT_MESH_MAX_RANKS) {
+        set_error("bad arguments");
+        return GPSAT_E_ARG;
+    }
+    char *bases[GPSAT_MESH_MAX_RANKS] = {nullptr};
+    for (int r = 0; r < n_ranks; r++) {
+        if (!handles[r]) {
+            set_error("null handle");
+            return GPSAT_E_ARG;
+        }
+        DeviceGuard guard(handles[r]->device);
+        int rc = mesh_prepare(handles[r]);
+        if (rc != GPSAT_OK) return rc;
+        if (handles[r]->ML.total != handles[0]->ML.total) {
+            set_error("mesh: the handles were created for different formulas or options");
+            return GPSAT_E_ARG;
+        }
+        bases[r] = handles[r]->region.p;
+    }
+    for (int r = 0; r < n_ranks; r++) {
+        DeviceGuard guard(handles[r]->device);
+        for (int q = 0; q < n_ranks; q++) {
+            if (handles[q]->device == handles[r]->device) continue;
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, handles[r]->device, handles[q]->device));
+            if (!can) {
+                set_error("mesh: GPU " + std::to_string(handles[r]->device) + " cannot access GPU " +
+                          std::to_string(handles[q]->device) + " as a peer");
+                return GPSAT_E_CUDA;
+            }
+            cudaError_t e = cudaDeviceEnablePeerAccess(handles[q]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+            cudaGetLastError();
+        }
+        // shards: interleaved (cube g -> rank g mod N), or — explicit sizes — contiguous ranges in rank order
+        int32_t nl = (n_roots - r + n_ranks - 1) / n_ranks, first = r, stride = n_ranks;
+        if (n_local) {
+            nl = n_local[r];
+            stride = 1;
+            first = 0;
+            for (int q = 0; q < r; q++) first += n_local[q];
+        }
+        if (nl < 0) nl = 0;
+        int rc = mesh_set(handles[r], n_ranks, r, bases, n_roots, nl > 0 ? first : 0, stride, nl);
+        if (rc != GPSAT_OK) return rc;
+    }
+    return GPSAT_OK;
+}
+
+int gpsat_mesh_detach(gpsat_t *h)
+{
+    if (!h) {
+        set_error("null handle");
+        return GPSAT_E_ARG;
+    }
+    h->mesh_ranks = 1;
+    h->mesh_rank = 0;
+    h->mesh_zero_local = false;
+    h->n_roots = 0;
+    h->root_first = 0;
+    h->root_stride = 1;
+    h->records_h.clear();
+    return GPSAT_OK;
+}
+
+// result block of a mesh rank: [root_flag n_roots][root_pending n_roots][records n_roots x 20 words]
+int64_t gpsat_mesh_result_words(gpsat_t *h) { return h ? (int64_t)roots_of(h) * (2 + (int64_t)(sizeof(gpsat_job_record) / 4)) : 0; }
+
+int gpsat_mesh_results_pack(gpsat_t *h, void *dev_block, int64_t words)
+{
+    if (!h || !dev_block || words < gpsat_mesh_result_words(h) || !h->records.p) {
+        set_error("bad arguments");
+        return GPSAT_E_ARG;
+    }
+    DeviceGuard guard(h->device);
+    const size_t nr = (size_t)roots_of(h);
+    int32_t *b = (int32_t *)dev_block;
+    CU(cudaMemcpyAsync(b, h->root_flag.p, nr * 4, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(b + nr, h->root_pending.p, nr * 4, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(b + 2 * nr, h->records.p, nr * sizeof(gpsat_job_record), cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return GPSAT_OK;
+}
+
+int gpsat_mesh_results_unpack(gpsat_t *h, const void *dev_block, int64_t words, int32_t *verdict, gpsat_stats *stats)
+{
+    if (!h || !dev_block || words < gpsat_mesh_result_words(h)) {
+        set_error("bad arguments");
+        return GPSAT_E_ARG;
+    }
+    DeviceGuard guard(h->device);
+    const size_t nr = (size_t)roots_of(h);
+    const int32_t *b = (const int32_t *)dev_block;
+    h->records_h.resize(nr);
+    h->root_pending_h.resize(nr);
+    h->root_flag_h.resize(nr);
+    CU(cudaMemcpyAsync(h->root_flag_h.data(), b, nr * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->root_pending_h.data(), b + nr, nr * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->records_h.data(), b + 2 * nr, nr * sizeof(gpsat_job_record), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (size_t j = 0; j < nr; j++) h->records_h[j].status = gpsat_root_status(h->root_flag_h[j], h->root_pending_h[j]);
+    if (verdict) *verdict = run_verdict(h, nullptr);
+    fill_stats(h, stats);
+    return GPSAT_OK;
+}
+
+int gpsat_handle_device(gpsat_t *h) { return h ? h->device : -1; }
 
 }  // extern "C"

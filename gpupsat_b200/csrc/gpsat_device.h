@@ -33,6 +33,24 @@
 #define GPSAT_POOL_SLOT_WORDS 16
 #define GPSAT_XCHG_HEADER_WORDS 8
 #define GPSAT_XCHG_MAGIC 0x47505358
+// Queue control block (dq_ctrl): word indices.  Every group sits on its own 128-byte line so that the ring tickets,
+// the job accounting and the words other GPUs write do not share a sector.
+#define GPSAT_DQC_TAIL 0          // push tickets
+#define GPSAT_DQC_HEAD 1          // pop tickets
+#define GPSAT_DQC_CREATED 32      // jobs created on this GPU: the root cubes it owns + the children it queued (monotonic)
+#define GPSAT_DQC_CLOSED 33       // jobs closed on this GPU, wherever they were created (monotonic)
+#define GPSAT_DQC_IDLE 64         // warps of this GPU with nothing to do
+#define GPSAT_DQC_INFLIGHT 65     // splits being prepared
+#define GPSAT_DQC_DONE 66         // set once every rank's closed == created (mesh: by the communication warp)
+#define GPSAT_DQC_STEALS 67       // children this GPU took from the rings of other GPUs
+#define GPSAT_DQC_STOP 68         // early-termination flag: 0 run, 1 SAT found, 2 external stop (≙ managed *state, main.cu:185)
+#define GPSAT_DQC_PUSHED 69       // pool slots already pushed to the peers (communication warp)
+#define GPSAT_DQC_REMOTE_TRIES 70 // remote pop attempts (diagnostics)
+#define GPSAT_DQC_PEER_QUEUE 96   // [GPSAT_MESH_MAX_RANKS] children queued on rank r, written by r's communication warp
+#define GPSAT_DQC_PEER_IDLE 128   // [GPSAT_MESH_MAX_RANKS] unmet demand of rank r (idle warps - queued children), its share for us
+#define GPSAT_DQC_WORDS 160
+#define GPSAT_MESH_MAX_RANKS 8
+
 // per-root outcome flags, combined with atomicMax (higher wins)
 #define GPSAT_FLAG_UNSAT 1
 #define GPSAT_FLAG_ABORTED 2
@@ -109,7 +127,7 @@ struct gpsat_run_buffers {
     // dynamic splitting: children of split cubes are queued here and popped by idle warps
     int32_t *dq_lits;              // dq_cap * GPSAT_DQ_MAXK
     int32_t *dq_meta;              // dq_cap * 4 : (root cube, length, slot sequence number, -); sequence starts at the slot index
-    int32_t *dq_ctrl;              // [0] tail (push tickets) [1] head (pop tickets) [2] outstanding jobs [3] idle warps [4] splits in flight
+    int32_t *dq_ctrl;              // GPSAT_DQC_* words
     int32_t *dq_hand;              // dq_cap * hand_words : per queued cube [n][vs 2n][records] (non-null when dynamic_split)
     int32_t hand_words;
     int32_t dq_cap;                // ring slots (power of two)
@@ -120,7 +138,43 @@ struct gpsat_run_buffers {
     long long *busy_ns;               // sum over warps of the time spent inside jobs (may be null)
     int32_t *park;                    // n_warps * park_words: per-warp parking blocks of budgeted steps (may be null)
     int32_t park_words;
+    // ---- mesh: the GPUs of one box as one work pool over NVLink peer memory (no reference equivalent).
+    // Every rank's queue region (control block, ring, hand-off blocks, foreign pool, facts) has the same layout; rank
+    // r's region starts at mesh_base[r] (own rank: the local pointers above point into it).  mesh_ranks <= 1: off.
+    int32_t mesh_ranks, mesh_rank;
+    char *mesh_base[GPSAT_MESH_MAX_RANKS];
+    int64_t mesh_off_ctrl, mesh_off_meta, mesh_off_lits, mesh_off_hand, mesh_off_xcur, mesh_off_xpool, mesh_off_facts;
+    int32_t *stage;                   // n_warps * hand_words: local copy of a hand-off block popped from another GPU
+    int32_t root_first, root_stride;  // global index of local cube i = root_first + i * root_stride (records / root_* arrays)
+    int32_t n_roots;                  // entries of records / root_pending / root_flag (all cubes of all ranks)
+    int32_t xpool_cap_slots;
+    int32_t mesh_n_vars;
 };
+
+// Layout of one rank's mesh region (bytes, every part 256-byte aligned): identical on every rank because it depends
+// only on (n_vars, hand_words, ring capacity, pool size).
+struct gpsat_mesh_layout {
+    int64_t ctrl, meta, lits, hand, xcur, xpool, facts, total;
+};
+static inline void gpsat_make_mesh_layout(int32_t n_vars, int32_t hand_words, int32_t dq_cap, int64_t pool_words,
+                                          gpsat_mesh_layout *m)
+{
+    int64_t at = 0;
+#define GPSAT_MTAKE(field, bytes)                 \
+    do {                                          \
+        m->field = at;                            \
+        at += (((int64_t)(bytes)) + 255) / 256 * 256; \
+    } while (0)
+    GPSAT_MTAKE(ctrl, GPSAT_DQC_WORDS * 4);
+    GPSAT_MTAKE(meta, (int64_t)dq_cap * 4 * 4);
+    GPSAT_MTAKE(lits, (int64_t)dq_cap * GPSAT_DQ_MAXK * 4);
+    GPSAT_MTAKE(hand, (int64_t)dq_cap * hand_words * 4);
+    GPSAT_MTAKE(xcur, 64);
+    GPSAT_MTAKE(xpool, pool_words * 4);
+    GPSAT_MTAKE(facts, n_vars > 0 ? n_vars : 1);
+#undef GPSAT_MTAKE
+    m->total = at;
+}
 
 // per-warp state block: word offsets of each array (every array starts on a 16-byte boundary)
 static inline void gpsat_make_layout(int32_t n_vars, int64_t n_lits, gpsat_state_layout *ly)

@@ -24,6 +24,163 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 
 __global__ void gpsat_stamp_kernel(unsigned long long *t0) { *t0 = globaltimer_ns(); }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Communication warp (mesh runs; no reference equivalent — the reference is single-GPU).
+// One warp per GPU lives inside the persistent solve kernel and does, over NVLink peer memory, what would otherwise
+// need the kernel to end and the host to run a collective:
+//   * advertises this GPU's queued children (PEER_QUEUE) and its unmet demand (PEER_IDLE) in the control block of
+//     every other GPU — idle warps there steal the children, busy cubes there split for the demand;
+//   * pushes the learnt clauses this GPU's jobs published since the last round into the foreign pool of every other
+//     GPU (the in-kernel form of the per-epoch all-gather: a 64-byte slot per clause, length written last) and learnt
+//     units into their `facts`;
+//   * forwards the early-termination flag (≙ managed *state, SATSolver/main.cu:185,266);
+//   * detects global termination: sum over ranks of `closed`, read BEFORE the sum of `created`; both counters only
+//     grow and closed <= created at every instant, so equal sums mean that no job was open at the moment the last
+//     `closed` was read — and then none can be created any more.
+// ---------------------------------------------------------------------------------------------------------------
+// what the communication warp needs of the kernel parameters, passed BY VALUE: handing the parameter structs to a
+// non-inlined function by reference would make the compiler keep an addressable copy of them in local memory for
+// every warp of the kernel
+struct CommArgs {
+    int mesh_ranks, mesh_rank, share_learnts, pool_cap_words, xpool_cap_slots, mesh_n_vars;
+    int *dq_ctrl;
+    const int *pool;
+    const int *pool_cursor;
+    const unsigned long long *t0;
+    unsigned long long budget_ns;
+    char *mesh_base[GPSAT_MESH_MAX_RANKS];
+    long long mesh_off_ctrl, mesh_off_xcur, mesh_off_xpool, mesh_off_facts;
+};
+
+__device__ __noinline__ void gpsat_comm_loop(const CommArgs B)
+{
+    const struct { int share_learnts; } P = {B.share_learnts};
+    const int lane = (int)(threadIdx.x & 31);
+    const int R = B.mesh_ranks, me = B.mesh_rank;
+    int *ctrl = B.dq_ctrl;
+    const bool peer_lane = lane < R && lane != me;
+    int *pctrl = peer_lane ? (int *)(B.mesh_base[lane] + B.mesh_off_ctrl) : ctrl;
+    const int n_workers = (int)(gridDim.x * (blockDim.x >> 5)) - 1;
+    const int pool_slots = B.pool_cap_words / GPSAT_POOL_SLOT_WORDS;
+    int pushed = *(volatile int *)(ctrl + GPSAT_DQC_PUSHED);
+    unsigned spins = 0;
+    while (true) {
+        const int stop = *(volatile int *)(ctrl + GPSAT_DQC_STOP);
+        if (stop) {   // a model was found here, or the host / another GPU asked to stop: tell everybody, leave
+            if (peer_lane && *(volatile int *)(pctrl + GPSAT_DQC_STOP) == 0) *(volatile int *)(pctrl + GPSAT_DQC_STOP) = 2;
+            break;
+        }
+        if (B.budget_ns && globaltimer_ns() > *B.t0 + B.budget_ns) break;
+        const int idle = *(volatile int *)(ctrl + GPSAT_DQC_IDLE);
+        const int queued = *(volatile int *)(ctrl + GPSAT_DQC_TAIL) - *(volatile int *)(ctrl + GPSAT_DQC_HEAD);
+        const int inflight = *(volatile int *)(ctrl + GPSAT_DQC_INFLIGHT);
+        if (peer_lane) {
+            int want = idle - queued - inflight;   // warps here that would take a child right now
+            want = want > 0 ? (want + R - 2) / (R - 1) : 0;
+            *(volatile int *)(pctrl + GPSAT_DQC_PEER_QUEUE + me) = queued > 0 ? queued : 0;
+            *(volatile int *)(pctrl + GPSAT_DQC_PEER_IDLE + me) = want;
+        }
+        // ---- learnt clauses published on this GPU since the last round -> every peer's foreign pool
+        if (B.pool != nullptr && P.share_learnts) {
+            int used = *(volatile int *)B.pool_cursor;
+            if (used > pool_slots) used = pool_slots;
+            while (pushed < used) {
+                const int slot = pushed + lane;
+                const int len = slot < used ? __ldcg(B.pool + (size_t)slot * GPSAT_POOL_SLOT_WORDS) : 0;
+                const unsigned ready = __ballot_sync(0xffffffffu, len > 0);
+                const int cnt = __ffs(~ready) - 1 < 0 ? 32 : __ffs(~ready) - 1;   // complete slots form a prefix
+                if (cnt == 0) break;
+                int4 w0 = make_int4(0, 0, 0, 0), w1 = w0, w2 = w0, w3 = w0;
+                if (lane < cnt) {
+                    const int4 *src = reinterpret_cast<const int4 *>(B.pool + (size_t)slot * GPSAT_POOL_SLOT_WORDS);
+                    w0 = __ldcg(src);
+                    w1 = __ldcg(src + 1);
+                    w2 = __ldcg(src + 2);
+                    w3 = __ldcg(src + 3);
+                }
+                int base = 0;   // lane r reserves cnt slots of rank r's foreign pool
+                if (peer_lane) base = atomicAdd_system((int *)(B.mesh_base[lane] + B.mesh_off_xcur), cnt);
+                for (int r = 0; r < R; ++r) {
+                    const int rb = __shfl_sync(0xffffffffu, base, r);
+                    if (r == me) continue;
+                    const int dst = rb + lane;
+                    if (lane < cnt && dst < B.xpool_cap_slots) {
+                        int *x = (int *)(B.mesh_base[r] + B.mesh_off_xpool) + (size_t)dst * GPSAT_POOL_SLOT_WORDS;
+                        int4 *x4 = reinterpret_cast<int4 *>(x);
+                        x4[1] = w1;
+                        x4[2] = w2;
+                        x4[3] = w3;
+                        x[1] = w0.y;
+                        x[2] = w0.z;
+                        x[3] = w0.w;
+                        if (w0.x == 1 && (w0.y >> 1) < B.mesh_n_vars)
+                            ((volatile unsigned char *)(B.mesh_base[r] + B.mesh_off_facts))[w0.y >> 1] = (unsigned char)(1 + (w0.y & 1));
+                        __threadfence_system();
+                        *(volatile int *)x = w0.x;   // length last: the slot is complete
+                    }
+                }
+                pushed += cnt;
+                if (cnt < 32) break;
+            }
+        }
+        // ---- termination: only worth the two NVLink round trips when this GPU has nothing to do
+        if ((idle >= n_workers && queued <= 0) || (spins & 15u) == 15u) {
+            const unsigned long long a = *(const volatile unsigned long long *)(pctrl + GPSAT_DQC_CREATED);
+            int closed = (lane < R) ? (int)(a >> 32) : 0;
+            __threadfence_system();
+            const unsigned long long b = *(const volatile unsigned long long *)(pctrl + GPSAT_DQC_CREATED);
+            int created = (lane < R) ? (int)(b & 0xffffffffull) : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                closed += __shfl_xor_sync(0xffffffffu, closed, o);
+                created += __shfl_xor_sync(0xffffffffu, created, o);
+            }
+            if (closed == created) {
+                if (lane == 0) *(volatile int *)(ctrl + GPSAT_DQC_DONE) = 1;
+                break;
+            }
+        }
+        spins++;
+        __nanosleep(1500);
+    }
+    if (lane == 0) *(volatile int *)(ctrl + GPSAT_DQC_PUSHED) = pushed;
+}
+
+// Queue state of a solve, initialised on the device (one small launch instead of several pageable H2D copies):
+// ring slots empty (sequence number = slot index), control block, one open job per root cube this rank owns.
+__global__ void __launch_bounds__(256)
+gpsat_queue_init_kernel(int *ctrl, int *meta, int dq_cap, int *root_pending, int *root_flag, int n_roots, int root_first,
+                        int root_stride, int n_local, int *xcur, unsigned char *facts, int n_vars, int *run_ctrl,
+                        unsigned long long *t0)
+{
+    const int tid = (int)(blockIdx.x * blockDim.x + threadIdx.x), nt = (int)(gridDim.x * blockDim.x);
+    for (int i = tid; i < GPSAT_DQC_WORDS; i += nt) ctrl[i] = (i == GPSAT_DQC_CREATED) ? n_local : 0;
+    if (meta)
+        for (int i = tid; i < dq_cap; i += nt) {
+            meta[4 * i] = 0;
+            meta[4 * i + 1] = 0;
+            meta[4 * i + 2] = i;
+            meta[4 * i + 3] = 0;
+        }
+    for (int i = tid; i < n_roots; i += nt) {
+        const int d = i - root_first;
+        root_pending[i] = (d >= 0 && d % root_stride == 0 && d / root_stride < n_local) ? 1 : 0;
+        root_flag[i] = 0;
+    }
+    if (xcur)
+        for (int i = tid; i < 16; i += nt) xcur[i] = 0;
+    if (facts)
+        for (int i = tid; i < n_vars; i += nt) facts[i] = 0;
+    if (tid == 0) {
+        run_ctrl[0] = 0;    // next_job
+        run_ctrl[1] = 0;
+        run_ctrl[2] = -1;   // sat_job
+        run_ctrl[3] = 0;
+        t0[0] = 0;
+        t0[1] = 0;
+    }
+}
+
 // kSmemState:   the per-job state blocks live in dynamic shared memory.
 // kSmemFormula: the read-only formula index (cl2, occ2, ostart) is staged once per block in shared memory, in front
 //               of the state blocks, and every warp of the block reads it from there.
@@ -63,10 +220,34 @@ gpsat_cdcl_kernel(const gpsat_formula_view F, const gpsat_solve_params P, const 
     int *arena = B.arena ? B.arena + (size_t)gwarp * (size_t)P.arena_words : nullptr;
 
     int *park = B.park ? B.park + (size_t)gwarp * (size_t)B.park_words : nullptr;
+    int *stage = B.stage ? B.stage + (size_t)gwarp * (size_t)(B.hand_words + GPSAT_DQ_MAXK) : nullptr;
 
+    // mesh: warp 0 of this GPU does not solve; it is the GPU's link to the other GPUs of the box
+    if (B.mesh_ranks > 1 && gwarp == 0) {
+        CommArgs C;
+        C.mesh_ranks = B.mesh_ranks;
+        C.mesh_rank = B.mesh_rank;
+        C.share_learnts = P.share_learnts;
+        C.pool_cap_words = B.pool_cap_words;
+        C.xpool_cap_slots = B.xpool_cap_slots;
+        C.mesh_n_vars = B.mesh_n_vars;
+        C.dq_ctrl = B.dq_ctrl;
+        C.pool = B.pool;
+        C.pool_cursor = B.pool_cursor;
+        C.t0 = B.t0;
+        C.budget_ns = B.budget_ns;
+#pragma unroll
+        for (int r = 0; r < GPSAT_MESH_MAX_RANKS; ++r) C.mesh_base[r] = B.mesh_base[r];
+        C.mesh_off_ctrl = B.mesh_off_ctrl;
+        C.mesh_off_xcur = B.mesh_off_xcur;
+        C.mesh_off_xpool = B.mesh_off_xpool;
+        C.mesh_off_facts = B.mesh_off_facts;
+        gpsat_comm_loop(C);
+        return;
+    }
     WarpSolver S;
     gpsat_bind(S, Fv, P, Ly, state, arena, park, B);
-    gpsat_warp_loop(S, P, B);
+    gpsat_warp_loop(S, P, B, stage);
 }
 
 typedef void (*cdcl_kernel_t)(const gpsat_formula_view, const gpsat_solve_params, const gpsat_state_layout,
@@ -238,6 +419,16 @@ cudaError_t launch_xchg_unpack(const int *blocks, int n_ranks, int my_rank, int 
 {
     gpsat_xchg_unpack_kernel<<<1, 256, 0, stream>>>(blocks, n_ranks, my_rank, block_words, xpool, xpool_cursor,
                                                     xpool_cap_slots, facts, n_vars);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_queue_init(int *ctrl, int *meta, int dq_cap, int *root_pending, int *root_flag, int n_roots,
+                              int root_first, int root_stride, int n_local, int *xcur, unsigned char *facts, int n_vars,
+                              int *run_ctrl, unsigned long long *t0, cudaStream_t stream)
+{
+    gpsat_queue_init_kernel<<<32, 256, 0, stream>>>(ctrl, meta, dq_cap, root_pending, root_flag, n_roots, root_first,
+                                                    root_stride > 0 ? root_stride : 1, n_local, xcur, facts, n_vars,
+                                                    run_ctrl, t0);
     return cudaGetLastError();
 }
 

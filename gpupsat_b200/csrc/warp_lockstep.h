@@ -66,6 +66,12 @@ static inline void gpsat_atomic_add_ll(long long *p, long long v) { *p += v; }
 static inline int gpsat_ld_volatile(const int *p) { return *(const volatile int *)p; }
 static inline int gpsat_ld_cg(const int *p) { return *p; }
 static inline void gpsat_nanosleep(unsigned) {}
+// mesh (several GPUs as one work pool): system-scope variants; the emulator runs one warp on one "GPU"
+static inline int gpsat_atomic_cas_sys(int *p, int cmp, int v) { return gpsat_atomic_cas(p, cmp, v); }
+static inline int gpsat_atomic_add_sys(int *p, int v) { return gpsat_atomic_add(p, v); }
+static inline void gpsat_threadfence_sys() {}
+static inline unsigned long long gpsat_ld_volatile64(const int *p) { unsigned long long v; std::memcpy(&v, p, 8); return v; }
+static inline void gpsat_copy_cg(int *dst, const int *src, int n_words, int lane) { if (lane == 0 && dst && src) std::memcpy(dst, src, (size_t)n_words * 4); }
 // emulated clock: one tick per query, so tests can make budgeted steps expire deterministically
 static unsigned long long g_gpsat_emu_clock = 0;
 static inline unsigned long long gpsat_now_ns() { return ++g_gpsat_emu_clock; }
@@ -146,6 +152,32 @@ __device__ __forceinline__ int gpsat_ld_volatile(const int *p) { return *(const 
 // cached in this SM's L1 before the writer published could otherwise be served stale
 __device__ __forceinline__ int gpsat_ld_cg(const int *p) { return __ldcg(p); }
 __device__ __forceinline__ void gpsat_nanosleep(unsigned ns) { __nanosleep(ns); }
+// mesh (the GPUs of one box as one work pool over NVLink peer memory): words that another GPU reads or updates are
+// accessed with system-scope atomics / fences; peer memory is never cached in this GPU's L2, .cg keeps it out of L1
+__device__ __forceinline__ int gpsat_atomic_cas_sys(int *p, int cmp, int v) { return atomicCAS_system(p, cmp, v); }
+__device__ __forceinline__ int gpsat_atomic_add_sys(int *p, int v) { return atomicAdd_system(p, v); }
+__device__ __forceinline__ void gpsat_threadfence_sys() { __threadfence_system(); }
+__device__ __forceinline__ unsigned long long gpsat_ld_volatile64(const int *p)
+{
+    return *(const volatile unsigned long long *)p;   // 8-byte aligned: one atomic snapshot of two adjacent words
+}
+// warp-cooperative copy of n_words (both sides 16-byte aligned, n_words rounded up to a multiple of 4 by the caller's
+// layout) with L2-coherent 128-bit loads: four loads in flight per lane
+__device__ __forceinline__ void gpsat_copy_cg(int *dst, const int *src, int n_words, int lane)
+{
+    const int n4 = (n_words + 3) >> 2;
+    const int4 *s4 = reinterpret_cast<const int4 *>(src);
+    int4 *d4 = reinterpret_cast<int4 *>(dst);
+    int i = lane;
+    for (; i + 96 < n4; i += 128) {
+        const int4 a = __ldcg(s4 + i), b = __ldcg(s4 + i + 32), c = __ldcg(s4 + i + 64), d = __ldcg(s4 + i + 96);
+        d4[i] = a;
+        d4[i + 32] = b;
+        d4[i + 64] = c;
+        d4[i + 96] = d;
+    }
+    for (; i < n4; i += 32) d4[i] = __ldcg(s4 + i);
+}
 __device__ __forceinline__ unsigned long long gpsat_now_ns()
 {
     unsigned long long t;

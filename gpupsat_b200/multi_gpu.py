@@ -14,7 +14,13 @@ Per epoch and per rank:
 The data path has no other collective: the clause database is replicated, cubes never move.
 
 `solver` is a gpupsat_b200.Solver (or, in the CPU tests, an object with the same five methods working on CPU
-tensors); `dist` is torch.distributed or None for a single process."""
+tensors); `dist` is torch.distributed or None for a single process.
+
+`solve_mesh` is the fused form (the product path on a GPU box): the GPUs are joined in a mesh over NVLink peer memory
+(include/gpsat.h: gpsat_mesh_*), a solve is ONE persistent launch per GPU inside which idle warps take split-off cubes
+from the other GPUs' rings, learnt clauses are stored straight into the peers' pools and termination is detected —
+and the only collectives left are the all-gather of the 64-byte IPC handles when the mesh is formed and the
+all-reduces of the per-cube result block at the end."""
 from __future__ import annotations
 
 import numpy as np
@@ -87,3 +93,83 @@ def solve_sharded(solver, dist, rank: int, world: int, device, *, budget_ms: flo
     info = {"epochs": epochs, "imported_clauses": imported, "exchange_bytes_per_epoch": 4 * words * world,
             "jobs_done_all_ranks": jobs, "local_verdict": local_verdict}
     return verdict, model, stats, info
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# mesh: the GPUs of one box as ONE work pool (one process per GPU, CUDA IPC)
+# ---------------------------------------------------------------------------------------------------------------
+def mesh_shard(n_roots: int, rank: int, world: int):
+    """global cube g -> rank g mod world; returns (first, stride, n_local) of this rank's shard."""
+    return rank, world, max(0, (n_roots - rank + world - 1) // world)
+
+
+def mesh_join(solver, dist, rank: int, world: int, device, n_roots: int):
+    """Forms the mesh: every rank exports its queue region (a 64-byte CUDA IPC handle), ONE all-gather distributes
+    the handles, every rank maps the others' regions.  The solver's cubes must already be its shard (cubes[rank::world])."""
+    import torch
+
+    mine = torch.as_tensor(solver.mesh_export()).to(device)
+    allh = torch.zeros(world * 64, dtype=torch.uint8, device=device)
+    if dist is not None and world > 1:
+        _all_gather(dist, allh, mine, world)
+    else:
+        allh.copy_(mine)
+    first, stride, n_local = mesh_shard(n_roots, rank, world)
+    solver.mesh_attach_ipc(world, rank, allh.cpu().numpy(), n_roots, first, stride, n_local)
+    return mesh_result_block(solver, device)
+
+
+def mesh_result_block(solver, device):
+    import torch
+
+    return torch.zeros(solver.mesh_result_words(), dtype=torch.int32, device=device)
+
+
+def reduce_results(dist, block, n_roots: int, world: int):
+    """[flags n_roots | open descendants n_roots | records n_roots x 20 words]: MAX, SUM (int32), SUM (int64)."""
+    if dist is None or world <= 1:
+        return
+    dist.all_reduce(block[:n_roots], op=dist.ReduceOp.MAX)
+    dist.all_reduce(block[n_roots:2 * n_roots], op=dist.ReduceOp.SUM)
+    import torch
+
+    dist.all_reduce(block[2 * n_roots:].view(torch.int64), op=dist.ReduceOp.SUM)
+
+
+def solve_mesh(solver, dist, rank: int, world: int, device, block, n_roots: int, *, budget_ms: float = 0.0,
+               max_steps: int | None = None):
+    """One mesh solve.  Returns (verdict, model or None, global stats, info).  budget_ms = 0: one launch per GPU until
+    the whole job is done; > 0: time-bounded steps (unfinished cubes park in place; used for the time-bounded configs)."""
+    import torch
+
+    solver.solve_begin()
+    if dist is not None and world > 1:
+        dist.barrier()                    # nobody steals from a ring its owner has not reset yet
+    steps = 0
+    while True:
+        done, _ = solver.solve_step(budget_ms)
+        steps += 1
+        if done or (max_steps is not None and steps >= max_steps):
+            break
+    local_verdict, model, local_stats = solver.solve_end()
+    solver.mesh_results_pack(block)
+    if device is not None and torch.device(device).type == "cuda":
+        torch.cuda.current_stream(device).synchronize()
+    reduce_results(dist, block, n_roots, world)
+    verdict, stats = solver.mesh_results_unpack(block)
+    for k in ("kernel_ms", "kernel_launches", "warp_busy_frac", "steals", "foreign_clauses", "pool_clauses", "blocks",
+              "warps_per_block", "smem_bytes_per_block", "state_in_smem"):
+        stats[k] = local_stats[k]
+    sat_rank = -1
+    if verdict == SAT:
+        has = torch.tensor([rank if local_verdict == SAT else world], dtype=torch.int32, device=device)
+        if dist is not None and world > 1:
+            dist.all_reduce(has, op=dist.ReduceOp.MIN)
+        sat_rank = int(has[0])
+        m = torch.as_tensor(np.ascontiguousarray(model, dtype=np.uint8)).to(device)
+        if dist is not None and world > 1:
+            dist.broadcast(m, src=sat_rank)
+        model = m.cpu().numpy()
+    else:
+        model = None
+    return verdict, model, stats, {"steps": steps, "sat_rank": sat_rank, "local_verdict": local_verdict}

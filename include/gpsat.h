@@ -11,7 +11,8 @@
  *         GPSAT_SAT = 0 (true), GPSAT_UNSAT = 1 (false), GPSAT_UNDEF = 2 (unassigned / no verdict)
  *   - every buffer is caller-owned; functions return GPSAT_OK (0) or a negative gpsat_error and never exit()
  *     (the reference's check() prints, cudaDeviceReset()s and exit(1)s: ErrorHandler/CudaMemoryErrorHandler.cu:3-10)
- *   - one handle is used from one host thread and owns one GPU (one process per GPU; cubes are sharded by the caller)
+ *   - one handle is used from one host thread and owns one GPU; several GPUs = several handles joined in a mesh
+ *     (gpsat_mesh_*: one process per GPU, or gpsat_multi_*: one process, one host thread per GPU)
  *   - there is NO CPU fallback: device entry points fail with GPSAT_E_NO_DEVICE when no CUDA device is usable
  */
 #ifndef GPSAT_H
@@ -150,7 +151,8 @@ typedef struct gpsat_stats {
     int32_t reserved;
     int64_t splits;               /* children created by dynamic splitting */
     double  warp_busy_frac;       /* sum of the time warps spent inside jobs / (warps x kernel time) */
-    int64_t foreign_clauses;      /* clauses received from other GPUs (gpsat_exchange_unpack / gpsat_pool_import) */
+    int64_t foreign_clauses;      /* clauses received from other GPUs (exchange, pool import, or pushed over NVLink by a mesh peer) */
+    int64_t steals;               /* mesh: children of cubes split on another GPU that this GPU took over NVLink peer memory */
 } gpsat_stats;
 
 /* ≙ DataToDevice ctor + CUDAClauseVec::alloc_and_copy_to_dev (SATSolver/DataToDevice.cu:11-56, Utils/CUDAClauseVec.cu:85-118):
@@ -228,6 +230,50 @@ int gpsat_exchange_unpack(gpsat_t *h, const void *dev_blocks, int32_t n_ranks, i
 int gpsat_debug_ctrl(gpsat_t *h, int32_t *out16);
 /* raw device pointers so a caller can run NCCL collectives on the pool / flag without staging through the host */
 int gpsat_device_ptrs(gpsat_t *h, void **pool_words, void **pool_cursor, void **stop_flag, void **stream);
+
+/* --- mesh: the GPUs of one box as ONE work pool over NVLink peer memory (no reference equivalent). ---
+ * Every rank owns a shard of the cubes (global cube g = root_first + i * root_stride for its local cube i) and a queue
+ * region (control block, ring of split-off cubes with their hand-off blocks, foreign learnt-clause pool) that the other
+ * ranks map.  Inside ONE persistent launch per GPU: idle warps take split-off cubes from the rings of other GPUs, busy
+ * cubes split for the demand other GPUs advertise, short learnt clauses are stored straight into the peers' foreign pools,
+ * the early-termination flag and global termination travel the same way — no kernel boundary, no host collective on the
+ * data path.  Per-cube records / outcome flags are per-rank contributions over ALL n_roots cubes: gpsat_mesh_results_pack
+ * copies them into a caller-owned DEVICE block [flags n_roots | open descendants n_roots | records n_roots x 20 words]; the
+ * caller reduces the blocks of all ranks (MAX over the first n_roots int32 words, SUM over the rest: int32 for the next
+ * n_roots words, int64 for the records — ncclAllReduce / torch.distributed.all_reduce) and gpsat_mesh_results_unpack turns
+ * the reduced block into the global verdict, records (gpsat_job_records: n_roots entries) and statistics.
+ * One process per GPU: gpsat_mesh_export + all-gather of the 64-byte handles + gpsat_mesh_attach_ipc (CUDA IPC).
+ * One process, several GPUs: gpsat_mesh_attach_local (peer access), or simply the gpsat_multi_* host below.
+ * Call order per solve: [all ranks] gpsat_solve_begin -> barrier -> gpsat_solve_step(budget) until done -> reduce results.
+ * The barrier matters: a peer must not steal from a ring that its owner has not reset yet. */
+#define GPSAT_IPC_HANDLE_BYTES 64
+#define GPSAT_MESH_MAX_GPUS 8
+int gpsat_mesh_export(gpsat_t *h, void *ipc_handle /* GPSAT_IPC_HANDLE_BYTES */);
+int gpsat_mesh_attach_ipc(gpsat_t *h, int32_t n_ranks, int32_t rank, const void *ipc_handles /* n_ranks x 64 bytes */,
+                          int32_t n_roots, int32_t root_first, int32_t root_stride, int32_t n_local /* may be 0 */);
+/* in-process mesh over handles[0..n_ranks).  n_local = NULL: cube g of the n_roots cubes belongs to rank g mod n_ranks;
+ * n_local given: rank r owns the next n_local[r] cubes (contiguous ranges in rank order; 0 = the rank only takes
+ * children of other GPUs).  Each handle's cubes must have been set to its shard before. */
+int gpsat_mesh_attach_local(gpsat_t *const *handles, int32_t n_ranks, int32_t n_roots, const int32_t *n_local);
+int gpsat_mesh_detach(gpsat_t *h);
+int64_t gpsat_mesh_result_words(gpsat_t *h);
+int gpsat_mesh_results_pack(gpsat_t *h, void *dev_block, int64_t words);
+int gpsat_mesh_results_unpack(gpsat_t *h, const void *dev_block, int64_t words, int32_t *verdict, gpsat_stats *stats);
+int gpsat_handle_device(gpsat_t *h);
+
+/* --- multi-GPU host in one process (≙ the host side of SATSolver/main.cu:197-310 for N GPUs; the reference drives one) ---
+ * One host thread per GPU, the formula replicated, cube g -> GPU g mod N, the GPUs meshed as above; per-cube results are
+ * reduced with ncclAllReduce (libnccl is loaded at run time; the reduction runs on the host when it cannot be loaded).
+ * n_gpus = 0: every visible GPU (at most GPSAT_MESH_MAX_GPUS); devices = NULL: ordinals 0 .. n_gpus-1. */
+typedef struct gpsat_multi gpsat_multi_t;
+int gpsat_multi_create(gpsat_multi_t **m, int32_t n_gpus, const int32_t *devices, int32_t n_vars, int64_t n_clauses,
+                       const int64_t *offsets, const int32_t *lits, const gpsat_opts *opts);
+int gpsat_multi_n_gpus(gpsat_multi_t *m);
+int gpsat_multi_set_cubes(gpsat_multi_t *m, int32_t n_cubes, const int64_t *cube_offsets, const int32_t *cube_lits);
+/* stats: counters summed over GPUs; kernel_ms = slowest GPU; warp_busy_frac = mean; reduce_backend (optional): 1 NCCL, 0 host */
+int gpsat_multi_solve(gpsat_multi_t *m, int32_t *verdict, uint8_t *model, gpsat_stats *stats, int32_t *reduce_backend);
+int gpsat_multi_job_records(gpsat_multi_t *m, gpsat_job_record *records, int32_t cap);
+void gpsat_multi_destroy(gpsat_multi_t *m);
 
 #ifdef __cplusplus
 }

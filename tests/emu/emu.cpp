@@ -33,7 +33,7 @@ extern "C" int gpsat_emu_run(int32_t n_vars, int64_t n_clauses, const int64_t *o
     gpsat_make_layout(n_vars, D.n_lits, &Ly);
     std::vector<int32_t> state((size_t)Ly.total_words, 0);
     std::vector<int32_t> arena((size_t)P.arena_words, 0);
-    int32_t next_job = 0, stop_flag = 0;
+    int32_t next_job = 0;
     *sat_job = -1;
     gpsat_run_buffers B;
     std::memset(&B, 0, sizeof(B));
@@ -41,7 +41,6 @@ extern "C" int gpsat_emu_run(int32_t n_vars, int64_t n_clauses, const int64_t *o
     B.cube_lits = cube_lits;
     B.n_cubes = n_cubes;
     B.next_job = &next_job;
-    B.stop_flag = &stop_flag;
     B.sat_job = sat_job;
     B.model = model;
     B.records = records;
@@ -58,7 +57,12 @@ extern "C" int gpsat_emu_run(int32_t n_vars, int64_t n_clauses, const int64_t *o
     std::vector<int32_t> dq_lits((size_t)GPSAT_DQ_CAP * GPSAT_DQ_MAXK, 0), dq_meta((size_t)GPSAT_DQ_CAP * 4, 0);
     for (int i = 0; i < GPSAT_DQ_CAP; i++) dq_meta[4 * (size_t)i + 2] = i;
     std::vector<int32_t> root_pending((size_t)n_cubes, 1), root_flag((size_t)n_cubes, 0);
-    int32_t dq_ctrl[8] = {0, 0, n_cubes, 0, 0, 0, 0, 0};
+    int32_t dq_ctrl[GPSAT_DQC_WORDS] = {0};
+    dq_ctrl[GPSAT_DQC_CREATED] = n_cubes;
+    B.stop_flag = dq_ctrl + GPSAT_DQC_STOP;
+    B.root_first = 0;
+    B.root_stride = 1;
+    B.n_roots = n_cubes;
     B.dq_lits = dq_lits.data();
     B.dq_meta = dq_meta.data();
     B.dq_ctrl = dq_ctrl;
@@ -81,9 +85,9 @@ extern "C" int gpsat_emu_run(int32_t n_vars, int64_t n_clauses, const int64_t *o
     do {
         t0 = gpsat_now_ns();
         gpsat_bind(S, F, P, Ly, state.data(), arena.data(), B.park, B);
-        gpsat_warp_loop(S, P, B);
+        gpsat_warp_loop(S, P, B, nullptr);
         launches++;
-    } while (budget_ticks && dq_ctrl[2] > 0 && !stop_flag && launches < 100000);
+    } while (budget_ticks && dq_ctrl[GPSAT_DQC_CREATED] != dq_ctrl[GPSAT_DQC_CLOSED] && !dq_ctrl[GPSAT_DQC_STOP] && launches < 100000);
     if (n_launches) *n_launches = launches;
     for (int j = 0; j < n_cubes; j++) records[j].status = gpsat_root_status(root_flag[j], root_pending[j]);
     return 0;

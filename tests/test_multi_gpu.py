@@ -120,3 +120,134 @@ def test_shard_cubes_is_a_partition():
         assert sum(len(p) for p in parts) == 4096
         assert np.array_equal(np.sort(np.concatenate(parts)[:, 0]), cubes[:, 0])
         assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# mesh harness (solve_mesh): join by one all-gather of the 64-byte handles, one launch, reduction of the result block
+# [flags: MAX | open descendants: SUM int32 | records: SUM int64], global verdict, model from the lowest SAT rank
+# ---------------------------------------------------------------------------------------------------------------
+REC_WORDS = 20
+FLAG_UNSAT, FLAG_SAT = 1, 5
+
+
+class ScriptedMeshSolver:
+    """Rank r closes the roots it owns (g mod world == r) plus, like a thief, root `steal` of the next rank; each
+    closed root contributes flag UNSAT (or SAT for `sat_root`), -1/+1 open-descendant bookkeeping and 7 implications."""
+
+    def __init__(self, rank, world, n_roots, n_vars, sat_root=None, leave_open=None):
+        self.rank, self.world, self.n_roots, self.n_vars = rank, world, n_roots, n_vars
+        self.sat_root, self.leave_open = sat_root, leave_open
+        self.attached, self.began, self.steps = None, False, 0
+
+    def mesh_export(self):
+        return np.full(64, 10 + self.rank, dtype=np.uint8)
+
+    def mesh_attach_ipc(self, n_ranks, rank, handles, n_roots, first, stride, n_local):
+        h = np.asarray(handles).reshape(n_ranks, 64)
+        assert (h[:, 0] == 10 + np.arange(n_ranks)).all()           # every rank's handle arrived, in rank order
+        assert (first, stride) == (rank, n_ranks) and n_local == len(range(rank, n_roots, n_ranks))
+        self.attached = (n_ranks, rank)
+
+    def mesh_result_words(self):
+        return self.n_roots * (2 + REC_WORDS)
+
+    def solve_begin(self):
+        assert self.attached == (self.world, self.rank)
+        self.began = True
+
+    def solve_step(self, budget_ms):
+        assert self.began
+        self.steps += 1
+        return True, mg.UNDEF
+
+    def solve_end(self):
+        v = mg.SAT if (self.sat_root is not None and self.sat_root % self.world == self.rank) else mg.UNDEF
+        return v, np.full(self.n_vars, self.rank, dtype=np.uint8), \
+            {k: 0 for k in ("kernel_ms", "kernel_launches", "warp_busy_frac", "steals", "foreign_clauses", "pool_clauses",
+                            "blocks", "warps_per_block", "smem_bytes_per_block", "state_in_smem")}
+
+    def mesh_results_pack(self, block):
+        b = block.numpy()
+        b[:] = 0
+        nr = self.n_roots
+        rec = b[2 * nr:].view(np.int64).reshape(nr, REC_WORDS // 2)
+        for g_ in range(nr):
+            if g_ % self.world == self.rank:
+                b[nr + g_] += 1                                    # the owner opened the root ...
+                if g_ == self.leave_open:
+                    continue
+                b[nr + g_] += 1                                    # ... split a child off it, closed its own half
+                b[nr + g_] -= 1
+                b[g_] = FLAG_SAT if g_ == self.sat_root else FLAG_UNSAT
+                rec[g_, 2] += 7
+            if (g_ + 1) % self.world == self.rank and g_ != self.leave_open:
+                b[nr + g_] -= 1                                    # the child was closed HERE, on another rank
+                b[g_] = max(b[g_], FLAG_UNSAT)
+                rec[g_, 2] += 7
+
+    def mesh_results_unpack(self, block):
+        b = block.numpy()
+        nr = self.n_roots
+        flags, pend = b[:nr], b[nr:2 * nr]
+        rec = b[2 * nr:].view(np.int64).reshape(nr, REC_WORDS // 2)
+        if (flags == FLAG_SAT).any():
+            v = mg.SAT
+        elif ((flags == FLAG_UNSAT) & (pend == 0)).all():
+            v = mg.UNSAT
+        else:
+            v = mg.UNDEF
+        return v, {"implications": int(rec[:, 2].sum()), "jobs_done": int(((flags > 0) & (pend == 0)).sum())}
+
+
+def _mesh_worker(rank, world, port, kw, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_roots = 9
+        s = ScriptedMeshSolver(rank, world, n_roots, 5, **kw)
+        block = mg.mesh_join(s, dist, rank, world, "cpu", n_roots)
+        verdict, model, stats, info = mg.solve_mesh(s, dist, rank, world, "cpu", block, n_roots)
+        out[rank] = {"verdict": verdict, "model": None if model is None else model.tolist(), "stats": stats,
+                     "sat_rank": info["sat_rank"], "steps": info["steps"]}
+    finally:
+        dist.destroy_process_group()
+
+
+def _run_mesh(**kw):
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_mesh_worker, args=(2, port, kw, out), nprocs=2, join=True)
+        return dict(out)
+
+
+def test_mesh_unsat_needs_the_contributions_of_every_rank():
+    out = _run_mesh()
+    assert out[0]["verdict"] == out[1]["verdict"] == mg.UNSAT
+    # every root was closed half by its owner and half by the other rank: only the reduced block says "closed"
+    assert out[0]["stats"]["jobs_done"] == out[1]["stats"]["jobs_done"] == 9
+    assert out[0]["stats"]["implications"] == 9 * 14
+    assert out[0]["model"] is None and out[0]["steps"] == 1
+
+
+def test_mesh_open_descendant_on_one_rank_keeps_the_verdict_undef():
+    out = _run_mesh(leave_open=4)
+    assert out[0]["verdict"] == out[1]["verdict"] == mg.UNDEF
+
+
+def test_mesh_sat_model_comes_from_the_lowest_sat_rank():
+    out = _run_mesh(sat_root=3)                                      # root 3 belongs to rank 1
+    assert out[0]["verdict"] == out[1]["verdict"] == mg.SAT
+    assert out[0]["sat_rank"] == out[1]["sat_rank"] == 1
+    assert out[0]["model"] == out[1]["model"] == [1] * 5
+
+
+def test_mesh_shard_matches_shard_cubes():
+    cubes = np.arange(37 * 3).reshape(37, 3)
+    for world in (1, 2, 3, 8):
+        for r in range(world):
+            first, stride, n_local = mg.mesh_shard(len(cubes), r, world)
+            assert np.array_equal(cubes[first::stride], mg.shard_cubes(cubes, r, world)) and n_local == len(cubes[first::stride])
+    assert mg.mesh_shard(2, 5, 8) == (5, 8, 0)                       # more ranks than cubes: an empty shard, not a stall
