@@ -5,7 +5,7 @@
 NVCC ?= /usr/local/cuda/bin/nvcc
 CXX  ?= g++
 ARCH := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := -std=c++17 -O3 $(ARCH) -lineinfo -Xcompiler -fPIC -Xptxas -v
+NVFLAGS := -std=c++17 -O3 $(ARCH) -lineinfo -Xcompiler -fPIC -Xptxas -v $(EXTRA_NVFLAGS)
 CSRC := gpupsat_b200/csrc
 DEPS := $(wildcard $(CSRC)/*.h $(CSRC)/*.inl include/*.h)
 

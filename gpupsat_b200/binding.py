@@ -29,7 +29,8 @@ class GpsatOpts(C.Structure):
                 ("share_max_len", C.c_int32), ("warps_per_block", C.c_int32), ("blocks", C.c_int32),
                 ("arena_words", C.c_int64), ("dynamic_split", C.c_int32), ("split_gap", C.c_int32),
                 ("split_burst", C.c_int32), ("share_import_max", C.c_int32), ("split_hand_words", C.c_int32),
-                ("reserved", C.c_int32 * 3)]
+                ("split_gap_hot", C.c_int32), ("split_at_start", C.c_int32), ("mesh_flags", C.c_int32),
+                ("split_mode", C.c_int32), ("max_learnts", C.c_int32), ("split_min", C.c_int32)]
 
 
 class GpsatStats(C.Structure):
@@ -111,6 +112,7 @@ def lib():
     L.gpsat_mesh_results_pack.argtypes = [vp, vp, i64]
     L.gpsat_mesh_results_unpack.argtypes = [vp, vp, i64, C.POINTER(i32), C.POINTER(GpsatStats)]
     L.gpsat_handle_device.argtypes = [vp]
+    L.gpsat_debug_words.argtypes = [vp, vp, i32]
     L.gpsat_multi_create.argtypes = [C.POINTER(vp), i32, vp, i32, i64, vp, vp, C.POINTER(GpsatOpts)]
     L.gpsat_multi_n_gpus.argtypes = [vp]
     L.gpsat_multi_set_cubes.argtypes = [vp, i32, vp, vp]
@@ -362,6 +364,11 @@ class Solver:
     def debug_ctrl(self):
         out = np.zeros(16, dtype=np.int32)
         _check(lib().gpsat_debug_ctrl(self.h, _p(out)))
+        return out
+
+    def debug_words(self, n=160):
+        out = np.zeros(n, dtype=np.int32)
+        _check(lib().gpsat_debug_words(self.h, _p(out), n))
         return out
 
     def request_stop(self):

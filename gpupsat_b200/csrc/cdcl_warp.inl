@@ -67,7 +67,7 @@ struct WarpSolver {
     float restart_factor;
     long long max_conflicts;
     // dynamic splitting
-    int dynamic_split, split_force, split_gap, split_burst, root;
+    int dynamic_split, split_force, split_gap, split_burst, split_gap_hot, split_hot_demand, split_at_start, split_mode, split_min, inherited, root;
     int *dq_lits, *dq_meta, *dq_ctrl, *root_pending, *dq_hand;
     int hand_words, dq_cap;
     int rel_slot, rel_seq;                 // queue slot this job was popped from (released once its content is consumed)
@@ -1073,12 +1073,17 @@ struct WarpSolver {
         int d = gpsat_ld_volatile(dq_ctrl + GPSAT_DQC_IDLE) -
                 (gpsat_ld_volatile(dq_ctrl + GPSAT_DQC_TAIL) - gpsat_ld_volatile(dq_ctrl + GPSAT_DQC_HEAD)) -
                 gpsat_ld_volatile(dq_ctrl + GPSAT_DQC_INFLIGHT);
-        GPSAT_NOUNROLL
-        for (int r = 0; r < mesh_ranks; ++r) d += gpsat_ld_volatile(dq_ctrl + GPSAT_DQC_PEER_IDLE + r);
+        // this GPU's idle warps take a new child before any other GPU can: what the peers advertise counts only once
+        // the local warps are served (d <= 0: -d children are queued beyond local demand)
+        if (d <= 0) {
+            GPSAT_NOUNROLL
+            for (int r = 0; r < mesh_ranks; ++r) d += gpsat_ld_volatile(dq_ctrl + GPSAT_DQC_PEER_IDLE + r);
+        }
         return d;
     }
 
-    // reserves a slot for writing; returns it (ticket in `ticket`) or -1 when the ring is full
+    // reserves a slot for writing; returns it (ticket in `ticket`) or -1 when the ring is (nearly) full.
+    // Push tickets are a fetch-add too; the margin covers every warp of the GPU drawing a ticket at the same moment.
     GPSAT_DEV int dq_acquire(int &ticket)
     {
         GPSAT_LANE_DECL
@@ -1091,24 +1096,13 @@ struct WarpSolver {
         }
         LANE0
         {
-            int pos = gpsat_ld_volatile(dq_ctrl + GPSAT_DQC_TAIL);
-            GPSAT_NOUNROLL
-            for (int tries = 0; tries < 64; ++tries) {
+            if (gpsat_ld_volatile(dq_ctrl + GPSAT_DQC_TAIL) - gpsat_ld_volatile(dq_ctrl + GPSAT_DQC_HEAD) < dq_cap - 4096) {
+                const int pos = gpsat_atomic_add(dq_ctrl + GPSAT_DQC_TAIL, 1);
                 const int slot = pos & (dq_cap - 1);
-                const int dif = gpsat_ld_volatile(dq_meta + 4 * slot + 2) - pos;
-                if (dif == 0) {
-                    const int old = gpsat_atomic_cas(dq_ctrl + GPSAT_DQC_TAIL, pos, pos + 1);
-                    if (old == pos) {
-                        LV(slot_v) = slot;
-                        LV(pos_v) = pos;
-                        break;
-                    }
-                    pos = old;
-                } else if (dif < 0) {
-                    break;   // full
-                } else {
-                    pos = gpsat_ld_volatile(dq_ctrl + GPSAT_DQC_TAIL);
-                }
+                // freed long ago by the consumer of ticket pos - dq_cap (it releases the slot as soon as it has copied it)
+                while (gpsat_ld_volatile(dq_meta + 4 * slot + 2) != pos) gpsat_nanosleep(200);
+                LV(slot_v) = slot;
+                LV(pos_v) = pos;
             }
         }
         ticket = SHFL(pos_v, 0);
@@ -1129,6 +1123,7 @@ struct WarpSolver {
             if (extra >= 0) dq_lits[(long long)slot * GPSAT_DQ_MAXK + k] = extra;
             dq_meta[4 * slot] = root;
             dq_meta[4 * slot + 1] = extra >= 0 ? k + 1 : k;
+            dq_meta[4 * slot + 3] = (int)((inherited + c_conflicts) / 2);   // the child is as hard as its parent was (a guess)
             gpsat_atomic_add(root_pending + root, 1);
             gpsat_atomic_add(dq_ctrl + GPSAT_DQC_CREATED, 1);
         }
@@ -1136,7 +1131,12 @@ struct WarpSolver {
         write_handoff(slot);
         if (mesh_ranks > 1) gpsat_threadfence_sys();   // the taker may be a warp of another GPU
         else gpsat_threadfence();
-        LANE0 { ((volatile int *)dq_meta)[4 * slot + 2] = ticket + 1; }   // publish
+        LANE0
+        {
+            ((volatile int *)dq_meta)[4 * slot + 2] = ticket + 1;   // publish
+            if (mesh_ranks > 1) gpsat_atomic_add_sys(dq_ctrl + GPSAT_DQC_AVAIL, 1);
+            else gpsat_atomic_add(dq_ctrl + GPSAT_DQC_AVAIL, 1);
+        }
         SYNCWARP();
     }
 
@@ -1152,7 +1152,11 @@ struct WarpSolver {
     }
 
     // Hand half of the remaining search space to another warp: queue cube + ~p, keep cube + p.
-    // Called with exactly the k cube literals decided and propagated.  Returns the new k.
+    // Guiding path (split_mode 0, called at any point of the search with dlevel > k): p is the OLDEST open decision of
+    // this job (the first literal of level k+1) — the untried side of that decision is the largest unexplored subtree,
+    // the job simply adopts p as one more cube literal and keeps its trail, its learnt clauses and its place in the
+    // search.  Otherwise (called with exactly the k cube literals decided and propagated): p = the VSIDS-best variable.
+    // Returns the new k.
     GPSAT_DEV int try_split(int k)
     {
         GPSAT_LANE_DECL
@@ -1166,7 +1170,8 @@ struct WarpSolver {
         }
         int slot = -1, ticket = 0, p = -1;
         if (SHFL(claim_v, 0)) {
-            p = pick_branch();
+            p = dlevel > k ? trail[trail_lim[k]] : pick_branch();
+            if (p >= 0 && split_mode == 2 && dlevel == k) p ^= 1;   // keep the side VSIDS would NOT try first
             if (p >= 0) slot = dq_acquire(ticket);
         }
         LANE0 { gpsat_atomic_add(dq_ctrl + GPSAT_DQC_INFLIGHT, -1); }   // from here on the child is counted by tail - head
@@ -1211,6 +1216,7 @@ struct WarpSolver {
             park[10] = conflicts_since_restart;
             park[11] = pool_mark;
             park[12] = xpool_mark;
+            park[13] = inherited;
         }
         SYNCWARP();
         gpsat_threadfence();
@@ -1234,6 +1240,7 @@ struct WarpSolver {
             conflicts_since_restart = park[10];
             pool_mark = park[11];
             xpool_mark = park[12];
+            inherited = park[13];
             cube = park + 16;
             const int n0 = park[3];
             LANES
@@ -1255,6 +1262,7 @@ struct WarpSolver {
         const bool queued_ok = mode == GPSAT_MODE_SOLVE && dynamic_split && k < GPSAT_DQ_MAXK;
         const bool may_split = queued_ok && k + 1 < GPSAT_DQ_MAXK;
         int want_split = 0, burst = 0;
+        int at_start = (may_split && split_at_start && !resume) ? 1 : 0;
         long long last_split_at = 0;
         if (queued_ok) {   // the cube may grow (splits) or be parked (budgeted steps): work on a private copy
             LANES
@@ -1321,9 +1329,15 @@ struct WarpSolver {
                         }
                     }
                 }
-                if (may_split && !want_split && c_conflicts - last_split_at >= split_gap && demand_hint() > 0) {
-                    want_split = 1;
-                    burst = 0;
+                if (may_split && !want_split && c_conflicts - last_split_at >= split_gap_hot &&
+                    inherited + c_conflicts >= split_min) {
+                    // a cube splits once it has proved hard (split_min), then every split_gap conflicts while warps are
+                    // idle — every split_gap_hot conflicts while more than 1/8 of the GPU's warps are idle (start and tail)
+                    const int d = demand_hint();
+                    if (d > 0 && (c_conflicts - last_split_at >= split_gap || d >= split_hot_demand)) {
+                        want_split = 1;
+                        burst = 0;
+                    }
                 }
                 continue;
             }
@@ -1335,19 +1349,24 @@ struct WarpSolver {
                 cancel_until(k < dlevel ? k : dlevel);
                 if (split_force) want_split = 1;
             }
-            if (want_split) {   // an idle warp is waiting: go back to the cube and give it half of what is left
-                want_split = 0;
-                if (dlevel >= k) {
-                    cancel_until(k);
-                    const int k2 = try_split(k);
-                    if (k2 != k) {
-                        // while warps are still idle keep peeling children off (cube+~p1, cube+p1+~p2, ...): the
-                        // number of busy warps then grows by split_burst per gap instead of doubling
-                        last_split_at = c_conflicts;
-                        if (++burst < split_burst && demand_hint() > 0) want_split = 1;
-                    }
-                    k = k2;
+            if (at_start && dlevel >= k) {   // the cube is placed and nothing has been searched yet: idle warps get their share now
+                at_start = 0;
+                if (demand_hint() >= split_hot_demand) {
+                    want_split = 1;
+                    burst = 0;
                 }
+            }
+            if (want_split && dlevel >= k) {   // an idle warp is waiting: give it half of what is left
+                want_split = 0;
+                if (split_mode != 1 || dlevel == k) cancel_until(k);
+                const int k2 = try_split(k);
+                if (k2 != k) {
+                    // while warps are still idle keep peeling children off (cube+~p1, cube+p1+~p2, ...): the
+                    // number of busy warps then grows by split_burst per gap instead of doubling
+                    last_split_at = c_conflicts;
+                    if (++burst < split_burst && demand_hint() > 0) want_split = 1;
+                }
+                k = k2;
             }
             if (use_learnts && (n_learnts >= max_learnts || (watch_bot - arena_top) < (arena_words - clause_base) / 4)) {
                 reduce_db();
@@ -1419,6 +1438,12 @@ GPSAT_DEV void gpsat_bind(WarpSolver &S, const gpsat_formula_view &F, const gpsa
     S.split_force = P.split_force;
     S.split_gap = P.split_gap > 0 ? P.split_gap : 1;
     S.split_burst = P.split_burst > 0 ? P.split_burst : 1;
+    S.split_gap_hot = P.split_gap_hot > 0 ? P.split_gap_hot : S.split_gap;
+    S.split_hot_demand = P.split_hot_demand > 0 ? P.split_hot_demand : 0x7fffffff;
+    S.split_at_start = P.split_at_start;
+    S.split_mode = P.split_mode;
+    S.split_min = P.split_min;
+    S.inherited = 0;
     S.root = 0;
     S.dq_lits = B.dq_lits;
     S.dq_meta = B.dq_meta;
@@ -1567,32 +1592,37 @@ GPSAT_DEV void gpsat_run_and_record(WarpSolver &S, int root, const int *cube, in
         if (status != GPSAT_JOB_SUSPENDED) {
             gpsat_atomic_add(B.root_pending + job, -1);
             gpsat_atomic_add(B.dq_ctrl + GPSAT_DQC_CLOSED, 1);
+            if (hand != nullptr) {   // size of a split-off cube, in conflicts (diagnostics)
+                int b = 0;
+                GPSAT_NOUNROLL
+                for (long long c = S.c_conflicts + 1; c > 1 && b < 15; c >>= 1) ++b;
+                gpsat_atomic_add(B.dq_ctrl + GPSAT_DQC_HIST + b, 1);
+            }
         }
     }
     SYNCWARP();
 }
 
 // Lane-0 code: takes the oldest child off a ring (this GPU's, or — `sys` — one that warps of several GPUs pop from).
-// Returns the pop ticket, or -1 when the ring is empty (or its next child is still being written).
+// Returns the pop ticket, or -1 when the ring holds no published child.
+// One atomic per step and no retry loop: a consumer first claims one of the published children on the AVAIL semaphore,
+// only then draws a pop ticket with a fetch-add, and waits for exactly that slot if its writer is still a few
+// microseconds from publishing (tickets are handed out in ring order, publications complete in any order).  The
+// compare-and-swap ring this replaces collapsed under ~2000 idle warps: 6 million lost CAS for 23 thousand pops in one
+// C2 shard, 1400 children queued in front of 1400 idle warps (profiles/r02_ring_*.txt).
 GPSAT_DEV int gpsat_ring_pop(int *ctrl, int *meta, int cap, bool sys)
 {
-    int pos = gpsat_ld_volatile(ctrl + GPSAT_DQC_HEAD);
-    GPSAT_NOUNROLL
-    for (int tries = 0; tries < 8; ++tries) {
-        const int slot = pos & (cap - 1);
-        const int dif = gpsat_ld_volatile(meta + 4 * slot + 2) - (pos + 1);
-        if (dif == 0) {
-            const int old = sys ? gpsat_atomic_cas_sys(ctrl + GPSAT_DQC_HEAD, pos, pos + 1)
-                                : gpsat_atomic_cas(ctrl + GPSAT_DQC_HEAD, pos, pos + 1);
-            if (old == pos) return pos;
-            pos = old;
-        } else if (dif < 0) {
-            return -1;
-        } else {
-            pos = gpsat_ld_volatile(ctrl + GPSAT_DQC_HEAD);
-        }
+    if (gpsat_ld_volatile(ctrl + GPSAT_DQC_AVAIL) <= 0) return -1;
+    const int had = sys ? gpsat_atomic_add_sys(ctrl + GPSAT_DQC_AVAIL, -1) : gpsat_atomic_add(ctrl + GPSAT_DQC_AVAIL, -1);
+    if (had <= 0) {   // somebody else took the last one: give the claim back
+        if (sys) gpsat_atomic_add_sys(ctrl + GPSAT_DQC_AVAIL, 1);
+        else gpsat_atomic_add(ctrl + GPSAT_DQC_AVAIL, 1);
+        return -1;
     }
-    return -1;
+    const int pos = sys ? gpsat_atomic_add_sys(ctrl + GPSAT_DQC_HEAD, 1) : gpsat_atomic_add(ctrl + GPSAT_DQC_HEAD, 1);
+    const int slot = pos & (cap - 1);
+    while (gpsat_ld_volatile(meta + 4 * slot + 2) != pos + 1) gpsat_nanosleep(200);
+    return pos;
 }
 
 // The warp's main loop: original cubes from the atomic cursor (≙ JobsQueue::next_job, SATSolver/JobsQueue.cu:10-32),
@@ -1632,7 +1662,7 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
                 if (kind == 3 && P.mode == GPSAT_MODE_SOLVE && P.dynamic_split) {
                     idx = gpsat_ring_pop(B.dq_ctrl, B.dq_meta, B.dq_cap, mesh);
                     if (idx >= 0) kind = 2;
-                    if (kind == 3 && mesh && stage != nullptr) {
+                    if (kind == 3 && mesh && stage != nullptr && !(P.mesh_flags & 1)) {
                         // children advertised by the other GPUs (their communication warps refresh PEER_QUEUE): claim one
                         // locally first, so that at most as many warps go out over NVLink as there are children to take
                         GPSAT_NOUNROLL
@@ -1676,7 +1706,10 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
             }
             // idle warps must not steal issue slots from the busy ones, nor hammer the queue counters in L2 (in the
             // tail of a run thousands of them poll the same sector that the splitting warps update): back off to 32 us
-            gpsat_nanosleep(4000u << (idle_spins < 3 ? idle_spins : 3));
+#if !defined(GPSAT_IDLE_NS)
+#define GPSAT_IDLE_NS 4000u
+#endif
+            gpsat_nanosleep(GPSAT_IDLE_NS << (idle_spins < 3 ? idle_spins : 3));
             idle_spins++;
             continue;
         }
@@ -1690,12 +1723,14 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
             gpsat_run_and_record(S, S.park[1], S.park + 16, S.park[2], nullptr, P, B, true);
         } else if (kind == 1) {
             const long long c0 = B.cube_offsets[idx], c1 = B.cube_offsets[idx + 1];
+            S.inherited = 0;
             gpsat_run_and_record(S, B.root_first + idx * B.root_stride, B.cube_lits + c0, (int)(c1 - c0), nullptr, P, B);
         } else if (kind == 2) {
             const int slot = idx & (B.dq_cap - 1);
             gpsat_threadfence();
             const int root = gpsat_ld_cg(B.dq_meta + 4 * slot);
             const int len = gpsat_ld_cg(B.dq_meta + 4 * slot + 1);
+            S.inherited = gpsat_ld_cg(B.dq_meta + 4 * slot + 3);
             const int *hand = B.dq_hand + (long long)slot * B.hand_words;
             S.rel_slot = slot;
             S.rel_seq = idx + B.dq_cap;   // the ticket that may write this slot next
@@ -1712,6 +1747,7 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
             gpsat_threadfence_sys();
             const int root = gpsat_ld_cg(rmeta + 4 * slot);
             const int len = gpsat_ld_cg(rmeta + 4 * slot + 1);
+            S.inherited = gpsat_ld_cg(rmeta + 4 * slot + 3);
             int used = gpsat_ld_cg(rhand);
             if (used < 0 || used > B.hand_words - 1 - 2 * S.n_vars) used = 0;
             LANES

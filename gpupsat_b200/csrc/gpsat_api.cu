@@ -310,6 +310,15 @@ gpsat_solve_params make_params(gpsat *h, int mode, int64_t implied_stride)
     P.split_gap = h->opts.split_gap > 0 ? h->opts.split_gap : 8;
     P.split_burst = h->opts.split_burst > 0 ? h->opts.split_burst : 4;
     P.share_import_max = h->opts.share_import_max > 0 ? h->opts.share_import_max : 256;
+    P.split_gap_hot = h->opts.split_gap_hot > 0 ? h->opts.split_gap_hot : std::max(1, P.split_gap / 2);   // measured: DESIGN.md
+    if (P.split_gap_hot > P.split_gap) P.split_gap_hot = P.split_gap;
+    P.split_hot_demand = std::max(1, h->blocks * h->warps_per_block / 8);
+    P.split_at_start = h->opts.split_at_start > 0 ? 1 : 0;
+    P.mesh_flags = h->opts.mesh_flags;
+    P.split_mode = h->opts.split_mode;
+    P.split_min = h->opts.split_min > 0 ? h->opts.split_min : 0;
+    if (h->opts.max_learnts > 0)
+        P.max_learnts_first = std::max(1, std::min(h->opts.max_learnts, P.learnt_refs_cap - h->D.n_vars - 2));
     return P;
 }
 
@@ -1623,5 +1632,15 @@ int gpsat_mesh_results_unpack(gpsat_t *h, const void *dev_block, int64_t words, 
 }
 
 int gpsat_handle_device(gpsat_t *h) { return h ? h->device : -1; }
+
+int gpsat_debug_words(gpsat_t *h, int32_t *out, int32_t n)
+{
+    if (!h || !out || n < 0 || n > GPSAT_DQC_WORDS) {
+        set_error("bad arguments");
+        return GPSAT_E_ARG;
+    }
+    std::memcpy(out, h->dq_ctrl_h, (size_t)n * sizeof(int32_t));
+    return GPSAT_OK;
+}
 
 }  // extern "C"

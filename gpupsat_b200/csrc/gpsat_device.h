@@ -35,8 +35,9 @@
 #define GPSAT_XCHG_MAGIC 0x47505358
 // Queue control block (dq_ctrl): word indices.  Every group sits on its own 128-byte line so that the ring tickets,
 // the job accounting and the words other GPUs write do not share a sector.
-#define GPSAT_DQC_TAIL 0          // push tickets
-#define GPSAT_DQC_HEAD 1          // pop tickets
+#define GPSAT_DQC_TAIL 0          // push tickets (fetch-add)
+#define GPSAT_DQC_HEAD 8          // pop tickets (fetch-add; a ticket is drawn only after a claim on AVAIL succeeded)
+#define GPSAT_DQC_AVAIL 16        // children published and not yet claimed (the semaphore consumers claim from)
 #define GPSAT_DQC_CREATED 32      // jobs created on this GPU: the root cubes it owns + the children it queued (monotonic)
 #define GPSAT_DQC_CLOSED 33       // jobs closed on this GPU, wherever they were created (monotonic)
 #define GPSAT_DQC_IDLE 64         // warps of this GPU with nothing to do
@@ -46,6 +47,8 @@
 #define GPSAT_DQC_STOP 68         // early-termination flag: 0 run, 1 SAT found, 2 external stop (≙ managed *state, main.cu:185)
 #define GPSAT_DQC_PUSHED 69       // pool slots already pushed to the peers (communication warp)
 #define GPSAT_DQC_REMOTE_TRIES 70 // remote pop attempts (diagnostics)
+#define GPSAT_DQC_HIST 72         // [16] children by floor(log2(conflicts + 1)) (diagnostics: how big are split-off cubes?)
+
 #define GPSAT_DQC_PEER_QUEUE 96   // [GPSAT_MESH_MAX_RANKS] children queued on rank r, written by r's communication warp
 #define GPSAT_DQC_PEER_IDLE 128   // [GPSAT_MESH_MAX_RANKS] unmet demand of rank r (idle warps - queued children), its share for us
 #define GPSAT_DQC_WORDS 160
@@ -92,6 +95,12 @@ struct gpsat_solve_params {
     int32_t split_gap;           // conflicts a job runs between two rounds of splitting
     int32_t split_burst;         // children handed out per round while warps are idle
     int32_t share_import_max;    // non-unit clauses a job takes from each shared pool when it starts (newest first)
+    int32_t split_gap_hot;       // gap while demand >= split_hot_demand (many idle warps: fill them fast)
+    int32_t split_hot_demand;    // demand from which the hot gap applies (1/8 of this GPU's warps)
+    int32_t split_at_start;      // 1: a cube may split before its first conflict while warps are idle
+    int32_t mesh_flags;          // test hooks: 1 no stealing, 2 no clause push
+    int32_t split_mode;          // 0 back to the cube + VSIDS-best, 1 guiding path (oldest open decision), 2 as 0 with sides swapped
+    int32_t split_min;           // hardness (own conflicts + inherited) a job needs before its first split
 };
 
 // word offsets (int32 units) of the per-warp state arrays inside one warp's state block
@@ -126,7 +135,7 @@ struct gpsat_run_buffers {
     int32_t formula_smem_words;    // size of that staging area (multiple of 4 words)
     // dynamic splitting: children of split cubes are queued here and popped by idle warps
     int32_t *dq_lits;              // dq_cap * GPSAT_DQ_MAXK
-    int32_t *dq_meta;              // dq_cap * 4 : (root cube, length, slot sequence number, -); sequence starts at the slot index
+    int32_t *dq_meta;              // dq_cap * 4 : (root cube, length, slot sequence number, inherited hardness); sequence starts at the slot index
     int32_t *dq_ctrl;              // GPSAT_DQC_* words
     int32_t *dq_hand;              // dq_cap * hand_words : per queued cube [n][vs 2n][records] (non-null when dynamic_split)
     int32_t hand_words;

@@ -77,7 +77,8 @@ __device__ __noinline__ void gpsat_comm_loop(const CommArgs B)
         if (peer_lane) {
             int want = idle - queued - inflight;   // warps here that would take a child right now
             want = want > 0 ? (want + R - 2) / (R - 1) : 0;
-            *(volatile int *)(pctrl + GPSAT_DQC_PEER_QUEUE + me) = queued > 0 ? queued : 0;
+            const int avail = *(volatile int *)(ctrl + GPSAT_DQC_AVAIL);   // published children nobody has claimed yet
+            *(volatile int *)(pctrl + GPSAT_DQC_PEER_QUEUE + me) = avail > 0 ? avail : 0;
             *(volatile int *)(pctrl + GPSAT_DQC_PEER_IDLE + me) = want;
         }
         // ---- learnt clauses published on this GPU since the last round -> every peer's foreign pool
@@ -227,7 +228,7 @@ gpsat_cdcl_kernel(const gpsat_formula_view F, const gpsat_solve_params P, const 
         CommArgs C;
         C.mesh_ranks = B.mesh_ranks;
         C.mesh_rank = B.mesh_rank;
-        C.share_learnts = P.share_learnts;
+        C.share_learnts = (P.mesh_flags & 2) ? 0 : P.share_learnts;
         C.pool_cap_words = B.pool_cap_words;
         C.xpool_cap_slots = B.xpool_cap_slots;
         C.mesh_n_vars = B.mesh_n_vars;

@@ -118,7 +118,16 @@ typedef struct gpsat_opts {
     int32_t split_burst;          /* children handed out per round while warps are idle; 0 = default (4) */
     int32_t share_import_max;     /* non-unit shared clauses a cube imports per pool when it starts; 0 = default (256) */
     int32_t split_hand_words;     /* learnt-clause words a split-off cube inherits from its parent; 0 = default */
-    int32_t reserved[3];
+    int32_t split_gap_hot;        /* gap used instead of split_gap while more than 1/8 of the GPU's warps are idle; 0 = split_gap / 2 */
+    int32_t split_at_start;       /* 1: a cube may split before its first conflict while more than 1/8 of the warps are idle
+                                     (default 0: measured slower on C2) */
+    int32_t mesh_flags;           /* test hooks: 1 = never take children of other GPUs, 2 = never push clauses to them */
+    int32_t split_mode;           /* 0 (default): back to the cube, branch on the VSIDS-best literal p, keep p, hand out ~p;
+                                     1: guiding path — hand out the untried side of the OLDEST open decision and keep searching
+                                     where the cube is; 2: as 0 but keep ~p (measured on C2: DESIGN.md section 3) */
+    int32_t max_learnts;          /* learnt clauses a job keeps before its first database reduction; 0 = default */
+    int32_t split_min;            /* a cube splits only once it has proved hard: conflicts (its own + half of what its parent
+                                     had when it was split off) before its first split; 0 = default */
 } gpsat_opts;
 
 void gpsat_opts_default(gpsat_opts *o);
@@ -260,6 +269,8 @@ int64_t gpsat_mesh_result_words(gpsat_t *h);
 int gpsat_mesh_results_pack(gpsat_t *h, void *dev_block, int64_t words);
 int gpsat_mesh_results_unpack(gpsat_t *h, const void *dev_block, int64_t words, int32_t *verdict, gpsat_stats *stats);
 int gpsat_handle_device(gpsat_t *h);
+/* diagnostics: the first n words of the queue control block as it was after the last launch (csrc/gpsat_device.h GPSAT_DQC_*) */
+int gpsat_debug_words(gpsat_t *h, int32_t *out, int32_t n);
 
 /* --- multi-GPU host in one process (≙ the host side of SATSolver/main.cu:197-310 for N GPUs; the reference drives one) ---
  * One host thread per GPU, the formula replicated, cube g -> GPU g mod N, the GPUs meshed as above; per-cube results are

@@ -23,7 +23,9 @@ class SolveParams(C.Structure):
                 ("share_learnts", C.c_int32), ("share_max_len", C.c_int32), ("max_learnts_first", C.c_int32),
                 ("learnt_refs_cap", C.c_int32), ("max_conflicts", C.c_int64), ("arena_words", C.c_int64),
                 ("implied_stride", C.c_int64), ("dynamic_split", C.c_int32), ("split_force", C.c_int32),
-                ("split_gap", C.c_int32), ("split_burst", C.c_int32), ("share_import_max", C.c_int32)]
+                ("split_gap", C.c_int32), ("split_burst", C.c_int32), ("share_import_max", C.c_int32),
+                ("split_gap_hot", C.c_int32), ("split_hot_demand", C.c_int32), ("split_at_start", C.c_int32),
+                ("mesh_flags", C.c_int32), ("split_mode", C.c_int32), ("split_min", C.c_int32)]
 
 
 def build(force=False):

@@ -77,7 +77,7 @@ def test_mesh_rank_without_cubes_steals_and_everything_closes():
     assert verdict == g.UNSAT
     assert len(rec) == len(cubes) and (rec["status"] == g.UNSAT).all()
     steals = [o[3]["steals"] for o in out]
-    assert steals[0] == 0 and steals[1] > 0
+    assert steals[1] > 0        # (rank 0 steals too: children of the cubes rank 1 took are queued on rank 1)
 
 
 @pytest.mark.parametrize("share", [0, 8])
