@@ -17,9 +17,10 @@ that instance: every cube is refuted by warp-per-cube CDCL (BCP + 1-UIP learning
   cpu_baseline  the reference's own solver classes built for the host (oracle/_ref) on a bounded sample of the same
              cubes (N=1, rank 0 only): one core as shipped, and cap-lifted with a per-cube timeout
 
-N > 1 (torchrun, one process per GPU): STRONG scaling on the SAME job set — the 4096 cubes of N=1, cube g -> rank
-g mod N — with the GPUs joined in a mesh over NVLink peer memory (include/gpsat.h gpsat_mesh_*): a solve is ONE
-persistent launch per GPU inside which idle warps take split-off cubes from the other GPUs' rings, short learnt clauses
+N > 1 (torchrun, one process per GPU): STRONG scaling on the SAME job set — the 4096 cubes of N=1 — with the GPUs
+joined in a mesh over NVLink peer memory (include/gpsat.h gpsat_mesh_*): a solve is ONE persistent launch per GPU
+inside which the cubes are handed out by one cursor that every GPU advances with atomics over NVLink, idle warps take
+split-off cubes from the other GPUs' rings, short learnt clauses
 are stored into the peers' pools and termination is detected; NCCL carries the IPC handles (one all-gather when the mesh
 is formed) and the all-reduces of the per-cube result block at the end.  GPSAT_BENCH_SCALING=weak gives every GPU its
 own 4096 cubes (k = 12 + log2 N over the same formula); GPSAT_BENCH_EXCHANGE=nccl runs the epoch loop with one NCCL
@@ -436,8 +437,11 @@ def run_ours(args):
 
     cnf, pre, cubes = make_workload(n_gpus)
     n_roots = len(cubes)
-    mine_idx = np.arange(rank, n_roots, n_gpus)
+    exchange_mesh = exchange == "mesh"
+    # mesh: every rank holds ALL cubes (one root cursor for the whole box); nccl epochs: static shard g mod N
+    mine_idx = np.arange(n_roots) if (exchange_mesh or n_gpus == 1) else np.arange(rank, n_roots, n_gpus)
     mine = cubes[mine_idx]
+    check_idx = np.arange(rank, n_roots, n_gpus)                 # the cubes this rank re-checks against the oracle
     offs, lits = pre.offsets, pre.lits
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -461,7 +465,7 @@ def run_ours(args):
         extra.setdefault("share_max_len", 2)
     solver = g.Solver(cnf.n_vars, offs, lits, device=local_rank, **extra)
     solver.set_cubes(mine)
-    block = mg.mesh_join(solver, dist, rank, n_gpus, dev, n_roots) if exchange == "mesh" else None
+    block = mg.mesh_join(solver, dist, rank, n_gpus, dev) if exchange == "mesh" else None
 
     xinfo = {"epochs": 0, "imported_clauses": 0, "exchange_bytes_per_epoch": 0}
 
@@ -509,7 +513,7 @@ def run_ours(args):
             t0 = time.perf_counter()
             s2 = g.Solver(cnf.n_vars, offs, lits, device=local_rank, **extra)
             s2.set_cubes(mine)
-            b2 = mg.mesh_join(s2, dist, rank, n_gpus, dev, n_roots) if exchange == "mesh" else None
+            b2 = mg.mesh_join(s2, dist, rank, n_gpus, dev) if exchange == "mesh" else None
             _ms2, st2, v2 = run_one(s2, b2)
             s2.close()
             torch.cuda.synchronize()
@@ -550,7 +554,7 @@ def run_ours(args):
         glob_rec = np.zeros(n_roots, dtype=g.RECORD_DTYPE)
         glob_rec["status"] = full.cpu().numpy()
         last_records = glob_rec
-    parity = parity_check(g, pre, cubes, mine_idx, last_records, verdict, n_gpus, rank, local_rank, extra, dist, dev)
+    parity = parity_check(g, pre, cubes, check_idx, last_records, verdict, n_gpus, rank, local_rank, extra, dist, dev)
 
     if rank == 0:
         peak, peak_src = load_peaks()

@@ -30,7 +30,7 @@ class GpsatOpts(C.Structure):
                 ("arena_words", C.c_int64), ("dynamic_split", C.c_int32), ("split_gap", C.c_int32),
                 ("split_burst", C.c_int32), ("share_import_max", C.c_int32), ("split_hand_words", C.c_int32),
                 ("split_gap_hot", C.c_int32), ("split_at_start", C.c_int32), ("mesh_flags", C.c_int32),
-                ("split_mode", C.c_int32), ("max_learnts", C.c_int32), ("split_min", C.c_int32)]
+                ("split_mode", C.c_int32), ("max_learnts", C.c_int32), ("split_min", C.c_int32), ("split_hard", C.c_int32)]
 
 
 class GpsatStats(C.Structure):
@@ -104,8 +104,8 @@ def lib():
     L.gpsat_debug_ctrl.argtypes = [vp, vp]
     L.gpsat_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.gpsat_mesh_export.argtypes = [vp, vp]
-    L.gpsat_mesh_attach_ipc.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32]
-    L.gpsat_mesh_attach_local.argtypes = [C.POINTER(vp), i32, i32, vp]
+    L.gpsat_mesh_attach_ipc.argtypes = [vp, i32, i32, vp]
+    L.gpsat_mesh_attach_local.argtypes = [C.POINTER(vp), i32]
     L.gpsat_mesh_detach.argtypes = [vp]
     L.gpsat_mesh_result_words.argtypes = [vp]
     L.gpsat_mesh_result_words.restype = i64
@@ -307,7 +307,7 @@ class Solver:
         return float(lib().gpsat_last_kernel_ms(self.h))
 
     def job_records(self, n=None):
-        n = self.n_cubes if n is None else n      # a mesh rank holds records of ALL cubes of all ranks (n = n_roots)
+        n = self.n_cubes if n is None else n
         rec = np.zeros(n, dtype=RECORD_DTYPE)
         _check(lib().gpsat_job_records(self.h, _p(rec), n))
         return rec
@@ -318,11 +318,10 @@ class Solver:
         _check(lib().gpsat_mesh_export(self.h, _p(buf)))
         return buf
 
-    def mesh_attach_ipc(self, n_ranks, rank, handles, n_roots, root_first, root_stride, n_local):
+    def mesh_attach_ipc(self, n_ranks, rank, handles):
         handles = np.ascontiguousarray(handles, dtype=np.uint8).reshape(-1)
         assert handles.size == 64 * n_ranks
-        _check(lib().gpsat_mesh_attach_ipc(self.h, n_ranks, rank, _p(handles), n_roots, root_first, root_stride, n_local))
-        self.n_roots = n_roots
+        _check(lib().gpsat_mesh_attach_ipc(self.h, n_ranks, rank, _p(handles)))
 
     def mesh_detach(self):
         _check(lib().gpsat_mesh_detach(self.h))
@@ -398,13 +397,10 @@ class Solver:
                 "imported_clauses": imported.value, "jobs_done": jobs.value}
 
 
-def mesh_attach_local(solvers, n_roots, n_local=None):
-    """In-process mesh over `solvers` (rank r = solvers[r]; cube g of the n_roots cubes belongs to rank g mod len)."""
+def mesh_attach_local(solvers):
+    """In-process mesh over `solvers` (rank r = solvers[r]); every solver holds the same, complete cube list."""
     arr = (C.c_void_p * len(solvers))(*[s.h for s in solvers])
-    nl = None if n_local is None else np.ascontiguousarray(n_local, dtype=np.int32)
-    _check(lib().gpsat_mesh_attach_local(arr, len(solvers), n_roots, _p(nl)))
-    for s in solvers:
-        s.n_roots = n_roots
+    _check(lib().gpsat_mesh_attach_local(arr, len(solvers)))
 
 
 class MultiSolver:

@@ -67,10 +67,18 @@ struct WarpSolver {
     float restart_factor;
     long long max_conflicts;
     // dynamic splitting
-    int dynamic_split, split_force, split_gap, split_burst, split_gap_hot, split_hot_demand, split_at_start, split_mode, split_min, inherited, root;
+    int dynamic_split, split_force, split_gap, split_burst, split_gap_hot, split_hot_demand, split_at_start, split_mode, split_min, split_hard, inherited, root;
     int *dq_lits, *dq_meta, *dq_ctrl, *root_pending, *dq_hand;
     int hand_words, dq_cap;
     int rel_slot, rel_seq;                 // queue slot this job was popped from (released once its content is consumed)
+    int *rel_meta;                         // ... and the ring it belongs to
+#if defined(GPSAT_PHASE_CLOCKS)
+    long long ph[6];                       // ns in: reset, import, propagate, analyze+learn, split, reduce_db
+    int stolen;
+#define GPSAT_PH(i, stmt) { const unsigned long long t_ph = gpsat_now_ns(); stmt; ph[i] += (long long)(gpsat_now_ns() - t_ph); }
+#else
+#define GPSAT_PH(i, stmt) { stmt; }
+#endif
     int mesh_ranks;                        // > 1: other GPUs pop from this GPU's ring (system-scope fences / atomics)
     const unsigned long long *t0;          // budgeted steps: jobs park themselves once now > *t0 + budget_ns
     unsigned long long budget_ns;
@@ -1146,7 +1154,7 @@ struct WarpSolver {
         GPSAT_LANE_DECL
         if (rel_slot < 0) return;
         gpsat_threadfence();
-        LANE0 { ((volatile int *)dq_meta)[4 * rel_slot + 2] = rel_seq; }
+        LANE0 { ((volatile int *)rel_meta)[4 * rel_slot + 2] = rel_seq; }
         SYNCWARP();
         rel_slot = -1;
     }
@@ -1229,7 +1237,7 @@ struct WarpSolver {
     {
         GPSAT_LANE_DECL
         conflict_out = GPSAT_NO_CONFLICT;
-        reset_job(resume);
+        GPSAT_PH(0, reset_job(resume))
         if (resume) {   // parked by this warp at the end of the previous step (see park_job)
             n_learnts = park[4];
             arena_top = park[5];
@@ -1263,6 +1271,7 @@ struct WarpSolver {
         const bool may_split = queued_ok && k + 1 < GPSAT_DQ_MAXK;
         int want_split = 0, burst = 0;
         int at_start = (may_split && split_at_start && !resume) ? 1 : 0;
+        int hard_start = (may_split && !resume && inherited >= split_hard) ? 1 : 0;
         long long last_split_at = 0;
         if (queued_ok) {   // the cube may grow (splits) or be parked (budgeted steps): work on a private copy
             LANES
@@ -1284,7 +1293,8 @@ struct WarpSolver {
                 for (int x = lane; x < 2 * n_vars; x += 32) vs[x] = gpsat_ld_cg(hand + 1 + x);
             }
             SYNCWARP();
-            const int st = import_stream(hand + 1 + 2 * n_vars, 0, gpsat_ld_cg(hand), 0);
+            int st;
+            GPSAT_PH(1, st = import_stream(hand + 1 + 2 * n_vars, 0, gpsat_ld_cg(hand), 0))
             release_slot();
             if (st != GPSAT_UNDEF) return st;
         }
@@ -1293,7 +1303,8 @@ struct WarpSolver {
             if (st != GPSAT_UNDEF) return st;
         }
         while (true) {
-            const int confl = propagate();
+            int confl;
+            GPSAT_PH(2, confl = propagate())
             if (oom) return GPSAT_JOB_OOM;
             if (confl != GPSAT_NO_CONFLICT) {
                 conflict_out = confl;
@@ -1301,7 +1312,8 @@ struct WarpSolver {
                 conflicts_since_restart++;
                 if (dlevel == 0 || mode == GPSAT_MODE_PROPAGATE) return GPSAT_UNSAT;
                 int bt;
-                const int n_out = analyze(confl, bt);
+                int n_out;
+                GPSAT_PH(3, n_out = analyze(confl, bt))
                 hash_learnt(n_out);
                 c_learnt_clauses++;
                 c_learnt_literals += n_out;
@@ -1329,7 +1341,12 @@ struct WarpSolver {
                         }
                     }
                 }
-                if (may_split && !want_split && c_conflicts - last_split_at >= split_gap_hot &&
+                if (may_split && !want_split && inherited + c_conflicts >= split_hard) {
+                    if (demand_hint() > 0) {   // a very hard cube: every conflict is a chance to hand work out
+                        want_split = 1;
+                        burst = 0;
+                    }
+                } else if (may_split && !want_split && c_conflicts - last_split_at >= split_gap_hot &&
                     inherited + c_conflicts >= split_min) {
                     // a cube splits once it has proved hard (split_min), then every split_gap conflicts while warps are
                     // idle — every split_gap_hot conflicts while more than 1/8 of the GPU's warps are idle (start and tail)
@@ -1355,11 +1372,18 @@ struct WarpSolver {
                     want_split = 1;
                     burst = 0;
                 }
+            } else if (hard_start && dlevel >= k) {   // split off a very hard cube: pass work on before searching
+                hard_start = 0;
+                if (demand_hint() > 0) {
+                    want_split = 1;
+                    burst = 0;
+                }
             }
             if (want_split && dlevel >= k) {   // an idle warp is waiting: give it half of what is left
                 want_split = 0;
                 if (split_mode != 1 || dlevel == k) cancel_until(k);
-                const int k2 = try_split(k);
+                int k2;
+                GPSAT_PH(4, k2 = try_split(k))
                 if (k2 != k) {
                     // while warps are still idle keep peeling children off (cube+~p1, cube+p1+~p2, ...): the
                     // number of busy warps then grows by split_burst per gap instead of doubling
@@ -1369,7 +1393,7 @@ struct WarpSolver {
                 k = k2;
             }
             if (use_learnts && (n_learnts >= max_learnts || (watch_bot - arena_top) < (arena_words - clause_base) / 4)) {
-                reduce_db();
+                GPSAT_PH(5, reduce_db())
                 if (oom) return GPSAT_JOB_OOM;
             }
             int next = -1;
@@ -1443,6 +1467,7 @@ GPSAT_DEV void gpsat_bind(WarpSolver &S, const gpsat_formula_view &F, const gpsa
     S.split_at_start = P.split_at_start;
     S.split_mode = P.split_mode;
     S.split_min = P.split_min;
+    S.split_hard = P.split_hard > 0 ? P.split_hard : 0x7fffffff;
     S.inherited = 0;
     S.root = 0;
     S.dq_lits = B.dq_lits;
@@ -1455,6 +1480,11 @@ GPSAT_DEV void gpsat_bind(WarpSolver &S, const gpsat_formula_view &F, const gpsa
     S.mesh_ranks = B.mesh_ranks > 1 ? B.mesh_ranks : 0;
     S.rel_slot = -1;
     S.rel_seq = 0;
+    S.rel_meta = B.dq_meta;
+#if defined(GPSAT_PHASE_CLOCKS)
+    for (int i = 0; i < 6; ++i) S.ph[i] = 0;
+    S.stolen = 0;
+#endif
     S.t0 = B.t0;
     S.budget_ns = B.budget_ns;
     S.use_learnts = (P.mode == GPSAT_MODE_SOLVE) ? 1 : 0;
@@ -1592,6 +1622,13 @@ GPSAT_DEV void gpsat_run_and_record(WarpSolver &S, int root, const int *cube, in
         if (status != GPSAT_JOB_SUSPENDED) {
             gpsat_atomic_add(B.root_pending + job, -1);
             gpsat_atomic_add(B.dq_ctrl + GPSAT_DQC_CLOSED, 1);
+#if defined(GPSAT_PHASE_CLOCKS)
+            for (int i = 0; i < 6; ++i) {   // words 104..115: jobs taken on this rank; 116..127: jobs taken from another rank
+                gpsat_atomic_add_ll((long long *)(B.dq_ctrl + (S.stolen ? 116 : 104) + 2 * i), S.ph[i]);
+                S.ph[i] = 0;
+            }
+            if (S.stolen) gpsat_atomic_add(B.dq_ctrl + 71, (int)S.c_conflicts);
+#endif
             if (hand != nullptr) {   // size of a split-off cube, in conflicts (diagnostics)
                 int b = 0;
                 GPSAT_NOUNROLL
@@ -1655,14 +1692,20 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
             } else if (S.park != nullptr && gpsat_ld_volatile(S.park) == 1) {
                 kind = 4;   // this warp parked a job at the end of the previous step
             } else {
-                if (gpsat_ld_volatile(B.next_job) < B.n_cubes) {
-                    idx = gpsat_atomic_add(B.next_job, 1);
+                // root cubes: ONE cursor for all GPUs of a mesh (rank 0's, over NVLink) — whichever warp of whichever GPU is
+                // free takes the next cube, so no GPU sits on unstarted cubes while another splits running ones
+                if (gpsat_ld_volatile(B.dq_ctrl + GPSAT_DQC_ROOTS_DONE) == 0) {
+                    idx = mesh ? gpsat_atomic_add_sys(B.next_job, 1) : gpsat_atomic_add(B.next_job, 1);
                     if (idx < B.n_cubes) kind = 1;
+                    else ((volatile int *)B.dq_ctrl)[GPSAT_DQC_ROOTS_DONE] = 1;
                 }
                 if (kind == 3 && P.mode == GPSAT_MODE_SOLVE && P.dynamic_split) {
                     idx = gpsat_ring_pop(B.dq_ctrl, B.dq_meta, B.dq_cap, mesh);
                     if (idx >= 0) kind = 2;
-                    if (kind == 3 && mesh && stage != nullptr && !(P.mesh_flags & 1)) {
+                    // ... but only once this GPU is running dry (more than 1/8 of its warps idle): a warp that merely found
+                    // its own ring empty for a moment gets a local child within microseconds
+                    if (kind == 3 && mesh && stage != nullptr && !(P.mesh_flags & 1) &&
+                        ((P.mesh_flags & 32) || gpsat_ld_volatile(B.dq_ctrl + GPSAT_DQC_IDLE) >= P.split_hot_demand)) {
                         // children advertised by the other GPUs (their communication warps refresh PEER_QUEUE): claim one
                         // locally first, so that at most as many warps go out over NVLink as there are children to take
                         GPSAT_NOUNROLL
@@ -1673,6 +1716,7 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
                             int *rctrl = (int *)(B.mesh_base[r] + B.mesh_off_ctrl);
                             int *rmeta = (int *)(B.mesh_base[r] + B.mesh_off_meta);
                             gpsat_atomic_add(B.dq_ctrl + GPSAT_DQC_REMOTE_TRIES, 1);
+                            if (P.mesh_flags & 16) continue;   // experiment: claim only
                             idx = gpsat_ring_pop(rctrl, rmeta, B.dq_cap, true);
                             if (idx >= 0) {
                                 kind = 5;
@@ -1724,7 +1768,7 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
         } else if (kind == 1) {
             const long long c0 = B.cube_offsets[idx], c1 = B.cube_offsets[idx + 1];
             S.inherited = 0;
-            gpsat_run_and_record(S, B.root_first + idx * B.root_stride, B.cube_lits + c0, (int)(c1 - c0), nullptr, P, B);
+            gpsat_run_and_record(S, idx, B.cube_lits + c0, (int)(c1 - c0), nullptr, P, B);
         } else if (kind == 2) {
             const int slot = idx & (B.dq_cap - 1);
             gpsat_threadfence();
@@ -1734,6 +1778,7 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
             const int *hand = B.dq_hand + (long long)slot * B.hand_words;
             S.rel_slot = slot;
             S.rel_seq = idx + B.dq_cap;   // the ticket that may write this slot next
+            S.rel_meta = B.dq_meta;
             gpsat_run_and_record(S, root, B.dq_lits + (long long)slot * GPSAT_DQ_MAXK, len, hand, P, B);
         } else {
             // a child queued on GPU `peer`: copy its cube and hand-off block over NVLink into this warp's staging block
@@ -1744,19 +1789,31 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
             int *rmeta = (int *)(B.mesh_base[peer] + B.mesh_off_meta);
             const int *rlits = (const int *)(B.mesh_base[peer] + B.mesh_off_lits) + (long long)slot * GPSAT_DQ_MAXK;
             const int *rhand = (const int *)(B.mesh_base[peer] + B.mesh_off_hand) + (long long)slot * B.hand_words;
-            gpsat_threadfence_sys();
+            if (P.mesh_flags & 4) gpsat_threadfence(); else gpsat_threadfence_sys();
             const int root = gpsat_ld_cg(rmeta + 4 * slot);
             const int len = gpsat_ld_cg(rmeta + 4 * slot + 1);
             S.inherited = gpsat_ld_cg(rmeta + 4 * slot + 3);
             int used = gpsat_ld_cg(rhand);
             if (used < 0 || used > B.hand_words - 1 - 2 * S.n_vars) used = 0;
+#if defined(GPSAT_PHASE_CLOCKS)
+            S.stolen = 1;
+#endif
+            if (P.mesh_flags & 8) {   // experiment: run straight from the other rank's slot, like a local pop
+                S.rel_slot = slot;
+                S.rel_seq = idx + B.dq_cap;
+                S.rel_meta = rmeta;
+                LANE0 { gpsat_atomic_add(B.dq_ctrl + GPSAT_DQC_STEALS, 1); }
+                gpsat_run_and_record(S, root, rlits, len, rhand, P, B);
+                busy_ns += gpsat_now_ns() - t_job;
+                continue;
+            }
             LANES
             {
                 gpsat_copy_cg(stage, rhand, 1 + 2 * S.n_vars + used, lane);
                 gpsat_copy_cg(stage + B.hand_words, rlits, GPSAT_DQ_MAXK, lane);
             }
             SYNCWARP();
-            gpsat_threadfence_sys();
+            if (P.mesh_flags & 4) gpsat_threadfence(); else gpsat_threadfence_sys();
             LANE0
             {
                 ((volatile int *)rmeta)[4 * slot + 2] = idx + B.dq_cap;   // the remote slot is free again
@@ -1765,6 +1822,9 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
             SYNCWARP();
             gpsat_run_and_record(S, root, stage + B.hand_words, len, stage, P, B);
         }
+#if defined(GPSAT_PHASE_CLOCKS)
+        S.stolen = 0;
+#endif
         busy_ns += gpsat_now_ns() - t_job;
     }
     LANE0

@@ -173,8 +173,6 @@ struct gpsat {
     // mesh (several GPUs as one work pool)
     int32_t mesh_ranks = 1, mesh_rank = 0;
     char *mesh_base[GPSAT_MESH_MAX_RANKS] = {nullptr};
-    int32_t n_roots = 0, root_first = 0, root_stride = 1;   // records / root_* arrays cover all cubes of all ranks
-    bool mesh_zero_local = false;      // this rank owns no root cube (it only takes children of other GPUs)
     std::vector<int32_t> root_pending_h, root_flag_h;
     int32_t dq_ctrl_h[GPSAT_DQC_WORDS] = {0};   // control block after the last launch
     DevBuf<int32_t> arena;
@@ -317,6 +315,7 @@ gpsat_solve_params make_params(gpsat *h, int mode, int64_t implied_stride)
     P.mesh_flags = h->opts.mesh_flags;
     P.split_mode = h->opts.split_mode;
     P.split_min = h->opts.split_min > 0 ? h->opts.split_min : 0;
+    P.split_hard = h->opts.split_hard > 0 ? h->opts.split_hard : 0x7fffffff;
     if (h->opts.max_learnts > 0)
         P.max_learnts_first = std::max(1, std::min(h->opts.max_learnts, P.learnt_refs_cap - h->D.n_vars - 2));
     return P;
@@ -385,7 +384,7 @@ int plan_geometry(gpsat *h, int mode)
     return GPSAT_OK;
 }
 
-int32_t roots_of(const gpsat *h) { return h->mesh_ranks > 1 ? h->n_roots : std::max(h->n_cubes, 1); }
+int32_t roots_of(const gpsat *h) { return std::max(h->n_cubes, 1); }   // every rank of a mesh holds ALL cubes
 
 int ensure_run_buffers(gpsat *h, int mode)
 {
@@ -419,8 +418,9 @@ gpsat_run_buffers make_buffers(gpsat *h, int mode, double budget_ms)
     const bool split = mode == GPSAT_MODE_SOLVE && h->opts.dynamic_split && h->region_full;
     B.cube_offsets = h->cube_offsets.p;
     B.cube_lits = h->cube_lits.p;
-    B.n_cubes = h->mesh_zero_local ? 0 : h->n_cubes;
-    B.next_job = h->ctrl.p + 0;
+    B.n_cubes = h->n_cubes;
+    // the root cursor: this handle's control block, or — mesh — rank 0's, which every GPU advances over NVLink
+    B.next_job = (mode == GPSAT_MODE_SOLVE && h->mesh_ranks > 1 ? (int32_t *)(h->mesh_base[0] + h->ML.ctrl) : dq_ctrl(h)) + GPSAT_DQC_CURSOR;
     B.stop_flag = dq_ctrl(h) + GPSAT_DQC_STOP;
     B.sat_job = h->ctrl.p + 2;
     B.model = h->model.p;
@@ -460,9 +460,6 @@ gpsat_run_buffers make_buffers(gpsat *h, int mode, double budget_ms)
     B.mesh_off_xpool = h->ML.xpool;
     B.mesh_off_facts = h->ML.facts;
     B.stage = (split && h->mesh_ranks > 1) ? h->stage.p : nullptr;
-    B.root_first = h->mesh_ranks > 1 ? h->root_first : 0;
-    B.root_stride = h->mesh_ranks > 1 ? h->root_stride : 1;
-    B.n_roots = roots_of(h);
     B.xpool_cap_slots = (int32_t)kPoolSlots;
     B.mesh_n_vars = h->D.n_vars;
     return B;
@@ -472,12 +469,11 @@ gpsat_run_buffers make_buffers(gpsat *h, int mode, double budget_ms)
 int reset_ctrl(gpsat *h)
 {
     const size_t nr = (size_t)roots_of(h);
-    const int n_local = h->mesh_zero_local ? 0 : h->n_cubes;
     CU(cudaMemsetAsync(h->records.p, 0, nr * sizeof(gpsat_job_record), h->stream));
     if (h->park.p) CU(cudaMemsetAsync(h->park.p, 0, h->park.n * sizeof(int32_t), h->stream));
     CU(gpsat_kernels::launch_queue_init(dq_ctrl(h), h->region_full ? region_i32(h, h->ML.meta) : nullptr, GPSAT_DQ_CAP,
-                                        h->root_pending.p, h->root_flag.p, (int)nr, h->mesh_ranks > 1 ? h->root_first : 0,
-                                        h->mesh_ranks > 1 ? h->root_stride : 1, n_local, xpool_cursor(h), facts(h),
+                                        h->root_pending.p, h->root_flag.p, (int)nr,
+                                        (h->mesh_ranks > 1 && h->mesh_rank != 0) ? 0 : 1, xpool_cursor(h), facts(h),
                                         h->D.n_vars, h->ctrl.p, h->t0.p, h->stream));
     if (h->region_full && (h->opts.share_learnts || h->mesh_ranks > 1))   // foreign slots must read "empty" (length 0)
         CU(cudaMemsetAsync(xpool(h), 0, (size_t)kPoolWords * sizeof(int32_t), h->stream));
@@ -957,7 +953,6 @@ int gpsat_set_cubes(gpsat_t *h, int32_t n_cubes, const int64_t *cube_offsets, co
     DeviceGuard guard(h->device);
     h->cube_lits_sorted.release();
     h->cube_short.release();
-    h->mesh_zero_local = false;
     if (n_cubes == 0) {
         h->n_cubes = 1;
         h->cube_offsets_h.assign(2, 0);
@@ -1396,6 +1391,7 @@ int gpsat_debug_ctrl(gpsat_t *h, int32_t *out16)
         out16[10] = c[GPSAT_DQC_STEALS];
         out16[11] = c[GPSAT_DQC_STOP];
         out16[1] = c[GPSAT_DQC_STOP];
+        out16[0] = c[GPSAT_DQC_CURSOR];
     }
     unsigned long long t[2] = {0, 0};
     CU(cudaMemcpy(t, h->t0.p, sizeof(t), cudaMemcpyDeviceToHost));
@@ -1443,33 +1439,18 @@ int mesh_prepare(gpsat *h)
     return ensure_region(h, true);
 }
 
-int mesh_set(gpsat *h, int32_t n_ranks, int32_t rank, char *const *bases, int32_t n_roots, int32_t root_first,
-             int32_t root_stride, int32_t n_local)
+int mesh_set(gpsat *h, int32_t n_ranks, int32_t rank, char *const *bases)
 {
-    if (n_ranks < 1 || n_ranks > GPSAT_MESH_MAX_RANKS || rank < 0 || rank >= n_ranks || n_roots < 1 || root_stride < 1 ||
-        n_local < 0 || (n_local > 0 && (int64_t)root_first + (int64_t)(n_local - 1) * root_stride >= n_roots)) {
+    if (n_ranks < 1 || n_ranks > GPSAT_MESH_MAX_RANKS || rank < 0 || rank >= n_ranks) {
         set_error("bad mesh arguments");
         return GPSAT_E_ARG;
     }
-    if (n_local > 0 && (!h->cubes_set || h->n_cubes != n_local)) {
-        set_error("mesh: n_local differs from the cubes set on this handle");
-        return GPSAT_E_STATE;
-    }
+    int rc = h->cubes_set ? GPSAT_OK : gpsat_set_cubes(h, 0, nullptr, nullptr);
+    if (rc != GPSAT_OK) return rc;
     h->mesh_ranks = n_ranks;
     h->mesh_rank = rank;
     for (int r = 0; r < GPSAT_MESH_MAX_RANKS; r++) h->mesh_base[r] = r < n_ranks ? bases[r] : nullptr;
     h->mesh_base[rank] = h->region.p;
-    h->n_roots = n_roots;
-    h->root_first = root_first;
-    h->root_stride = root_stride;
-    h->mesh_zero_local = n_local == 0;
-    if (n_local == 0) {
-        h->n_cubes = 1;   // the job list stays the default empty cube, but the kernel is told that this rank owns none
-        h->cube_offsets_h.assign(2, 0);
-        CU(h->cube_offsets.upload(h->cube_offsets_h.data(), h->cube_offsets_h.size(), h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        h->cubes_set = true;
-    }
     h->records_h.clear();
     return GPSAT_OK;
 }
@@ -1491,8 +1472,7 @@ int gpsat_mesh_export(gpsat_t *h, void *ipc_handle)
     return GPSAT_OK;
 }
 
-int gpsat_mesh_attach_ipc(gpsat_t *h, int32_t n_ranks, int32_t rank, const void *ipc_handles, int32_t n_roots,
-                          int32_t root_first, int32_t root_stride, int32_t n_local)
+int gpsat_mesh_attach_ipc(gpsat_t *h, int32_t n_ranks, int32_t rank, const void *ipc_handles)
 {
     if (!h || !ipc_handles || n_ranks < 1 || n_ranks > GPSAT_MESH_MAX_RANKS || rank < 0 || rank >= n_ranks) {
         set_error("bad arguments");
@@ -1520,10 +1500,10 @@ int gpsat_mesh_attach_ipc(gpsat_t *h, int32_t n_ranks, int32_t rank, const void 
         }
         bases[r] = (char *)p;
     }
-    return mesh_set(h, n_ranks, rank, bases, n_roots, root_first, root_stride, n_local);
+    return mesh_set(h, n_ranks, rank, bases);
 }
 
-int gpsat_mesh_attach_local(gpsat_t *const *handles, int32_t n_ranks, int32_t n_roots, const int32_t *n_local)
+int gpsat_mesh_attach_local(gpsat_t *const *handles, int32_t n_ranks)
 {
     if (!handles || n_ranks < 1 || n_ranks > GPSAT_MESH_MAX_RANKS) {
         set_error("bad arguments");
@@ -1559,16 +1539,11 @@ int gpsat_mesh_attach_local(gpsat_t *const *handles, int32_t n_ranks, int32_t n_
             if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
             cudaGetLastError();
         }
-        // shards: interleaved (cube g -> rank g mod N), or — explicit sizes — contiguous ranges in rank order
-        int32_t nl = (n_roots - r + n_ranks - 1) / n_ranks, first = r, stride = n_ranks;
-        if (n_local) {
-            nl = n_local[r];
-            stride = 1;
-            first = 0;
-            for (int q = 0; q < r; q++) first += n_local[q];
+        if (handles[r]->n_cubes != handles[0]->n_cubes) {
+            set_error("mesh: every handle must hold the same (complete) cube list");
+            return GPSAT_E_ARG;
         }
-        if (nl < 0) nl = 0;
-        int rc = mesh_set(handles[r], n_ranks, r, bases, n_roots, nl > 0 ? first : 0, stride, nl);
+        int rc = mesh_set(handles[r], n_ranks, r, bases);
         if (rc != GPSAT_OK) return rc;
     }
     return GPSAT_OK;
@@ -1582,10 +1557,6 @@ int gpsat_mesh_detach(gpsat_t *h)
     }
     h->mesh_ranks = 1;
     h->mesh_rank = 0;
-    h->mesh_zero_local = false;
-    h->n_roots = 0;
-    h->root_first = 0;
-    h->root_stride = 1;
     h->records_h.clear();
     return GPSAT_OK;
 }

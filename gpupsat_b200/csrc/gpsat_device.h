@@ -38,6 +38,8 @@
 #define GPSAT_DQC_TAIL 0          // push tickets (fetch-add)
 #define GPSAT_DQC_HEAD 8          // pop tickets (fetch-add; a ticket is drawn only after a claim on AVAIL succeeded)
 #define GPSAT_DQC_AVAIL 16        // children published and not yet claimed (the semaphore consumers claim from)
+#define GPSAT_DQC_CURSOR 24       // next root cube (≙ JobsQueue::next_job_index, SATSolver/JobsQueue.cu:16); mesh: rank 0's is THE cursor of all GPUs
+#define GPSAT_DQC_ROOTS_DONE 25   // this GPU has seen the cursor run past the last root cube (no more remote fetches)
 #define GPSAT_DQC_CREATED 32      // jobs created on this GPU: the root cubes it owns + the children it queued (monotonic)
 #define GPSAT_DQC_CLOSED 33       // jobs closed on this GPU, wherever they were created (monotonic)
 #define GPSAT_DQC_IDLE 64         // warps of this GPU with nothing to do
@@ -101,6 +103,7 @@ struct gpsat_solve_params {
     int32_t mesh_flags;          // test hooks: 1 no stealing, 2 no clause push
     int32_t split_mode;          // 0 back to the cube + VSIDS-best, 1 guiding path (oldest open decision), 2 as 0 with sides swapped
     int32_t split_min;           // hardness (own conflicts + inherited) a job needs before its first split
+    int32_t split_hard;          // hardness from which a job splits after every conflict and at its start (0x7fffffff = never)
 };
 
 // word offsets (int32 units) of the per-warp state arrays inside one warp's state block
@@ -154,8 +157,6 @@ struct gpsat_run_buffers {
     char *mesh_base[GPSAT_MESH_MAX_RANKS];
     int64_t mesh_off_ctrl, mesh_off_meta, mesh_off_lits, mesh_off_hand, mesh_off_xcur, mesh_off_xpool, mesh_off_facts;
     int32_t *stage;                   // n_warps * hand_words: local copy of a hand-off block popped from another GPU
-    int32_t root_first, root_stride;  // global index of local cube i = root_first + i * root_stride (records / root_* arrays)
-    int32_t n_roots;                  // entries of records / root_pending / root_flag (all cubes of all ranks)
     int32_t xpool_cap_slots;
     int32_t mesh_n_vars;
 };

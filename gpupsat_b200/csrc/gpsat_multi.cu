@@ -1,6 +1,6 @@
 // Multi-GPU host in ONE process (include/gpsat.h: gpsat_multi_*): the N-GPU form of what SATSolver/main.cu:197-310
-// does for one GPU.  One gpsat handle and one host thread per GPU; the formula is replicated, cube g belongs to GPU
-// g mod N, and the handles are joined in a mesh (gpsat_mesh_attach_local) so that the GPUs behave as one work pool over
+// does for one GPU.  One gpsat handle and one host thread per GPU; formula and cube list are replicated,
+// and the handles are joined in a mesh (gpsat_mesh_attach_local) so that the GPUs behave as one work pool over
 // NVLink peer memory.  A solve is ONE persistent launch per GPU; afterwards the per-cube outcome flags / open-descendant
 // counts / records of the ranks are reduced with ncclAllReduce (MAX, SUM, SUM).  libnccl is loaded at run time with
 // dlopen, so that libgpsat.so itself carries no NCCL dependency and a process that also loads torch's NCCL sees one
@@ -170,23 +170,14 @@ int gpsat_multi_set_cubes(gpsat_multi_t *m, int32_t n_cubes, const int64_t *cube
         set_error("bad arguments");
         return GPSAT_E_ARG;
     }
-    // n_cubes = 0: the single empty cube (the reference's sequential mode), owned by GPU 0; the others only steal
+    // every GPU holds the complete cube list; the mesh hands the cubes out through ONE cursor.  n_cubes = 0: the single
+    // empty cube (the reference's sequential mode) — one GPU takes it, the others live off the cubes it splits off
     const int32_t total = std::max(n_cubes, 1);
-    std::vector<int32_t> n_local((size_t)m->n, 0);
     for (int r = 0; r < m->n; r++) {
-        std::vector<int64_t> offs(1, 0);
-        std::vector<int32_t> ls;
-        for (int32_t g = r; g < n_cubes; g += m->n) {
-            ls.insert(ls.end(), cube_lits + cube_offsets[g], cube_lits + cube_offsets[g + 1]);
-            offs.push_back((int64_t)ls.size());
-        }
-        n_local[(size_t)r] = n_cubes == 0 ? (r == 0 ? 1 : 0) : (int32_t)offs.size() - 1;
-        int rc = GPSAT_OK;
-        if (n_cubes == 0) rc = r == 0 ? gpsat_set_cubes(m->h[r], 0, nullptr, nullptr) : GPSAT_OK;
-        else if (offs.size() > 1) rc = gpsat_set_cubes(m->h[r], (int32_t)offs.size() - 1, offs.data(), ls.data());
+        int rc = gpsat_set_cubes(m->h[r], n_cubes, cube_offsets, cube_lits);
         if (rc != GPSAT_OK) return rc;
     }
-    int rc = gpsat_mesh_attach_local(m->h.data(), m->n, total, nullptr);   // interleaved shards, as built above
+    int rc = gpsat_mesh_attach_local(m->h.data(), m->n);
     if (rc != GPSAT_OK) return rc;
     m->n_cubes = total;
     m->cubes_set = true;

@@ -150,12 +150,13 @@ __device__ __noinline__ void gpsat_comm_loop(const CommArgs B)
 // Queue state of a solve, initialised on the device (one small launch instead of several pageable H2D copies):
 // ring slots empty (sequence number = slot index), control block, one open job per root cube this rank owns.
 __global__ void __launch_bounds__(256)
-gpsat_queue_init_kernel(int *ctrl, int *meta, int dq_cap, int *root_pending, int *root_flag, int n_roots, int root_first,
-                        int root_stride, int n_local, int *xcur, unsigned char *facts, int n_vars, int *run_ctrl,
-                        unsigned long long *t0)
+gpsat_queue_init_kernel(int *ctrl, int *meta, int dq_cap, int *root_pending, int *root_flag, int n_roots, int owner,
+                        int *xcur, unsigned char *facts, int n_vars, int *run_ctrl, unsigned long long *t0)
 {
+    // owner: this rank's control block holds the root cursor of the run (single GPU, or rank 0 of a mesh): the root
+    // cubes count as created here, and their "one open job each" lives in this rank's root_pending
     const int tid = (int)(blockIdx.x * blockDim.x + threadIdx.x), nt = (int)(gridDim.x * blockDim.x);
-    for (int i = tid; i < GPSAT_DQC_WORDS; i += nt) ctrl[i] = (i == GPSAT_DQC_CREATED) ? n_local : 0;
+    for (int i = tid; i < GPSAT_DQC_WORDS; i += nt) ctrl[i] = (i == GPSAT_DQC_CREATED && owner) ? n_roots : 0;
     if (meta)
         for (int i = tid; i < dq_cap; i += nt) {
             meta[4 * i] = 0;
@@ -164,8 +165,7 @@ gpsat_queue_init_kernel(int *ctrl, int *meta, int dq_cap, int *root_pending, int
             meta[4 * i + 3] = 0;
         }
     for (int i = tid; i < n_roots; i += nt) {
-        const int d = i - root_first;
-        root_pending[i] = (d >= 0 && d % root_stride == 0 && d / root_stride < n_local) ? 1 : 0;
+        root_pending[i] = owner ? 1 : 0;
         root_flag[i] = 0;
     }
     if (xcur)
@@ -173,7 +173,7 @@ gpsat_queue_init_kernel(int *ctrl, int *meta, int dq_cap, int *root_pending, int
     if (facts)
         for (int i = tid; i < n_vars; i += nt) facts[i] = 0;
     if (tid == 0) {
-        run_ctrl[0] = 0;    // next_job
+        run_ctrl[0] = 0;
         run_ctrl[1] = 0;
         run_ctrl[2] = -1;   // sat_job
         run_ctrl[3] = 0;
@@ -423,13 +423,12 @@ cudaError_t launch_xchg_unpack(const int *blocks, int n_ranks, int my_rank, int 
     return cudaGetLastError();
 }
 
-cudaError_t launch_queue_init(int *ctrl, int *meta, int dq_cap, int *root_pending, int *root_flag, int n_roots,
-                              int root_first, int root_stride, int n_local, int *xcur, unsigned char *facts, int n_vars,
-                              int *run_ctrl, unsigned long long *t0, cudaStream_t stream)
+cudaError_t launch_queue_init(int *ctrl, int *meta, int dq_cap, int *root_pending, int *root_flag, int n_roots, int owner,
+                              int *xcur, unsigned char *facts, int n_vars, int *run_ctrl, unsigned long long *t0,
+                              cudaStream_t stream)
 {
-    gpsat_queue_init_kernel<<<32, 256, 0, stream>>>(ctrl, meta, dq_cap, root_pending, root_flag, n_roots, root_first,
-                                                    root_stride > 0 ? root_stride : 1, n_local, xcur, facts, n_vars,
-                                                    run_ctrl, t0);
+    gpsat_queue_init_kernel<<<32, 256, 0, stream>>>(ctrl, meta, dq_cap, root_pending, root_flag, n_roots, owner, xcur,
+                                                    facts, n_vars, run_ctrl, t0);
     return cudaGetLastError();
 }
 

@@ -16,12 +16,12 @@ cudaError_t cdcl_occupancy(int warps_per_block, size_t smem_bytes, bool smem_sta
 cudaError_t cdcl_attributes(int *regs_per_thread, size_t *local_bytes);
 int cdcl_max_warps_per_block();
 
-// queue state of a solve initialised on the device: empty ring, control block (created = n_local), root arrays (one
-// open job per root cube this rank owns: global index root_first + i * root_stride), foreign-pool cursor, facts,
-// run_ctrl = [next_job, -, sat_job, -], t0 = [launch stamp, busy time]
-cudaError_t launch_queue_init(int *ctrl, int *meta, int dq_cap, int *root_pending, int *root_flag, int n_roots,
-                              int root_first, int root_stride, int n_local, int *xcur, unsigned char *facts, int n_vars,
-                              int *run_ctrl, unsigned long long *t0, cudaStream_t stream);
+// queue state of a solve initialised on the device: empty ring, control block, root arrays, foreign-pool cursor, facts,
+// run_ctrl = [-, -, sat_job, -], t0 = [launch stamp, busy time].  owner = this rank's control block holds the root
+// cursor (single GPU, or rank 0 of a mesh): created = n_roots and one open job per root are booked here.
+cudaError_t launch_queue_init(int *ctrl, int *meta, int dq_cap, int *root_pending, int *root_flag, int n_roots, int owner,
+                              int *xcur, unsigned char *facts, int n_vars, int *run_ctrl, unsigned long long *t0,
+                              cudaStream_t stream);
 // stamps *t0 with the GPU's globaltimer (deadline base for budgeted steps)
 cudaError_t launch_stamp(unsigned long long *t0, cudaStream_t stream);
 

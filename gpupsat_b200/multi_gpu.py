@@ -98,14 +98,10 @@ def solve_sharded(solver, dist, rank: int, world: int, device, *, budget_ms: flo
 # ---------------------------------------------------------------------------------------------------------------
 # mesh: the GPUs of one box as ONE work pool (one process per GPU, CUDA IPC)
 # ---------------------------------------------------------------------------------------------------------------
-def mesh_shard(n_roots: int, rank: int, world: int):
-    """global cube g -> rank g mod world; returns (first, stride, n_local) of this rank's shard."""
-    return rank, world, max(0, (n_roots - rank + world - 1) // world)
-
-
-def mesh_join(solver, dist, rank: int, world: int, device, n_roots: int):
+def mesh_join(solver, dist, rank: int, world: int, device):
     """Forms the mesh: every rank exports its queue region (a 64-byte CUDA IPC handle), ONE all-gather distributes
-    the handles, every rank maps the others' regions.  The solver's cubes must already be its shard (cubes[rank::world])."""
+    the handles, every rank maps the others' regions.  Every rank's solver holds the SAME, complete cube list: the
+    cubes are handed out by one cursor (rank 0's) that all GPUs advance over NVLink."""
     import torch
 
     mine = torch.as_tensor(solver.mesh_export()).to(device)
@@ -114,8 +110,7 @@ def mesh_join(solver, dist, rank: int, world: int, device, n_roots: int):
         _all_gather(dist, allh, mine, world)
     else:
         allh.copy_(mine)
-    first, stride, n_local = mesh_shard(n_roots, rank, world)
-    solver.mesh_attach_ipc(world, rank, allh.cpu().numpy(), n_roots, first, stride, n_local)
+    solver.mesh_attach_ipc(world, rank, allh.cpu().numpy())
     return mesh_result_block(solver, device)
 
 
@@ -156,6 +151,8 @@ def solve_mesh(solver, dist, rank: int, world: int, device, block, n_roots: int,
     if device is not None and torch.device(device).type == "cuda":
         torch.cuda.current_stream(device).synchronize()
     reduce_results(dist, block, n_roots, world)
+    if device is not None and torch.device(device).type == "cuda":
+        torch.cuda.current_stream(device).synchronize()       # unpack runs on the library's own stream
     verdict, stats = solver.mesh_results_unpack(block)
     for k in ("kernel_ms", "kernel_launches", "warp_busy_frac", "steals", "foreign_clauses", "pool_clauses", "blocks",
               "warps_per_block", "smem_bytes_per_block", "state_in_smem"):

@@ -128,6 +128,8 @@ typedef struct gpsat_opts {
     int32_t max_learnts;          /* learnt clauses a job keeps before its first database reduction; 0 = default */
     int32_t split_min;            /* a cube splits only once it has proved hard: conflicts (its own + half of what its parent
                                      had when it was split off) before its first split; 0 = default */
+    int32_t split_hard;           /* hardness from which a cube splits after EVERY conflict (and right when it starts) while warps
+                                     are idle: the few very hard cubes that decide the tail of a run; 0 = default, -1 = off */
 } gpsat_opts;
 
 void gpsat_opts_default(gpsat_opts *o);
@@ -241,29 +243,26 @@ int gpsat_debug_ctrl(gpsat_t *h, int32_t *out16);
 int gpsat_device_ptrs(gpsat_t *h, void **pool_words, void **pool_cursor, void **stop_flag, void **stream);
 
 /* --- mesh: the GPUs of one box as ONE work pool over NVLink peer memory (no reference equivalent). ---
- * Every rank owns a shard of the cubes (global cube g = root_first + i * root_stride for its local cube i) and a queue
- * region (control block, ring of split-off cubes with their hand-off blocks, foreign learnt-clause pool) that the other
- * ranks map.  Inside ONE persistent launch per GPU: idle warps take split-off cubes from the rings of other GPUs, busy
- * cubes split for the demand other GPUs advertise, short learnt clauses are stored straight into the peers' foreign pools,
- * the early-termination flag and global termination travel the same way — no kernel boundary, no host collective on the
- * data path.  Per-cube records / outcome flags are per-rank contributions over ALL n_roots cubes: gpsat_mesh_results_pack
- * copies them into a caller-owned DEVICE block [flags n_roots | open descendants n_roots | records n_roots x 20 words]; the
- * caller reduces the blocks of all ranks (MAX over the first n_roots int32 words, SUM over the rest: int32 for the next
- * n_roots words, int64 for the records — ncclAllReduce / torch.distributed.all_reduce) and gpsat_mesh_results_unpack turns
- * the reduced block into the global verdict, records (gpsat_job_records: n_roots entries) and statistics.
+ * Every rank holds the formula AND the complete cube list, and owns a queue region (control block, ring of split-off cubes
+ * with their hand-off blocks, foreign learnt-clause pool) that the other ranks map.  Inside ONE persistent launch per GPU:
+ * root cubes are handed out by ONE cursor (rank 0's, advanced by every GPU with atomics over NVLink), idle warps take
+ * split-off cubes from the rings of other GPUs, busy cubes split for the demand other GPUs advertise, short learnt clauses
+ * are stored straight into the peers' foreign pools, the early-termination flag and global termination travel the same way
+ * — no kernel boundary, no host collective on the data path.  Per-cube records / outcome flags are per-rank contributions
+ * over ALL cubes: gpsat_mesh_results_pack copies them into a caller-owned DEVICE block
+ * [flags n | open descendants n | records n x 20 words] (n = number of cubes); the caller reduces the blocks of all ranks
+ * (MAX over the first n int32 words, SUM over the rest: int32 for the next n words, int64 for the records —
+ * ncclAllReduce / torch.distributed.all_reduce) and gpsat_mesh_results_unpack turns the reduced block into the global
+ * verdict, records (gpsat_job_records) and statistics.
  * One process per GPU: gpsat_mesh_export + all-gather of the 64-byte handles + gpsat_mesh_attach_ipc (CUDA IPC).
  * One process, several GPUs: gpsat_mesh_attach_local (peer access), or simply the gpsat_multi_* host below.
  * Call order per solve: [all ranks] gpsat_solve_begin -> barrier -> gpsat_solve_step(budget) until done -> reduce results.
- * The barrier matters: a peer must not steal from a ring that its owner has not reset yet. */
+ * The barrier matters: a peer must not touch a cursor or ring that its owner has not reset yet. */
 #define GPSAT_IPC_HANDLE_BYTES 64
 #define GPSAT_MESH_MAX_GPUS 8
 int gpsat_mesh_export(gpsat_t *h, void *ipc_handle /* GPSAT_IPC_HANDLE_BYTES */);
-int gpsat_mesh_attach_ipc(gpsat_t *h, int32_t n_ranks, int32_t rank, const void *ipc_handles /* n_ranks x 64 bytes */,
-                          int32_t n_roots, int32_t root_first, int32_t root_stride, int32_t n_local /* may be 0 */);
-/* in-process mesh over handles[0..n_ranks).  n_local = NULL: cube g of the n_roots cubes belongs to rank g mod n_ranks;
- * n_local given: rank r owns the next n_local[r] cubes (contiguous ranges in rank order; 0 = the rank only takes
- * children of other GPUs).  Each handle's cubes must have been set to its shard before. */
-int gpsat_mesh_attach_local(gpsat_t *const *handles, int32_t n_ranks, int32_t n_roots, const int32_t *n_local);
+int gpsat_mesh_attach_ipc(gpsat_t *h, int32_t n_ranks, int32_t rank, const void *ipc_handles /* n_ranks x 64 bytes */);
+int gpsat_mesh_attach_local(gpsat_t *const *handles, int32_t n_ranks);   /* rank r = handles[r] */
 int gpsat_mesh_detach(gpsat_t *h);
 int64_t gpsat_mesh_result_words(gpsat_t *h);
 int gpsat_mesh_results_pack(gpsat_t *h, void *dev_block, int64_t words);
@@ -273,7 +272,7 @@ int gpsat_handle_device(gpsat_t *h);
 int gpsat_debug_words(gpsat_t *h, int32_t *out, int32_t n);
 
 /* --- multi-GPU host in one process (≙ the host side of SATSolver/main.cu:197-310 for N GPUs; the reference drives one) ---
- * One host thread per GPU, the formula replicated, cube g -> GPU g mod N, the GPUs meshed as above; per-cube results are
+ * One host thread per GPU, formula and cube list replicated, the GPUs meshed as above (one root cursor); per-cube results are
  * reduced with ncclAllReduce (libnccl is loaded at run time; the reduction runs on the host when it cannot be loaded).
  * n_gpus = 0: every visible GPU (at most GPSAT_MESH_MAX_GPUS); devices = NULL: ordinals 0 .. n_gpus-1. */
 typedef struct gpsat_multi gpsat_multi_t;

@@ -33,14 +33,12 @@ extern "C" int gpsat_emu_run(int32_t n_vars, int64_t n_clauses, const int64_t *o
     gpsat_make_layout(n_vars, D.n_lits, &Ly);
     std::vector<int32_t> state((size_t)Ly.total_words, 0);
     std::vector<int32_t> arena((size_t)P.arena_words, 0);
-    int32_t next_job = 0;
     *sat_job = -1;
     gpsat_run_buffers B;
     std::memset(&B, 0, sizeof(B));
     B.cube_offsets = cube_offsets;
     B.cube_lits = cube_lits;
     B.n_cubes = n_cubes;
-    B.next_job = &next_job;
     B.sat_job = sat_job;
     B.model = model;
     B.records = records;
@@ -60,9 +58,7 @@ extern "C" int gpsat_emu_run(int32_t n_vars, int64_t n_clauses, const int64_t *o
     int32_t dq_ctrl[GPSAT_DQC_WORDS] = {0};
     dq_ctrl[GPSAT_DQC_CREATED] = n_cubes;
     B.stop_flag = dq_ctrl + GPSAT_DQC_STOP;
-    B.root_first = 0;
-    B.root_stride = 1;
-    B.n_roots = n_cubes;
+    B.next_job = dq_ctrl + GPSAT_DQC_CURSOR;
     B.dq_lits = dq_lits.data();
     B.dq_meta = dq_meta.data();
     B.dq_ctrl = dq_ctrl;

@@ -30,9 +30,9 @@ def main():
     opts = dict(share_learnts=1, share_max_len=share_len) if share_len else {}
     steals = 0
     with g.Solver(cnf.n_vars, pre.offsets, pre.lits, device=local, **opts) as s:
-        s.set_cubes(mine)
+        s.set_cubes(cubes if mode == "mesh" else mine)      # mesh: every rank holds all cubes (one root cursor)
         if mode == "mesh":
-            block = mg.mesh_join(s, dist, rank, world, dev, len(cubes))
+            block = mg.mesh_join(s, dist, rank, world, dev)
             verdict, model, stats, info = mg.solve_mesh(s, dist, rank, world, dev, block, len(cubes), budget_ms=2000.0,
                                                         max_steps=30)
             rec = s.job_records(len(cubes))                           # global records after the reduction

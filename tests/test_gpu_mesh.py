@@ -22,21 +22,16 @@ def _instance(n, m, seed, b=8, t=32):
     return pre, pre.choose_cubes(b, t)
 
 
-def _mesh_solve(pre, cubes, n_local, n_ranks=2, budget_ms=3000.0, **opts):
-    """rank r owns cubes[r::n_ranks] unless n_local overrides (a rank with 0 cubes only steals)."""
+def _mesh_solve(pre, cubes, n_ranks=2, budget_ms=3000.0, rank_blocks=None, **opts):
+    """every rank holds all cubes; rank_blocks = CTAs per rank (default: the GPU split evenly)"""
     import torch
     n_roots = len(cubes)
-    solvers = [g.Solver(pre.n_vars, pre.offsets, pre.lits, device=0, blocks=148 // n_ranks, **opts) for _ in range(n_ranks)]
+    rank_blocks = rank_blocks or [148 // n_ranks] * n_ranks
+    solvers = [g.Solver(pre.n_vars, pre.offsets, pre.lits, device=0, blocks=rank_blocks[r], **opts) for r in range(n_ranks)]
     try:
-        if n_local is None:
-            shards = [cubes[r::n_ranks] for r in range(n_ranks)]
-        else:
-            cuts = np.concatenate([[0], np.cumsum(n_local)])
-            shards = [cubes[cuts[r]:cuts[r + 1]] for r in range(n_ranks)]
-        for r, s in enumerate(solvers):
-            if n_local is None or n_local[r] > 0:
-                s.set_cubes(shards[r])
-        g.mesh_attach_local(solvers, n_roots, n_local)
+        for s in solvers:
+            s.set_cubes(cubes)
+        g.mesh_attach_local(solvers)
         blocks = [torch.zeros(s.mesh_result_words(), dtype=torch.int32, device="cuda:0") for s in solvers]
         out = [None] * n_ranks
         barrier = threading.Barrier(n_ranks)
@@ -70,21 +65,20 @@ def _mesh_solve(pre, cubes, n_local, n_ranks=2, budget_ms=3000.0, **opts):
             s.close()
 
 
-def test_mesh_rank_without_cubes_steals_and_everything_closes():
-    pre, cubes = _instance(250, 1065, 0, 2, 32)          # 1024 cubes
-    # rank 0 owns every cube, rank 1 none: every job rank 1 runs is a child taken from rank 0's ring
-    verdict, stats, rec, out = _mesh_solve(pre, cubes, [len(cubes), 0])
+def test_mesh_small_rank_lives_off_the_big_one_and_everything_closes():
+    pre, cubes = _instance(250, 1065, 0, 1, 4)            # 64 cubes for 2 x 1480 warps: almost every job is a split-off cube
+    verdict, stats, rec, out = _mesh_solve(pre, cubes, rank_blocks=[100, 48])
     assert verdict == g.UNSAT
     assert len(rec) == len(cubes) and (rec["status"] == g.UNSAT).all()
-    steals = [o[3]["steals"] for o in out]
-    assert steals[1] > 0        # (rank 0 steals too: children of the cubes rank 1 took are queued on rank 1)
+    assert sum(o[3]["steals"] for o in out) > 0           # split-off cubes crossed between the ranks' rings
+    assert stats["splits"] > 0 and stats["jobs_done"] == len(cubes)
 
 
 @pytest.mark.parametrize("share", [0, 8])
 def test_mesh_two_ranks_unsat_all_cubes_closed(share):
     pre, cubes = _instance(250, 1065, 0, 2, 32)
     opts = dict(share_learnts=1, share_max_len=share) if share else {}
-    verdict, stats, rec, out = _mesh_solve(pre, cubes, None, **opts)
+    verdict, stats, rec, out = _mesh_solve(pre, cubes, **opts)
     assert verdict == g.UNSAT
     assert len(rec) == len(cubes) and (rec["status"] == g.UNSAT).all()
     assert stats["jobs_done"] == len(cubes) and stats["conflicts"] > 0
@@ -96,7 +90,7 @@ def test_mesh_sat_early_termination_and_model():
     offs, lits = random_ksat(200, 820, 1)
     pre = g.Cnf.from_arrays(offs, lits).preprocess()
     cubes = pre.choose_cubes(2, 32)
-    verdict, stats, rec, out = _mesh_solve(pre, cubes, None)
+    verdict, stats, rec, out = _mesh_solve(pre, cubes)
     assert verdict == g.SAT
     models = [o[2] for o in out if o[1] == g.SAT]
     assert models and all(check_model(pre.offsets, pre.lits, m) for m in models)
@@ -115,4 +109,4 @@ def test_multi_solver_two_handles_on_one_gpu():
     with g.MultiSolver(pre2.n_vars, pre2.offsets, pre2.lits, n_gpus=2, devices=[0, 0], blocks=74) as ms:
         ms.set_cubes(None)
         verdict, model, stats = ms.solve()
-    assert verdict == g.UNSAT and stats["splits"] > 0 and stats["steals"] > 0
+    assert verdict == g.UNSAT and stats["splits"] > 0          # one root cube: every other job is a split-off cube

@@ -142,10 +142,9 @@ class ScriptedMeshSolver:
     def mesh_export(self):
         return np.full(64, 10 + self.rank, dtype=np.uint8)
 
-    def mesh_attach_ipc(self, n_ranks, rank, handles, n_roots, first, stride, n_local):
+    def mesh_attach_ipc(self, n_ranks, rank, handles):
         h = np.asarray(handles).reshape(n_ranks, 64)
         assert (h[:, 0] == 10 + np.arange(n_ranks)).all()           # every rank's handle arrived, in rank order
-        assert (first, stride) == (rank, n_ranks) and n_local == len(range(rank, n_roots, n_ranks))
         self.attached = (n_ranks, rank)
 
     def mesh_result_words(self):
@@ -205,7 +204,7 @@ def _mesh_worker(rank, world, port, kw, out):
     try:
         n_roots = 9
         s = ScriptedMeshSolver(rank, world, n_roots, 5, **kw)
-        block = mg.mesh_join(s, dist, rank, world, "cpu", n_roots)
+        block = mg.mesh_join(s, dist, rank, world, "cpu")
         verdict, model, stats, info = mg.solve_mesh(s, dist, rank, world, "cpu", block, n_roots)
         out[rank] = {"verdict": verdict, "model": None if model is None else model.tolist(), "stats": stats,
                      "sat_rank": info["sat_rank"], "steps": info["steps"]}
@@ -242,12 +241,3 @@ def test_mesh_sat_model_comes_from_the_lowest_sat_rank():
     assert out[0]["verdict"] == out[1]["verdict"] == mg.SAT
     assert out[0]["sat_rank"] == out[1]["sat_rank"] == 1
     assert out[0]["model"] == out[1]["model"] == [1] * 5
-
-
-def test_mesh_shard_matches_shard_cubes():
-    cubes = np.arange(37 * 3).reshape(37, 3)
-    for world in (1, 2, 3, 8):
-        for r in range(world):
-            first, stride, n_local = mg.mesh_shard(len(cubes), r, world)
-            assert np.array_equal(cubes[first::stride], mg.shard_cubes(cubes, r, world)) and n_local == len(cubes[first::stride])
-    assert mg.mesh_shard(2, 5, 8) == (5, 8, 0)                       # more ranks than cubes: an empty shard, not a stall
