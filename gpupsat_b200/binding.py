@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libgpsat.so")
 SAT, UNSAT, UNDEF = 0, 1, 2
 DECIDE_REFERENCE, DECIDE_VSIDS = 0, 1
 BCP_WATCHED, BCP_OCCURRENCE = 0, 1
-STRATEGY_DISTRIBUTED, STRATEGY_UNIFORM = 0, 1
+STRATEGY_DISTRIBUTED, STRATEGY_UNIFORM, STRATEGY_SIMPLE = 0, 1, 2
 E_NO_DEVICE = -2
 
 RECORD_DTYPE = np.dtype([
@@ -30,7 +30,7 @@ class GpsatOpts(C.Structure):
                 ("arena_words", C.c_int64), ("dynamic_split", C.c_int32), ("split_gap", C.c_int32),
                 ("split_burst", C.c_int32), ("share_import_max", C.c_int32), ("split_hand_words", C.c_int32),
                 ("split_gap_hot", C.c_int32), ("split_at_start", C.c_int32), ("mesh_flags", C.c_int32),
-                ("split_mode", C.c_int32), ("max_learnts", C.c_int32), ("split_min", C.c_int32), ("split_hard", C.c_int32)]
+                ("split_mode", C.c_int32), ("max_learnts", C.c_int32), ("split_min", C.c_int32), ("phase_stats", C.c_int32), ("split_hard", C.c_int32)]
 
 
 class GpsatStats(C.Structure):
@@ -113,8 +113,10 @@ def lib():
     L.gpsat_mesh_results_unpack.argtypes = [vp, vp, i64, C.POINTER(i32), C.POINTER(GpsatStats)]
     L.gpsat_handle_device.argtypes = [vp]
     L.gpsat_debug_words.argtypes = [vp, vp, i32]
+    L.gpsat_get_phase_stats.argtypes = [vp, vp]
     L.gpsat_multi_create.argtypes = [C.POINTER(vp), i32, vp, i32, i64, vp, vp, C.POINTER(GpsatOpts)]
     L.gpsat_multi_n_gpus.argtypes = [vp]
+    L.gpsat_multi_set_time_limit.argtypes = [vp, C.c_double]
     L.gpsat_multi_set_cubes.argtypes = [vp, i32, vp, vp]
     L.gpsat_multi_solve.argtypes = [vp, C.POINTER(i32), vp, C.POINTER(GpsatStats), C.POINTER(i32)]
     L.gpsat_multi_job_records.argtypes = [vp, vp, i32]
@@ -365,6 +367,13 @@ class Solver:
         _check(lib().gpsat_debug_ctrl(self.h, _p(out)))
         return out
 
+    def phase_stats(self):
+        """gpsat_get_phase_stats: dict of arrays ns[8], count[8] + backtracked_levels, jobs, job_ns, idle_ns"""
+        buf = np.zeros(20, dtype=np.int64)
+        _check(lib().gpsat_get_phase_stats(self.h, _p(buf)))
+        return {"ns": buf[:8].copy(), "count": buf[8:16].copy(), "backtracked_levels": int(buf[16]), "jobs": int(buf[17]),
+                "job_ns": int(buf[18]), "idle_ns": int(buf[19])}
+
     def debug_words(self, n=160):
         out = np.zeros(n, dtype=np.int32)
         _check(lib().gpsat_debug_words(self.h, _p(out), n))
@@ -431,6 +440,9 @@ class MultiSolver:
 
     def __exit__(self, *a):
         self.close()
+
+    def set_time_limit(self, ms):
+        _check(lib().gpsat_multi_set_time_limit(self.h, float(ms)))
 
     def set_cubes(self, cubes):
         if cubes is None:

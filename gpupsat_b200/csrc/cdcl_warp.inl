@@ -72,13 +72,24 @@ struct WarpSolver {
     int hand_words, dq_cap;
     int rel_slot, rel_seq;                 // queue slot this job was popped from (released once its content is consumed)
     int *rel_meta;                         // ... and the ring it belongs to
-#if defined(GPSAT_PHASE_CLOCKS)
-    long long ph[6];                       // ns in: reset, import, propagate, analyze+learn, split, reduce_db
-    int stolen;
-#define GPSAT_PH(i, stmt) { const unsigned long long t_ph = gpsat_now_ns(); stmt; ph[i] += (long long)(gpsat_now_ns() - t_ph); }
-#else
-#define GPSAT_PH(i, stmt) { stmt; }
-#endif
+    // per-phase statistics (opts.phase_stats; ≙ RuntimeStatistics, Statistics/RuntimeStatistics.cuh:17-66): lane 0 keeps
+    // ns / count per phase in this warp's state block and folds them into the control block when a job ends
+    int phase_stats;
+    long long *phs;   // [GPSAT_N_PHASES] ns, then [1] backtracked levels behind the counts
+    int *phn;         // [GPSAT_N_PHASES] counts
+#define GPSAT_PH(i, stmt)                                              \
+    {                                                                  \
+        unsigned long long t_ph = 0;                                   \
+        if (phase_stats) t_ph = gpsat_now_ns();                        \
+        stmt;                                                          \
+        if (phase_stats) {                                             \
+            LANE0                                                      \
+            {                                                          \
+                phs[i] += (long long)(gpsat_now_ns() - t_ph);          \
+                phn[i] += 1;                                           \
+            }                                                          \
+        }                                                              \
+    }
     int mesh_ranks;                        // > 1: other GPUs pop from this GPU's ring (system-scope fences / atomics)
     const unsigned long long *t0;          // budgeted steps: jobs park themselves once now > *t0 + budget_ns
     unsigned long long budget_ns;
@@ -1314,10 +1325,14 @@ struct WarpSolver {
                 int bt;
                 int n_out;
                 GPSAT_PH(3, n_out = analyze(confl, bt))
+                const int dl_before = dlevel;
                 hash_learnt(n_out);
                 c_learnt_clauses++;
                 c_learnt_literals += n_out;
-                cancel_until(bt);
+                GPSAT_PH(GPSAT_PHASE_BACKTRACK, cancel_until(bt))
+                if (phase_stats) {
+                    LANE0 { phs[GPSAT_N_PHASES + GPSAT_N_PHASES / 2] += (long long)(dl_before - bt); }
+                }
                 if (n_out == 1) {
                     enqueue(lbuf[0], GPSAT_REASON_NONE);
                 } else {
@@ -1415,7 +1430,7 @@ struct WarpSolver {
             }
             if (next < 0) {
                 if (mode == GPSAT_MODE_PROPAGATE) return GPSAT_UNDEF;
-                next = pick_branch();
+                GPSAT_PH(GPSAT_PHASE_DECIDE, next = pick_branch())
                 if (next < 0) return GPSAT_SAT;
                 c_decisions++;
                 if (max_iterations && c_decisions > max_iterations) return GPSAT_UNDEF;
@@ -1481,10 +1496,6 @@ GPSAT_DEV void gpsat_bind(WarpSolver &S, const gpsat_formula_view &F, const gpsa
     S.rel_slot = -1;
     S.rel_seq = 0;
     S.rel_meta = B.dq_meta;
-#if defined(GPSAT_PHASE_CLOCKS)
-    for (int i = 0; i < 6; ++i) S.ph[i] = 0;
-    S.stolen = 0;
-#endif
     S.t0 = B.t0;
     S.budget_ns = B.budget_ns;
     S.use_learnts = (P.mode == GPSAT_MODE_SOLVE) ? 1 : 0;
@@ -1492,6 +1503,9 @@ GPSAT_DEV void gpsat_bind(WarpSolver &S, const gpsat_formula_view &F, const gpsa
     S.arena_words = (int)P.arena_words;
     S.lw_head = arena;
     S.lwbits = (uint32_t *)(state + Ly.lwbits);
+    S.phase_stats = P.phase_stats;
+    S.phs = (long long *)(state + Ly.ph);
+    S.phn = (int *)(state + Ly.ph + 2 * GPSAT_N_PHASES);
     S.hist = arena + 6 * F.n_vars;
     S.refs = arena + 6 * F.n_vars + 64;
     S.refs_cap = P.learnt_refs_cap;
@@ -1622,13 +1636,17 @@ GPSAT_DEV void gpsat_run_and_record(WarpSolver &S, int root, const int *cube, in
         if (status != GPSAT_JOB_SUSPENDED) {
             gpsat_atomic_add(B.root_pending + job, -1);
             gpsat_atomic_add(B.dq_ctrl + GPSAT_DQC_CLOSED, 1);
-#if defined(GPSAT_PHASE_CLOCKS)
-            for (int i = 0; i < 6; ++i) {   // words 104..115: jobs taken on this rank; 116..127: jobs taken from another rank
-                gpsat_atomic_add_ll((long long *)(B.dq_ctrl + (S.stolen ? 116 : 104) + 2 * i), S.ph[i]);
-                S.ph[i] = 0;
+            if (P.phase_stats) {
+                GPSAT_NOUNROLL
+                for (int i = 0; i < GPSAT_N_PHASES; ++i) {
+                    gpsat_atomic_add_ll((long long *)(B.dq_ctrl + GPSAT_DQC_PHASE) + i, S.phs[i]);
+                    gpsat_atomic_add_ll((long long *)(B.dq_ctrl + GPSAT_DQC_PHASE) + GPSAT_N_PHASES + i, (long long)S.phn[i]);
+                    S.phs[i] = 0;
+                    S.phn[i] = 0;
+                }
+                gpsat_atomic_add_ll((long long *)(B.dq_ctrl + GPSAT_DQC_PHASE) + 2 * GPSAT_N_PHASES, S.phs[GPSAT_N_PHASES + GPSAT_N_PHASES / 2]);
+                S.phs[GPSAT_N_PHASES + GPSAT_N_PHASES / 2] = 0;
             }
-            if (S.stolen) gpsat_atomic_add(B.dq_ctrl + 71, (int)S.c_conflicts);
-#endif
             if (hand != nullptr) {   // size of a split-off cube, in conflicts (diagnostics)
                 int b = 0;
                 GPSAT_NOUNROLL
@@ -1672,6 +1690,14 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
     int is_idle = 0, idle_spins = 0, rot = 0;
     unsigned long long busy_ns = 0;
     const bool mesh = B.mesh_ranks > 1;
+    if (P.phase_stats) {   // the state block (shared memory) starts uninitialised
+        LANE0
+        {
+            GPSAT_NOUNROLL
+            for (int i = 0; i < GPSAT_N_PHASES + GPSAT_N_PHASES / 2 + 1; ++i) S.phs[i] = 0;
+        }
+        SYNCWARP();
+    }
     while (true) {
         LANEVAR(int, kind_v);   // 0 exit, 1 original cube, 2 queued child, 3 wait, 4 resume the job this warp parked, 5 child of another GPU
         LANEVAR(int, idx_v);
@@ -1795,9 +1821,6 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
             S.inherited = gpsat_ld_cg(rmeta + 4 * slot + 3);
             int used = gpsat_ld_cg(rhand);
             if (used < 0 || used > B.hand_words - 1 - 2 * S.n_vars) used = 0;
-#if defined(GPSAT_PHASE_CLOCKS)
-            S.stolen = 1;
-#endif
             if (P.mesh_flags & 8) {   // experiment: run straight from the other rank's slot, like a local pop
                 S.rel_slot = slot;
                 S.rel_seq = idx + B.dq_cap;
@@ -1822,9 +1845,6 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
             SYNCWARP();
             gpsat_run_and_record(S, root, stage + B.hand_words, len, stage, P, B);
         }
-#if defined(GPSAT_PHASE_CLOCKS)
-        S.stolen = 0;
-#endif
         busy_ns += gpsat_now_ns() - t_job;
     }
     LANE0

@@ -314,6 +314,7 @@ gpsat_solve_params make_params(gpsat *h, int mode, int64_t implied_stride)
     P.split_at_start = h->opts.split_at_start > 0 ? 1 : 0;
     P.mesh_flags = h->opts.mesh_flags;
     P.split_mode = h->opts.split_mode;
+    P.phase_stats = (mode == GPSAT_MODE_SOLVE && h->opts.phase_stats) ? 1 : 0;
     P.split_min = h->opts.split_min > 0 ? h->opts.split_min : 0;
     P.split_hard = h->opts.split_hard > 0 ? h->opts.split_hard : 0x7fffffff;
     if (h->opts.max_learnts > 0)
@@ -1603,6 +1604,33 @@ int gpsat_mesh_results_unpack(gpsat_t *h, const void *dev_block, int64_t words, 
 }
 
 int gpsat_handle_device(gpsat_t *h) { return h ? h->device : -1; }
+
+int gpsat_get_phase_stats(gpsat_t *h, gpsat_phase_stats *out)
+{
+    if (!h || !out) {
+        set_error("bad arguments");
+        return GPSAT_E_ARG;
+    }
+    std::memset(out, 0, sizeof(*out));
+    if (!h->opts.phase_stats) {
+        set_error("the handle was created without opts.phase_stats");
+        return GPSAT_E_STATE;
+    }
+    const int64_t *w = (const int64_t *)(h->dq_ctrl_h + GPSAT_DQC_PHASE);
+    for (int i = 0; i < GPSAT_N_PHASES; i++) {
+        out->ns[i] = w[i];
+        out->count[i] = w[GPSAT_N_PHASES + i];
+    }
+    out->backtracked_levels = w[2 * GPSAT_N_PHASES];
+    out->jobs = h->dq_ctrl_h[GPSAT_DQC_CLOSED];
+    DeviceGuard guard(h->device);
+    unsigned long long busy = 0;
+    if (h->t0.p) CU(cudaMemcpy(&busy, h->t0.p + 1, sizeof(busy), cudaMemcpyDeviceToHost));
+    out->job_ns = (int64_t)busy;
+    const double warp_ns = (double)h->blocks * h->warps_per_block * h->kernel_ms * 1e6;
+    out->idle_ns = (int64_t)std::max(0.0, warp_ns - (double)busy);
+    return GPSAT_OK;
+}
 
 int gpsat_debug_words(gpsat_t *h, int32_t *out, int32_t n)
 {

@@ -53,7 +53,8 @@
 
 #define GPSAT_DQC_PEER_QUEUE 96   // [GPSAT_MESH_MAX_RANKS] children queued on rank r, written by r's communication warp
 #define GPSAT_DQC_PEER_IDLE 128   // [GPSAT_MESH_MAX_RANKS] unmet demand of rank r (idle warps - queued children), its share for us
-#define GPSAT_DQC_WORDS 160
+#define GPSAT_DQC_PHASE 160       // [GPSAT_N_PHASES] int64 ns per phase, then [GPSAT_N_PHASES] int64 counts, then int64 backtracked levels (opts.phase_stats)
+#define GPSAT_DQC_WORDS 200
 #define GPSAT_MESH_MAX_RANKS 8
 
 // per-root outcome flags, combined with atomicMax (higher wins)
@@ -101,6 +102,7 @@ struct gpsat_solve_params {
     int32_t split_hot_demand;    // demand from which the hot gap applies (1/8 of this GPU's warps)
     int32_t split_at_start;      // 1: a cube may split before its first conflict while warps are idle
     int32_t mesh_flags;          // test hooks: 1 no stealing, 2 no clause push
+    int32_t phase_stats;         // 1: per-phase time / count accumulators (≙ RuntimeStatistics, Statistics/RuntimeStatistics.cuh:17-66)
     int32_t split_mode;          // 0 back to the cube + VSIDS-best, 1 guiding path (oldest open decision), 2 as 0 with sides swapped
     int32_t split_min;           // hardness (own conflicts + inherited) a job needs before its first split
     int32_t split_hard;          // hardness from which a job splits after every conflict and at its start (0x7fffffff = never)
@@ -108,7 +110,7 @@ struct gpsat_solve_params {
 
 // word offsets (int32 units) of the per-warp state arrays inside one warp's state block
 struct gpsat_state_layout {
-    int32_t val, seen, level, reason, trail, trail_lim, wbits, vs, lbuf, cube, lwbits;
+    int32_t val, seen, level, reason, trail, trail_lim, wbits, vs, lbuf, cube, lwbits, ph;
     int32_t total_words;
     int32_t lbuf_words;
 };
@@ -208,6 +210,7 @@ static inline void gpsat_make_layout(int32_t n_vars, int64_t n_lits, gpsat_state
     GPSAT_TAKE(lbuf, ly->lbuf_words);
     GPSAT_TAKE(cube, GPSAT_DQ_MAXK);
     GPSAT_TAKE(lwbits, (2 * n + 31) / 32);
+    GPSAT_TAKE(ph, 2 * GPSAT_N_PHASES + GPSAT_N_PHASES + 2);   // int64 ns[8] | int32 count[8] | int64 backtracked levels
 #undef GPSAT_TAKE
     ly->total_words = at;
 }

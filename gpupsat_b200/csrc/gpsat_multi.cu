@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -77,6 +78,7 @@ struct gpsat_multi {
     std::vector<ncclComm_t> comm;
     bool nccl_ready = false;
     std::vector<gpsat_job_record> records;
+    double time_limit_ms = 0;           // 0 = until done
 };
 
 namespace {
@@ -164,6 +166,16 @@ int gpsat_multi_create(gpsat_multi_t **out, int32_t n_gpus, const int32_t *devic
 
 int gpsat_multi_n_gpus(gpsat_multi_t *m) { return m ? m->n : 0; }
 
+int gpsat_multi_set_time_limit(gpsat_multi_t *m, double ms)
+{
+    if (!m || ms < 0) {
+        set_error("bad arguments");
+        return GPSAT_E_ARG;
+    }
+    m->time_limit_ms = ms;
+    return GPSAT_OK;
+}
+
 int gpsat_multi_set_cubes(gpsat_multi_t *m, int32_t n_cubes, const int64_t *cube_offsets, const int32_t *cube_lits)
 {
     if (!m || n_cubes < 0 || (n_cubes > 0 && !cube_offsets)) {
@@ -215,9 +227,13 @@ int gpsat_multi_solve(gpsat_multi_t *m, int32_t *verdict, uint8_t *model, gpsat_
             // time-bounded launches (unfinished cubes park in place and resume): a GPU whose peer never shows up ends
             // its step instead of spinning for ever; a run shorter than the budget is a single launch
             int32_t done = 0, v = GPSAT_UNDEF;
+            const auto t_start = std::chrono::steady_clock::now();
+            double left = m->time_limit_ms;
             do {
-                rc = gpsat_solve_step(m->h[r], kStepBudgetMs, &done, &v);
-            } while (rc == GPSAT_OK && !done);
+                const double budget = m->time_limit_ms > 0 ? std::min(kStepBudgetMs, std::max(left, 1.0)) : kStepBudgetMs;
+                rc = gpsat_solve_step(m->h[r], budget, &done, &v);
+                left = m->time_limit_ms - std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
+            } while (rc == GPSAT_OK && !done && (m->time_limit_ms <= 0 || left > 0));
             if (rc == GPSAT_OK) rc = gpsat_solve_end(m->h[r], &local_verdict[(size_t)r], local_model[(size_t)r].data(), &local_stats[(size_t)r]);
             if (rc == GPSAT_OK) rc = gpsat_mesh_results_pack(m->h[r], m->block[r], words);
         }

@@ -677,7 +677,33 @@ int gpsat_choose_cubes(const gpsat_cnf *pre, int32_t blocks, int32_t threads, in
         return GPSAT_E_ARG;
     }
     const int64_t live = (int64_t)pre->n_vars - (int64_t)pre->solved.size();
-    const int k = gpsat_host::vars_per_job(live, blocks, threads, strategy);
+    if (strategy == GPSAT_STRATEGY_SIMPLE) {
+        // SimpleJobChooser::evaluate / addJobs (JobsManager/SimpleJobChooser.cu:22-75; USE_SIMPLE_JOBS_GENERATION,
+        // SATSolver/Configs.cuh:44, off as shipped): the first min(live, UNIFORM_NUMBER_OF_VARS = 7) variables in index
+        // order that preprocessing did not solve, positive branch first at every depth
+        const int k = (int)std::min<int64_t>(std::max<int64_t>(live, 0), 7);
+        *vars_per_job = k;
+        *n_cubes = 1 << k;
+        if (!cube_lits) return GPSAT_OK;
+        if (cube_lits_cap < (int64_t)k << k) {
+            gpsat_host::set_error("cube buffer too small");
+            return GPSAT_E_CAPACITY;
+        }
+        std::vector<char> dead((size_t)std::max(pre->n_vars, 1), 0);
+        for (int32_t x : pre->solved) dead[(size_t)(x >> 1)] = 1;
+        std::vector<int32_t> vars;
+        for (int32_t v = 0; v < pre->n_vars && (int)vars.size() < k; v++)
+            if (!dead[(size_t)v]) vars.push_back(v);
+        for (int64_t j = 0; j < (int64_t)1 << k; j++)
+            for (int i = 0; i < k; i++)
+                cube_lits[j * k + i] = 2 * vars[(size_t)i] + ((((j >> (k - 1 - i)) & 1) == 0) ? 1 : 0);
+        return GPSAT_OK;
+    }
+    int k = gpsat_host::vars_per_job(live, blocks, threads, strategy);
+    // fewer than 3 live variables: the reference's size_t arithmetic wraps (live - MIN_FREE_VARS) and asks for more cube
+    // variables than exist (its main() forces the sequential path before that, SATSolver/main.cu:133-139); a cube cannot
+    // hold more variables than are live
+    if ((int64_t)k > std::max<int64_t>(live, 0)) k = (int)std::max<int64_t>(live, 0);
     *vars_per_job = k;
     *n_cubes = 1 << k;
     if (!cube_lits) return GPSAT_OK;

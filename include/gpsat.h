@@ -78,6 +78,7 @@ int32_t        gpsat_cnf_n_lines(const gpsat_cnf *f);             /* n_lines() o
 
 #define GPSAT_STRATEGY_DISTRIBUTED 0   /* ChoosingStrategy::DISTRIBUTE_JOBS_PER_THREAD */
 #define GPSAT_STRATEGY_UNIFORM     1   /* ChoosingStrategy::UNIFORM */
+#define GPSAT_STRATEGY_SIMPLE      2   /* SimpleJobChooser (JobsManager/SimpleJobChooser.cu:22-75; USE_SIMPLE_JOBS_GENERATION, off as shipped) */
 /* ≙ MaxClauseJobChooser::evaluate/getJobs + VariableChooser::evaluate (JobsManager/JobChooser.cu:52-133,
  * JobsManager/VariableChooser.cu:23-40).  `pre` is a preprocessed formula.  Writes vars-per-job and the job count
  * (2^k); when cube_lits != NULL fills n_cubes*k literals (cube j, position i positive iff bit (k-1-i) of j is 0). */
@@ -128,6 +129,8 @@ typedef struct gpsat_opts {
     int32_t max_learnts;          /* learnt clauses a job keeps before its first database reduction; 0 = default */
     int32_t split_min;            /* a cube splits only once it has proved hard: conflicts (its own + half of what its parent
                                      had when it was split off) before its first split; 0 = default */
+    int32_t phase_stats;          /* 1: time and count per solver phase (gpsat_phase_stats), the counterpart of the reference's
+                                     RuntimeStatistics timers (Statistics/RuntimeStatistics.cuh:17-66); default 0 */
     int32_t split_hard;           /* hardness from which a cube splits after EVERY conflict (and right when it starts) while warps
                                      are idle: the few very hard cubes that decide the tail of a run; 0 = default, -1 = off */
 } gpsat_opts;
@@ -202,6 +205,34 @@ int gpsat_eval_clauses(gpsat_t *h, int32_t n_assignments, const uint8_t *assignm
  * satisfiable (model[v] = 1/0, a total assignment that satisfies the uploaded formula), GPSAT_UNSAT if every cube is
  * refuted, GPSAT_UNDEF if a cap (max_iterations / max_conflicts) stopped some job and none was SAT. */
 int gpsat_solve(gpsat_t *h, int32_t *verdict, uint8_t *model, gpsat_stats *stats);
+
+/* ≙ RuntimeStatistics (Statistics/RuntimeStatistics.cuh:17-66, printed by print_function_time_statistics,
+ * Statistics/RuntimeStatistics.cu:299-360): time (ns, summed over warps, GPU globaltimer) and number of runs per phase
+ * of the last solve on a handle created with opts.phase_stats = 1.  The reference keeps one clock64 total per thread and
+ * phase; here one total per GPU and phase.  Mapping of the reference's phases: "job" = job_ns / jobs, "pre-processing"
+ * (cube placement, SATSolver::preprocess) = RESET + IMPORT, "decision" = DECIDE, "conflict analyzing" (its name for
+ * propagate-until-no-conflict, ConflictAnalyzer::propagate) = PROPAGATE + ANALYZE, "backtracking" = BACKTRACK, "structures
+ * reset" = RESET, "next job" = idle_ns (warps waiting for a cube); the reference's "creating structures", "add jobs to
+ * assumptions", "processing results" and the three pre-processing sub-phases have no counterpart (no per-thread object
+ * construction, cubes are read in place, records are a few atomics): reported as not run. */
+#define GPSAT_N_PHASES 8
+#define GPSAT_PHASE_RESET 0        /* per-job state reset (≙ reset_structures) */
+#define GPSAT_PHASE_IMPORT 1       /* hand-off block / shared clauses attached at job start */
+#define GPSAT_PHASE_PROPAGATE 2    /* two-watched-literal BCP */
+#define GPSAT_PHASE_ANALYZE 3      /* first-UIP analysis */
+#define GPSAT_PHASE_SPLIT 4        /* handing half of the cube to another warp */
+#define GPSAT_PHASE_REDUCE 5       /* learnt-database reduction */
+#define GPSAT_PHASE_DECIDE 6       /* VSIDS / reference decision */
+#define GPSAT_PHASE_BACKTRACK 7    /* cancel_until after a conflict or restart */
+typedef struct gpsat_phase_stats {
+    int64_t ns[GPSAT_N_PHASES];
+    int64_t count[GPSAT_N_PHASES];
+    int64_t backtracked_levels;   /* sum over backjumps of the levels undone (≙ total_backtracked_levels) */
+    int64_t jobs;                 /* jobs run (cubes + split-off cubes) */
+    int64_t job_ns;               /* warp time inside jobs */
+    int64_t idle_ns;              /* warp time waiting for a job */
+} gpsat_phase_stats;
+int gpsat_get_phase_stats(gpsat_t *h, gpsat_phase_stats *out);
 
 /* CUDA-event time (ms) of the kernels of the last gpsat_solve / gpsat_propagate_all on this handle */
 double gpsat_last_kernel_ms(gpsat_t *h);
@@ -279,6 +310,9 @@ typedef struct gpsat_multi gpsat_multi_t;
 int gpsat_multi_create(gpsat_multi_t **m, int32_t n_gpus, const int32_t *devices, int32_t n_vars, int64_t n_clauses,
                        const int64_t *offsets, const int32_t *lits, const gpsat_opts *opts);
 int gpsat_multi_n_gpus(gpsat_multi_t *m);
+/* time-bounded solves (0 = until done): when the limit is reached the open cubes stay parked, the verdict is GPSAT_UNDEF
+ * unless a model was found, and the records say how many cubes were closed */
+int gpsat_multi_set_time_limit(gpsat_multi_t *m, double ms);
 int gpsat_multi_set_cubes(gpsat_multi_t *m, int32_t n_cubes, const int64_t *cube_offsets, const int32_t *cube_lits);
 /* stats: counters summed over GPUs; kernel_ms = slowest GPU; warp_busy_frac = mean; reduce_backend (optional): 1 NCCL, 0 host */
 int gpsat_multi_solve(gpsat_multi_t *m, int32_t *verdict, uint8_t *model, gpsat_stats *stats, int32_t *reduce_backend);

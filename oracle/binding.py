@@ -145,6 +145,8 @@ class Reference:
         L.ref_get_solved_literals.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_get_formula.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_cubes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
+        L.ref_cubes_simple.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+        L.ref_clause_status.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_propagate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_counter_implications.restype = C.c_longlong
@@ -176,6 +178,24 @@ class Reference:
         out = np.zeros(max(n * k.value, 1), dtype=np.int32)
         self.lib.ref_cubes(self.h, blocks, threads, strategy, C.byref(k), _p(out), n * k.value)
         return out[: n * k.value].reshape(n, k.value)
+
+    def cubes_simple(self):
+        """SimpleJobChooser (JobsManager/SimpleJobChooser.cu:22-75): the generator behind USE_SIMPLE_JOBS_GENERATION."""
+        k = C.c_int(0)
+        n = self.lib.ref_cubes_simple(self.h, C.byref(k), None, 0)
+        out = np.zeros(max(n * k.value, 1), dtype=np.int32)
+        self.lib.ref_cubes_simple(self.h, C.byref(k), _p(out), n * k.value)
+        return out[: n * k.value].reshape(n, k.value)
+
+    def clause_status(self, assignment):
+        """VariablesStateHandler::clause_status of every clause under `assignment` (0 true, 1 false, 2 unassigned)."""
+        a = np.ascontiguousarray(assignment, dtype=np.uint8)
+        m = self.lib.ref_n_clauses(self.h)
+        status = np.zeros(m, dtype=np.int32)
+        unit = np.zeros(m, dtype=np.int32)
+        got = self.lib.ref_clause_status(self.h, _p(a), _p(status), _p(unit))
+        assert got == m
+        return status, unit
 
     def propagate(self, cube):
         cube = np.ascontiguousarray(cube, dtype=np.int32)

@@ -29,7 +29,7 @@ SATSolver/SATSolver.cu SATSolver/VariablesStateHandler.cu SATSolver/DecisionMake
 Statistics/RuntimeStatistics.cu ErrorHandler/CudaMemoryErrorHandler.cu
 Preprocessing/RepeatedLiteralsRemover.cu Preprocessing/UnaryClausesRemover.cu
 FileManager/FormulaData.cu FileManager/FileUtils.cu
-JobsManager/JobChooser.cu JobsManager/VariableChooser.cu
+JobsManager/JobChooser.cu JobsManager/VariableChooser.cu JobsManager/SimpleJobChooser.cu
 "
 CXX="${CXX:-g++}"
 FLAGS="-std=c++20 -O2 -w -fpermissive -fPIC -D__CUDA_ARCH__=1000 -x c++ -include $HERE/stub/cuda_runtime.h -I$HERE/stub -I$SRC -I$SRC/SATSolver -I$SRC/Utils"

@@ -9,6 +9,10 @@
  *   ref_open       FormulaData::add_clause / set_n_vars / copy_host_clauses_to_dev  (FileManager/FormulaData.cu:19-38,82-105)
  *                  exactly as CnfManager::read_cnf does (FileManager/CnfReader.cpp:86-135) minus the Boost parser
  *   ref_cubes      MaxClauseJobChooser::evaluate/getJobs (JobsManager/JobChooser.cu:52-90) through a JobsQueue
+ *   ref_cubes_simple  SimpleJobChooser::evaluate/getJobs (JobsManager/SimpleJobChooser.cu:22-75), the generator behind
+ *                  USE_SIMPLE_JOBS_GENERATION (SATSolver/Configs.cuh:44, off as shipped)
+ *   ref_clause_status  VariablesStateHandler::clause_status (SATSolver/VariablesStateHandler.cu:180-206) over the whole
+ *                  formula under an arbitrary partial assignment
  *   ref_propagate  VariablesStateHandler::set_assumptions + ConflictAnalyzerWithWatchedLits::set_assumptions
  *                  = SATSolver::preprocess (SATSolver/SATSolver.cu:231-246), then the KernelContext::finished reset
  *                  (SATSolver/Parallelizer.cu:60-74)
@@ -22,6 +26,7 @@
 #include "SATSolver/SolverTypes.cuh"
 #include "FileManager/FormulaData.cuh"
 #include "JobsManager/JobChooser.cuh"
+#include "JobsManager/SimpleJobChooser.cuh"
 #include "SATSolver/JobsQueue.cuh"
 #include "SATSolver/SATSolver.cuh"
 #include "Statistics/RuntimeStatistics.cuh"
@@ -159,6 +164,72 @@ int ref_cubes(void *hv, int blocks, int threads, int strategy, int *vars_per_job
         }
     }
     return n_jobs;
+}
+
+
+/* SimpleJobChooser: the first min(live vars, UNIFORM_NUMBER_OF_VARS) live variables, positive branch first. */
+int ref_cubes_simple(void *hv, int *vars_per_job, int32_t *out, int64_t out_cap)
+{
+    RefHandle *h = (RefHandle *)hv;
+    SimpleJobChooser chooser((size_t)h->n_vars, h->dead_host);
+    chooser.evaluate();
+    int n_jobs = (int)chooser.get_n_jobs();
+    unsigned counter = 0;
+    JobsQueue queue((size_t)n_jobs, &counter);
+    chooser.getJobs(queue);
+    queue.close();
+    int k = (int)queue.largest_job_size();
+    *vars_per_job = k;
+    if (out) {
+        for (int j = 0; j < n_jobs; j++) {
+            Job job = queue.next_job();
+            for (size_t i = 0; i < job.n_literals; i++) {
+                int64_t pos = (int64_t)j * k + (int64_t)i;
+                if (pos < out_cap) out[pos] = job.literals[i].x;
+            }
+            free(job.literals);
+        }
+    }
+    return n_jobs;
+}
+
+/* clause_status of every clause under `assignment` (per variable: 0 = true, 1 = false, 2 = unassigned — the reference's
+ * sat_status).  status[c] in {0 SAT, 1 UNSAT, 2 UNDEF}; unit[c] = the single unassigned literal of a unit clause, else -1. */
+int ref_clause_status(void *hv, const uint8_t *assignment, int32_t *status, int32_t *unit)
+{
+    RefHandle *h = (RefHandle *)hv;
+    ensure_common(h);
+    Var *fv = (Var *)malloc(sizeof(Var) * (h->n_vars + 1));
+    Decision *dec = (Decision *)malloc(sizeof(Decision) * (h->n_vars + 1));
+    Decision *imp = (Decision *)malloc(sizeof(Decision) * (h->n_vars + 1));
+    DecisionMaker *dm = new DecisionMaker(h->formula_dev, (size_t)h->n_vars);
+    VariablesStateHandler *vh = new VariablesStateHandler(h->n_vars, &h->dead_view, dm, fv, dec, imp);
+    dm->set_vars_handler(vh);
+    for (int v = 0; v < h->n_vars; v++) {
+        if (assignment[v] > 1) continue;
+        bool dead = false;
+        for (Var d : h->dead_host) dead = dead || d == v;
+        if (dead) continue;
+        Decision d;
+        d.literal = mkLit(v, assignment[v] == 0);
+        d.decision_level = 1;
+        d.implicated_from_formula = false;
+        vh->new_implication(d);
+    }
+    int m = h->formula_dev->size_of();
+    for (int c = 0; c < m; c++) {
+        Lit l;
+        l.x = -1;
+        sat_status st = vh->clause_status(h->formula_dev->get((size_t)c), &l);
+        status[c] = (int)st;
+        if (unit) unit[c] = l.x;
+    }
+    delete vh;
+    delete dm;
+    free(fv);
+    free(dec);
+    free(imp);
+    return m;
 }
 
 /* BCP of one cube from an empty trail. status: 0 SAT, 1 UNSAT (conflict), 2 UNDEF. implied = literals in discovery order. */

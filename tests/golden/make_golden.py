@@ -107,7 +107,36 @@ def main():
         R = Reference(offs, lits)
         cb = R.cubes(2, 2, 0)
     cubes["sat_8v_random-b2-t2"] = {"k": int(cb.shape[1]), "n": int(len(cb)), "vars": (cb[0] >> 1).tolist()}
+    # SimpleJobChooser (USE_SIMPLE_JOBS_GENERATION): on a formula with solved (dead) variables and on uf250
+    simple = {}
+    pc = out["preprocess"]["case3"]
+    for name, (o2, l2) in {"preprocess-case3": (np.array(pc["offsets"], dtype=np.int64), np.array(pc["lits"], dtype=np.int32)),
+                           "uf250-1065-seed0": random_ksat(250, 1065, 0)}.items():
+        with Quiet():
+            R = Reference(o2, l2)
+            cs = R.cubes_simple()
+        simple[name] = {"k": int(cs.shape[1]), "n": int(len(cs)), "vars": (cs[0] >> 1).tolist(), "second": cs[1].tolist(),
+                        "last": cs[-1].tolist(),
+                        "checksum": int((cs.astype(np.int64) * (np.arange(cs.size).reshape(cs.shape) % 1009 + 1)).sum())}
+    cubes["simple"] = simple
     out["cubes"] = cubes
+
+    # 5. clause evaluation: VariablesStateHandler::clause_status of every clause under seeded partial assignments
+    ev = {}
+    for name, (n, m, seed) in {"uf50-218-seed0": (50, 218, 0), "uf250-1065-seed0": (250, 1065, 0)}.items():
+        offs, lits = random_ksat(n, m, seed)
+        rows = []
+        rg = np.random.default_rng(1234 + seed + n)
+        with Quiet():
+            R = Reference(offs, lits)
+            for frac in (0.0, 0.3, 0.7, 0.95, 1.0):
+                a = np.full(n, 2, dtype=np.uint8)
+                pick = rg.random(n) < frac
+                a[pick] = rg.integers(0, 2, size=int(pick.sum()), dtype=np.uint8)
+                st, unit = R.clause_status(a)
+                rows.append({"assignment": a.tolist(), "status": st.tolist(), "unit": unit.tolist()})
+        ev[name] = rows
+    out["clause_status"] = ev
 
     with open(os.path.join(HERE, "reference_outputs.json"), "w") as f:
         json.dump(out, f, indent=None, separators=(",", ":"))

@@ -74,3 +74,61 @@ def test_pigeonhole_and_errors(tmp_path):
     assert rc != 0 and "was not found" in out          # exit(-1), main.cu:115-118
     rc, out = run_cli(["--version"], tmp_path)
     assert rc == 0 and "v0.0.1" in out
+
+
+def test_statistics_surface_and_simple_strategy(tmp_path):
+    """-v 2 prints the reference's statistics sections (Statistics/RuntimeStatistics.cu:299-360) from the kernel's phase
+    counters; -s simple = SimpleJobChooser (JobsManager/SimpleJobChooser.cu:22-75)"""
+    offs, lits = random_ksat(50, 218, 1)
+    p = tmp_path / "u.cnf"
+    p.write_text(to_dimacs(offs, lits, 50))
+    out = subprocess.run([CLI, str(p), "-b", "2", "-t", "2", "-v", "2"], capture_output=True, text=True, cwd=tmp_path)
+    assert out.returncode == 0
+    t = out.stdout
+    titles = ["*****Statistics******", "Total job's time:", "Pre-processing time:", "Decision time:", "Conflict analyzing time:",
+              "Backtracking time:", "Structures reset time:", "Creating structures time:", "Next job time:",
+              "Add jobs to assumptions time:", "Processing results time:", "Average backtracked levels:",
+              "Pre-processing - handling assumptions time:", "Pre-processing - adding assumptions to graph time:",
+              "Pre-processing - adding handling vars time:"]
+    pos = [t.index(x) for x in titles]                      # all present ...
+    assert pos == sorted(pos)                               # ... in the reference's order
+    assert "run " in t.split("Decision time:")[1].split("Conflict analyzing time:")[0]      # decisions were timed
+    assert "UNSATISFIABLE" in t
+    out = subprocess.run([CLI, str(p), "-s", "simple"], capture_output=True, text=True, cwd=tmp_path)
+    assert "Simple jobs generation is ON" in out.stdout and "Number of jobs = 128" in out.stdout and "UNSATISFIABLE" in out.stdout
+
+
+def test_edge_case_files(tmp_path):
+    (tmp_path / "e.cnf").write_text("p cnf 0 0\n")
+    out = subprocess.run([CLI, str(tmp_path / "e.cnf")], capture_output=True, text=True, cwd=tmp_path)
+    assert out.returncode == 0 and "SATISFIABLE" in out.stdout
+    (tmp_path / "f.cnf").write_text("p cnf 3 2\n1 2 3 0\n0\n")
+    out = subprocess.run([CLI, str(tmp_path / "f.cnf")], capture_output=True, text=True, cwd=tmp_path)
+    assert out.returncode == 0 and "UNSATISFIABLE" in out.stdout
+    (tmp_path / "g.cnf").write_text("p cnf 3 3\n1 2 0\n-1 2 0\n3 0\n")          # one live variable pair after the unit
+    out = subprocess.run([CLI, str(tmp_path / "g.cnf"), "-b", "4", "-t", "4"], capture_output=True, text=True, cwd=tmp_path)
+    assert out.returncode == 0 and "SATISFIABLE" in out.stdout and "was verified" in out.stdout
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+def test_cli_on_all_gpus_gives_the_same_verdicts(tmp_path):
+    """gpupsat FILE.cnf -b 64 -t 32 --gpus 0: the C++ multi-GPU host (gpsat_multi_*) behind the drop-in CLI"""
+    for n, m, seed, want in ((250, 1065, 0, "UNSATISFIABLE"), (200, 820, 1, "SATISFIABLE")):
+        offs, lits = random_ksat(n, m, seed)
+        p = tmp_path / f"m{seed}.cnf"
+        p.write_text(to_dimacs(offs, lits, n))
+        one = subprocess.run([CLI, str(p), "-b", "64", "-t", "32"], capture_output=True, text=True, cwd=tmp_path)
+        many = subprocess.run([CLI, str(p), "-b", "64", "-t", "32", "--gpus", "0", "-v", "2"], capture_output=True, text=True, cwd=tmp_path)
+        assert one.returncode == 0 and many.returncode == 0, many.stdout[-500:]
+        assert want in one.stdout.splitlines() and want in many.stdout.splitlines()
+        assert "Number of GPUs:" in many.stdout
+        if want == "SATISFIABLE":
+            assert "Solution was verified" in many.stdout

@@ -453,3 +453,72 @@ def test_state_in_global_memory_path():
         s.set_cubes(pre.choose_cubes(2, 32))
         verdict, model, stats = s.solve()
     assert verdict == g.SAT and check_model(pre.offsets, pre.lits, model)
+
+
+# ---- pins against outputs of the REFERENCE itself (tests/golden/reference_outputs.json, generated by executing
+# oracle/_ref = the reference's own classes; tests/golden/make_golden.py) run through the CUDA path ----------------------
+from tests.helpers import golden  # noqa: E402
+
+G = golden()
+
+
+@pytest.mark.parametrize("name", sorted(k for k in G["verdicts"] if k.startswith(("uf20", "uf50", "php"))))
+def test_golden_reference_verdicts_through_the_cuda_path(name):
+    """the 20 uf20/uf50 verdicts and the 3 pigeonhole verdicts the reference produced, sequential mode (-b 1 -t 1)"""
+    if name.startswith("uf"):
+        n, m = int(name.split("-")[0][2:]), int(name.split("-")[1])
+        offs, lits = random_ksat(n, m, int(name.split("seed")[1]))
+    else:
+        _, p, h = name.split("-")
+        offs, lits = pigeonhole(int(p), int(h))
+    cnf = g.Cnf.from_arrays(offs, lits)
+    verdict, model, stats = g.solve_cnf(cnf, sequential=True)
+    assert verdict == G["verdicts"][name]
+    if verdict == g.SAT:
+        assert check_model(offs, lits, model)
+
+
+def test_max_iterations_1000_reproduces_the_reference_undef():
+    """as shipped the reference gives up after 1000 decisions (SATSolver/Configs.cuh:23): uf100-426 seed 0 -> UNDEF;
+    the same cap on the CUDA path (reference decision rule) gives UNDEF too, no cap gives the cap-lifted UNSAT"""
+    offs, lits = random_ksat(100, 426, 0)
+    cnf = g.Cnf.from_arrays(offs, lits)
+    assert G["verdicts"]["uf100-426-seed0-as-shipped"] == g.UNDEF and G["verdicts"]["uf100-426-seed0-nocap"] == g.UNSAT
+    v_cap, _, _ = g.solve_cnf(cnf, sequential=True, decision=g.DECIDE_REFERENCE, max_iterations=1000, dynamic_split=0)
+    v_free, _, _ = g.solve_cnf(cnf, sequential=True, decision=g.DECIDE_REFERENCE, dynamic_split=0)
+    assert v_cap == g.UNDEF and v_free == g.UNSAT
+
+
+@pytest.mark.parametrize("name,n,m,seed", [("uf50-218-seed0", 50, 218, 0), ("uf250-1065-seed0", 250, 1065, 0)])
+def test_eval_clauses_equals_reference_clause_status(name, n, m, seed):
+    """gpsat_eval_clauses against VariablesStateHandler::clause_status executed by the reference (golden fixture)"""
+    offs, lits = random_ksat(n, m, seed)
+    pre = g.Cnf.from_arrays(offs, lits).preprocess()
+    rows = G["clause_status"][name]
+    a = np.array([r["assignment"] for r in rows], dtype=np.uint8)
+    with g.Solver(n, pre.offsets, pre.lits) as s:
+        st, unit = s.eval_clauses(a)
+    assert st.tolist() == [r["status"] for r in rows]
+    assert unit.tolist() == [r["unit"] for r in rows]
+
+
+def test_single_cube_propagate_equals_propagate_all_in_ternary_mode():
+    """gpsat_propagate(j) narrows the job list to one cube; the ternary sweep kernel's per-cube info (short-list count,
+    distinct-variables flag) must follow it (it read cube 0's)"""
+    offs, lits = random_ksat(600, 2400, 11)
+    rng = np.random.default_rng(3)
+    cubes = []
+    for j in range(12):
+        ln = int(rng.integers(5, 120))
+        vs = rng.choice(600, size=ln, replace=(j % 3 == 0))          # every third cube repeats variables
+        cubes.append((2 * vs + rng.integers(0, 2, size=ln)).astype(np.int32))
+    co = np.concatenate([[0], np.cumsum([len(c) for c in cubes])]).astype(np.int64)
+    cl = np.concatenate(cubes)
+    with g.Solver(600, offs, lits, bcp=g.binding.BCP_OCCURRENCE) as s:
+        s.set_cubes(cube_offsets=co, cube_lits=cl)
+        allr = s.propagate_all()
+        for j in range(len(cubes)):
+            st, imp, cc = s.propagate(j)
+            assert st == allr["status"][j]
+            if st == g.UNDEF:
+                assert set(imp.tolist()) == set(allr["implied"][j, : allr["n_implied"][j]].tolist())

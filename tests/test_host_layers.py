@@ -7,6 +7,7 @@ import pytest
 
 import gpupsat_b200 as g
 from gpupsat_b200.instances import parse_dimacs_text, pigeonhole, random_ksat, to_dimacs
+from oracle.binding import Reference
 from tests.helpers import cube_checksum, golden, have_ref
 
 G = golden()
@@ -230,3 +231,30 @@ def test_ternary_state_arithmetic_of_the_sweep_kernel():
     for sgn in (0, 1):
         lit = 2 * v + sgn
         assert np.array_equal(lit // 10, v // 5) and np.array_equal(lit % 10, 2 * (v % 5) + sgn)
+
+
+# ---- SimpleJobChooser (JobsManager/SimpleJobChooser.cu:22-75, behind USE_SIMPLE_JOBS_GENERATION) = GPSAT_STRATEGY_SIMPLE
+@pytest.mark.parametrize("name", ["preprocess-case3", "uf250-1065-seed0"])
+def test_simple_job_chooser_matches_reference_golden(name):
+    d = G["cubes"]["simple"][name]
+    if name == "uf250-1065-seed0":
+        offs, lits = random_ksat(250, 1065, 0)
+    else:
+        pc = G["preprocess"]["case3"]
+        offs, lits = np.array(pc["offsets"], dtype=np.int64), np.array(pc["lits"], dtype=np.int32)
+    pre = g.Cnf.from_arrays(offs, lits).preprocess()
+    cs = pre.choose_cubes(8, 32, g.binding.STRATEGY_SIMPLE)
+    assert cs.shape == (d["n"], d["k"]) and (cs[0] >> 1).tolist() == d["vars"]
+    assert cs[1].tolist() == d["second"] and cs[-1].tolist() == d["last"] and cube_checksum(cs) == d["checksum"]
+    assert not set((cs[0] >> 1).tolist()) & set((pre.solved >> 1).tolist())      # solved (dead) variables are skipped
+
+
+def test_simple_job_chooser_matches_reference_live(reference_available, quiet):
+    if not reference_available:
+        pytest.skip("reference build not present")
+    for seed in (3, 4):
+        offs, lits = random_ksat(40, 170, seed)
+        with quiet():
+            want = Reference(offs, lits).cubes_simple()
+        got = g.Cnf.from_arrays(offs, lits).preprocess().choose_cubes(1, 1, g.binding.STRATEGY_SIMPLE)
+        assert np.array_equal(got, want)

@@ -5,7 +5,7 @@ import pytest
 
 import gpupsat_b200 as g
 from gpupsat_b200.instances import check_model, parse_dimacs_text, pigeonhole, random_ksat
-from oracle.binding import Oracle
+from oracle.binding import Oracle, Reference
 from tests.helpers import cube_csr, golden, have_ref, model_from_lits
 
 G = golden()
@@ -143,3 +143,37 @@ def test_eval_clauses_semantics():
     st, unit = o.eval_clauses(np.array([[F, F, U, U], [T, T, T, U], [U, U, U, U], [F, F, F, T]], dtype=np.uint8))
     assert st.tolist() == [[2, 0, 2], [0, 1, 2], [2, 2, 2], [1, 0, 0]]
     assert unit.tolist() == [[5, -1, -1], [-1, -1, -1], [-1, -1, -1], [-1, -1, -1]]
+
+
+# ---- clause evaluation pinned by EXECUTING the reference's VariablesStateHandler::clause_status
+# (SATSolver/VariablesStateHandler.cu:180-206) — live where oracle/_ref is built from /root/reference, and through the
+# committed fixture (tests/golden/reference_outputs.json: "clause_status") everywhere else
+@pytest.mark.parametrize("name,n,m,seed", [("uf50-218-seed0", 50, 218, 0), ("uf250-1065-seed0", 250, 1065, 0)])
+def test_eval_clauses_equals_reference_golden(name, n, m, seed):
+    offs, lits = random_ksat(n, m, seed)
+    pre = g.Cnf.from_arrays(offs, lits).preprocess()
+    o = Oracle(n, pre.offsets, pre.lits)
+    for row in G["clause_status"][name]:
+        a = np.array(row["assignment"], dtype=np.uint8)
+        st, unit = o.eval_clauses(a[None, :])
+        assert st[0].tolist() == row["status"]
+        assert unit[0].tolist() == row["unit"]
+
+
+def test_eval_clauses_equals_reference_live(reference_available, quiet):
+    if not reference_available:
+        pytest.skip("reference build not present")
+    offs, lits = random_ksat(100, 426, 5)
+    with quiet():
+        R = Reference(offs, lits)
+        poff, plits = R.formula()
+    o = Oracle(100, poff, plits)
+    rg = np.random.default_rng(99)
+    for frac in (0.1, 0.5, 0.9, 1.0):
+        a = np.full(100, 2, dtype=np.uint8)
+        pick = rg.random(100) < frac
+        a[pick] = rg.integers(0, 2, size=int(pick.sum()), dtype=np.uint8)
+        with quiet():
+            st_ref, unit_ref = R.clause_status(a)
+        st, unit = o.eval_clauses(a[None, :])
+        assert st[0].tolist() == st_ref.tolist() and unit[0].tolist() == unit_ref.tolist()
