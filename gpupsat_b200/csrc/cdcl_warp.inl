@@ -1731,7 +1731,7 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
                     // ... but only once this GPU is running dry (more than 1/8 of its warps idle): a warp that merely found
                     // its own ring empty for a moment gets a local child within microseconds
                     if (kind == 3 && mesh && stage != nullptr && !(P.mesh_flags & 1) &&
-                        ((P.mesh_flags & 32) || gpsat_ld_volatile(B.dq_ctrl + GPSAT_DQC_IDLE) >= P.split_hot_demand)) {
+                        gpsat_ld_volatile(B.dq_ctrl + GPSAT_DQC_IDLE) >= P.split_hot_demand) {
                         // children advertised by the other GPUs (their communication warps refresh PEER_QUEUE): claim one
                         // locally first, so that at most as many warps go out over NVLink as there are children to take
                         GPSAT_NOUNROLL
@@ -1742,7 +1742,6 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
                             int *rctrl = (int *)(B.mesh_base[r] + B.mesh_off_ctrl);
                             int *rmeta = (int *)(B.mesh_base[r] + B.mesh_off_meta);
                             gpsat_atomic_add(B.dq_ctrl + GPSAT_DQC_REMOTE_TRIES, 1);
-                            if (P.mesh_flags & 16) continue;   // experiment: claim only
                             idx = gpsat_ring_pop(rctrl, rmeta, B.dq_cap, true);
                             if (idx >= 0) {
                                 kind = 5;
@@ -1789,23 +1788,33 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
             LANE0 { gpsat_atomic_add(B.dq_ctrl + GPSAT_DQC_IDLE, -1); }
         }
         const unsigned long long t_job = gpsat_now_ns();
+        // ONE call site of the solver for every kind of job: each extra site would be another inlined copy of the whole
+        // program, and the instruction cache is this kernel's first bottleneck (profiles/r02_cdcl_ncu_a.json)
+        int job_root, job_k;
+        const int *job_cube, *job_hand = nullptr;
+        bool job_resume = false;
         if (kind == 4) {
-            gpsat_run_and_record(S, S.park[1], S.park + 16, S.park[2], nullptr, P, B, true);
+            job_root = S.park[1];
+            job_cube = S.park + 16;
+            job_k = S.park[2];
+            job_resume = true;
         } else if (kind == 1) {
             const long long c0 = B.cube_offsets[idx], c1 = B.cube_offsets[idx + 1];
             S.inherited = 0;
-            gpsat_run_and_record(S, idx, B.cube_lits + c0, (int)(c1 - c0), nullptr, P, B);
+            job_root = idx;
+            job_cube = B.cube_lits + c0;
+            job_k = (int)(c1 - c0);
         } else if (kind == 2) {
             const int slot = idx & (B.dq_cap - 1);
             gpsat_threadfence();
-            const int root = gpsat_ld_cg(B.dq_meta + 4 * slot);
-            const int len = gpsat_ld_cg(B.dq_meta + 4 * slot + 1);
+            job_root = gpsat_ld_cg(B.dq_meta + 4 * slot);
+            job_k = gpsat_ld_cg(B.dq_meta + 4 * slot + 1);
             S.inherited = gpsat_ld_cg(B.dq_meta + 4 * slot + 3);
-            const int *hand = B.dq_hand + (long long)slot * B.hand_words;
+            job_hand = B.dq_hand + (long long)slot * B.hand_words;
+            job_cube = B.dq_lits + (long long)slot * GPSAT_DQ_MAXK;
             S.rel_slot = slot;
             S.rel_seq = idx + B.dq_cap;   // the ticket that may write this slot next
             S.rel_meta = B.dq_meta;
-            gpsat_run_and_record(S, root, B.dq_lits + (long long)slot * GPSAT_DQ_MAXK, len, hand, P, B);
         } else {
             // a child queued on GPU `peer`: copy its cube and hand-off block over NVLink into this warp's staging block
             // (one bulk copy instead of a dependent remote load per imported clause), free the remote slot, run it here.
@@ -1815,36 +1824,29 @@ GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const
             int *rmeta = (int *)(B.mesh_base[peer] + B.mesh_off_meta);
             const int *rlits = (const int *)(B.mesh_base[peer] + B.mesh_off_lits) + (long long)slot * GPSAT_DQ_MAXK;
             const int *rhand = (const int *)(B.mesh_base[peer] + B.mesh_off_hand) + (long long)slot * B.hand_words;
-            if (P.mesh_flags & 4) gpsat_threadfence(); else gpsat_threadfence_sys();
-            const int root = gpsat_ld_cg(rmeta + 4 * slot);
-            const int len = gpsat_ld_cg(rmeta + 4 * slot + 1);
+            gpsat_threadfence_sys();
+            job_root = gpsat_ld_cg(rmeta + 4 * slot);
+            job_k = gpsat_ld_cg(rmeta + 4 * slot + 1);
             S.inherited = gpsat_ld_cg(rmeta + 4 * slot + 3);
             int used = gpsat_ld_cg(rhand);
             if (used < 0 || used > B.hand_words - 1 - 2 * S.n_vars) used = 0;
-            if (P.mesh_flags & 8) {   // experiment: run straight from the other rank's slot, like a local pop
-                S.rel_slot = slot;
-                S.rel_seq = idx + B.dq_cap;
-                S.rel_meta = rmeta;
-                LANE0 { gpsat_atomic_add(B.dq_ctrl + GPSAT_DQC_STEALS, 1); }
-                gpsat_run_and_record(S, root, rlits, len, rhand, P, B);
-                busy_ns += gpsat_now_ns() - t_job;
-                continue;
-            }
             LANES
             {
                 gpsat_copy_cg(stage, rhand, 1 + 2 * S.n_vars + used, lane);
                 gpsat_copy_cg(stage + B.hand_words, rlits, GPSAT_DQ_MAXK, lane);
             }
             SYNCWARP();
-            if (P.mesh_flags & 4) gpsat_threadfence(); else gpsat_threadfence_sys();
+            gpsat_threadfence_sys();
             LANE0
             {
                 ((volatile int *)rmeta)[4 * slot + 2] = idx + B.dq_cap;   // the remote slot is free again
                 gpsat_atomic_add(B.dq_ctrl + GPSAT_DQC_STEALS, 1);
             }
             SYNCWARP();
-            gpsat_run_and_record(S, root, stage + B.hand_words, len, stage, P, B);
+            job_cube = stage + B.hand_words;
+            job_hand = stage;
         }
+        gpsat_run_and_record(S, job_root, job_cube, job_k, job_hand, P, B, job_resume);
         busy_ns += gpsat_now_ns() - t_job;
     }
     LANE0

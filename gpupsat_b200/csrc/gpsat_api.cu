@@ -141,12 +141,11 @@ struct gpsat {
     DevBuf<uint8_t> val0;
     // occurrence-mode BCP (opts.bcp == GPSAT_BCP_OCCURRENCE)
     DevBuf<int32_t> occ_clause, occ_pair, orange;
-    DevBuf<uint32_t> valbits, valbits_cta, occ_bucket;
+    DevBuf<uint32_t> valbits_cta, occ_bucket;
     DevBuf<int32_t> cube_lits_sorted, cube_short;   // ternary sweep kernel: every cube's literals ordered by occurrence-count class
     int32_t tern_state_bytes = 0;
     DevBuf<int64_t> sweep_counters;
     int uniform3 = 0;
-    int sweep_cluster = 0;   // cluster size used by the last occurrence-mode propagation (0 = HBM-bitmap kernel)
     // cubes
     int32_t n_cubes = 0;
     int32_t cube_base = 0;             // gpsat_propagate: index of the one cube the narrowed job list starts at
@@ -338,8 +337,7 @@ int plan_geometry(gpsat *h, int mode)
     h->state_in_smem = 1;
     h->formula_in_smem = 0;
     h->formula_smem_words = 0;
-    const bool allow_formula = std::getenv("GPSAT_NO_SMEM_FORMULA") == nullptr;
-    if (allow_formula && mode == GPSAT_MODE_SOLVE && f_words * 4 + 8 * bytes_per_warp <= smem_max) {
+    if (mode == GPSAT_MODE_SOLVE && f_words * 4 + 8 * bytes_per_warp <= smem_max) {
         h->formula_in_smem = 1;
         h->formula_smem_words = (int)f_words;
     }
@@ -579,78 +577,27 @@ int propagate_all_occurrence(gpsat *h, int32_t *status, int32_t *n_implied, int3
     const size_t nc = (size_t)h->n_cubes;
     if (implied_stride <= 0) implied_stride = h->D.n_vars;       // the implied block doubles as the trail
     const int32_t val_words = (h->D.n_vars + 15) / 16;
-    // Kernel choice, best first (measured on C4):
+    // Kernel choice (measured on C4):
     //   1. ternary kernel — pure 3-SAT whose base-3 state fits one SM (gpsat_create built the bucket index);
     //   2. one CTA per job, assigned-bit filter in shared memory + 2-bit values in an L2-resident global block — any
-    //      clause lengths, as long as one bit per variable fits one SM;
-    //   3. one thread-block cluster per job with the 2-bit bitmap in distributed shared memory: the smallest cluster
-    //      whose per-CTA slice is at most 160 KB (measured faster than more, smaller slices, whose larger share of
-    //      remote lookups loads the SM-to-SM network: profiles/r01_c4_sweep_f.json);
-    //   4. HBM-bitmap kernel (one warp per job) when even 16 CTAs cannot hold the bitmap.
-    // GPSAT_SWEEP_TERNARY=0 / GPSAT_SWEEP_CLUSTER / GPSAT_SWEEP_THREADS / GPSAT_SWEEP_SLICE_KB override for
-    // experiments and tests (GPSAT_SWEEP_CLUSTER=0: HBM-bitmap kernel).
-    int cluster = 0, slice_log2 = 4, cthreads = 1024;
-    // first choice when the database qualifies (gpsat_create built the bucket index): the ternary kernel
-    const bool use_tern = h->tern_state_bytes > 0 && !std::getenv("GPSAT_SWEEP_CLUSTER") &&
-                          !(std::getenv("GPSAT_SWEEP_TERNARY") && std::atoi(std::getenv("GPSAT_SWEEP_TERNARY")) == 0);
+    //      clause lengths, any variable count (the filter is exact up to 2^20 variables, aliased beyond).
+    // opts.sweep_flags (test hook): 1 = general kernel even for pure 3-SAT, bits 8.. = log2 of the filter size.
+    const bool use_tern = h->tern_state_bytes > 0 && !(h->opts.sweep_flags & 1);
+    int cluster = -1, slice_log2 = 10, cthreads = 1024;
     {
-        const char *e_cl = std::getenv("GPSAT_SWEEP_CLUSTER"), *e_th = std::getenv("GPSAT_SWEEP_THREADS"),
-                   *e_kb = std::getenv("GPSAT_SWEEP_SLICE_KB");
-        const int slice_kb = e_kb ? std::atoi(e_kb) : 160;
-        if (e_th) cthreads = std::max(32, std::min(1024, std::atoi(e_th) / 32 * 32));
-        int want = e_cl ? std::atoi(e_cl) : -1;
-        // first choice: one CTA per job, assigned bits (n/8 bytes) in shared memory, values in global (no cluster)
-        if (want < 0) {
-            // exact filter: 2^k >= n bits; GPSAT_SWEEP_CTAS=2 halves it (aliased filter) so that two CTAs share an SM
-            const char *e_ct = std::getenv("GPSAT_SWEEP_CTAS");
-            const int per_sm = e_ct ? std::max(1, std::min(2, std::atoi(e_ct))) : 1;
-            int lg = 10;
-            while (((int64_t)1 << lg) < h->D.n_vars) lg++;
-            if (per_sm == 2 && lg > 10) lg--;
-            if (((size_t)1 << (lg - 3)) + 1024 <= h->prop.sharedMemPerBlockOptin / (size_t)per_sm) {
-                cluster = -per_sm;
-                slice_log2 = lg;
-                want = 0;
-            }
-        }
-        if (want != 0) {
-            for (int cs = (want > 0 ? want : 1); cs <= 16; cs *= 2) {
-                int lg = 4;
-                while (((int64_t)1 << lg) * cs < val_words) lg++;
-                if (((int64_t)4 << lg) <= (int64_t)slice_kb * 1024 || (want > 0 && ((int64_t)4 << lg) <= 200 * 1024)) {
-                    cluster = cs;
-                    slice_log2 = lg;
-                    break;
-                }
-                if (want > 0) break;
-            }
-        }
+        int lg = 10;
+        while (((int64_t)1 << lg) < h->D.n_vars) lg++;
+        while (lg > 10 && ((size_t)1 << (lg - 3)) + 1024 > h->prop.sharedMemPerBlockOptin) lg--;   // aliased filter
+        const int forced = (h->opts.sweep_flags >> 8) & 31;
+        if (forced >= 10 && forced <= lg) lg = forced;
+        slice_log2 = lg;
     }
-    int wpb = h->opts.warps_per_block > 0 ? std::min(h->opts.warps_per_block, 32) : 32;
-    int blocks = h->opts.blocks > 0 ? h->opts.blocks : h->prop.multiProcessorCount;   // 1024 threads: 1 block per SM
-    if (cluster > 0) {
-        wpb = cthreads / 32;
-        int cap = 0;
-        CU(gpsat_kernels::sweep_cluster_capacity(cluster, cthreads, (size_t)4 << slice_log2, &cap));
-        if (cap < 1) {
-            cluster = 0;   // this cluster shape cannot be scheduled: HBM-bitmap kernel
-            wpb = 32;
-        } else {
-            blocks = h->opts.blocks > 0 ? std::min(h->opts.blocks, cap) : cap;
-            if ((int64_t)blocks > (int64_t)nc) blocks = (int)std::max<size_t>(nc, 1);
-        }
-    }
-    if (cluster == 0) {
-        const int64_t need = ((int64_t)nc + wpb - 1) / wpb;
-        if (blocks > need) blocks = (int)std::max<int64_t>(need, 1);
-    }
+    int wpb = cthreads / 32;
+    int blocks = h->prop.multiProcessorCount;
     int32_t cta_val_words = 0;
-    if (cluster < 0) {
-        wpb = cthreads / 32;
+    if (!use_tern) {
         int per_sm = 0;
-        if (cluster == -2 && !std::getenv("GPSAT_SWEEP_THREADS")) cthreads = 768;
-        wpb = cthreads / 32;
-        CU(gpsat_kernels::sweep_cta_capacity(slice_log2, cthreads, -cluster, &per_sm));
+        CU(gpsat_kernels::sweep_cta_capacity(slice_log2, cthreads, 1, &per_sm));
         if (per_sm < 1) {
             set_error("sweep kernel configuration does not fit on an SM");
             return GPSAT_E_CUDA;
@@ -661,12 +608,7 @@ int propagate_all_occurrence(gpsat *h, int32_t *status, int32_t *n_implied, int3
         cta_val_words = (val_words + 3) / 4 * 4;
         CU(h->valbits_cta.ensure((size_t)blocks * (size_t)cta_val_words));   // zeroed by the kernel per job
     }
-    const size_t n_warps = (size_t)blocks * wpb;
     CU(h->ctrl.ensure(4));
-    if (cluster == 0 && h->valbits.n < n_warps * (size_t)val_words) {
-        CU(h->valbits.ensure(n_warps * (size_t)val_words));
-        CU(cudaMemsetAsync(h->valbits.p, 0, n_warps * (size_t)val_words * sizeof(uint32_t), h->stream));
-    }
     CU(h->implied.ensure(nc * (size_t)implied_stride));
     CU(h->n_implied.ensure(nc));
     CU(h->conflict_clause.ensure(nc));
@@ -687,8 +629,8 @@ int propagate_all_occurrence(gpsat *h, int32_t *status, int32_t *n_implied, int3
     L.clits = h->clits.p;
     L.cube_offsets = h->cube_offsets.p;
     L.cube_lits = h->cube_lits.p;
-    L.valbits = cluster < 0 ? h->valbits_cta.p : h->valbits.p;
-    L.val_words = cluster < 0 ? cta_val_words : val_words;
+    L.valbits = h->valbits_cta.p;
+    L.val_words = cta_val_words;
     L.implied = h->implied.p;
     L.stride = implied_stride;
     L.n_implied = h->n_implied.p;
@@ -699,9 +641,10 @@ int propagate_all_occurrence(gpsat *h, int32_t *status, int32_t *n_implied, int3
     L.blocks = blocks;
     L.warps_per_block = wpb;
     L.cluster_size = cluster;
-    // measured (C4, 1184 jobs): evict-first index loads 12.9 -> 11.2 ms, L2 persistence of the value blocks 11.0 ms
-    L.stream_index = std::getenv("GPSAT_SWEEP_LDCS") ? std::atoi(std::getenv("GPSAT_SWEEP_LDCS")) : (use_tern ? 2 : 1);
-    if (cluster < 0 && !use_tern && (!std::getenv("GPSAT_SWEEP_PERSIST") || std::atoi(std::getenv("GPSAT_SWEEP_PERSIST")))) {
+    // measured (C4, 1184 jobs): CTA-filter kernel — evict-first index loads 12.9 -> 11.2 ms, L2 persistence of the value
+    // blocks 11.0 ms; ternary kernel — 2 x 32-byte read-only bucket loads
+    L.stream_index = use_tern ? 2 : 1;
+    if (!use_tern) {
         // keep the per-CTA value blocks resident in L2 while the occurrence index streams through it
         const size_t bytes = (size_t)blocks * (size_t)cta_val_words * sizeof(uint32_t);
         int max_win = 0, max_persist = 0;
@@ -719,40 +662,28 @@ int propagate_all_occurrence(gpsat *h, int32_t *status, int32_t *n_implied, int3
         cudaGetLastError();
     }
     L.slice_log2 = slice_log2;
-    if (const char *e_fg = std::getenv("GPSAT_L2_FETCH")) {   // experiment: L2 fetch granularity hint (32 / 64 / 128)
-        size_t before = 0, after = 0;
-        cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
-        cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(e_fg));
-        cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
-        std::fprintf(stderr, "[gpsat] L2 fetch granularity %zu -> %zu (%s)\n", before, after, cudaGetErrorString(e));
-        cudaGetLastError();
-    }
     if (use_tern) {   // one CTA per SM, whole job state in shared memory: nothing else to size
         L.bucket = h->occ_bucket.p;
         L.tern_state_bytes = h->tern_state_bytes;
-        L.l2_prefetch = std::getenv("GPSAT_SWEEP_L2PF") ? std::atoi(std::getenv("GPSAT_SWEEP_L2PF")) : 0;   // measured: 4.39 ms either way
-        if (h->cube_lits_sorted.p && !(std::getenv("GPSAT_SWEEP_SORT") && std::atoi(std::getenv("GPSAT_SWEEP_SORT")) == 0))
+        L.l2_prefetch = 0;       // measured: 4.39 ms with or without prefetch.global.L2 of the next batch's buckets
+        if (h->cube_lits_sorted.p)
             L.cube_lits = h->cube_lits_sorted.p, L.cube_short = h->cube_short.p + h->cube_base;   // per-cube info follows the narrowed job list
-        // measured on C4: 5.59 ms without, 5.67 ms with the bucket fetched one batch ahead (the lookups, not memory, bound it)
-        L.tern_prefetch = std::getenv("GPSAT_SWEEP_PREFETCH") ? std::atoi(std::getenv("GPSAT_SWEEP_PREFETCH")) : 0;
+        L.tern_prefetch = 0;     // measured: 5.59 ms without, 5.67 ms with the bucket fetched one batch ahead in registers
         blocks = h->prop.multiProcessorCount;
         if (h->opts.blocks > 0) blocks = std::min(blocks, h->opts.blocks);
         if ((int64_t)blocks > (int64_t)nc) blocks = (int)std::max<size_t>(nc, 1);
         wpb = 32;
-        cluster = -1;
         L.blocks = blocks;
         L.warps_per_block = wpb;
-        L.cluster_size = cluster;
     }
-    if (cluster != 0) CU(cudaMemsetAsync(h->sweep_counters.p, 0, 2 * nc * sizeof(int64_t), h->stream));
+    L.cluster_size = cluster;
+    CU(cudaMemsetAsync(h->sweep_counters.p, 0, 2 * nc * sizeof(int64_t), h->stream));
     h->kernel_ms = 0;
     h->kernel_launches = 0;
     h->blocks = blocks;
     h->warps_per_block = wpb;
-    h->smem_bytes = use_tern ? gpsat_kernels::tern_smem_bytes(h->tern_state_bytes)
-                             : cluster > 0 ? ((size_t)4 << slice_log2) : cluster < 0 ? ((size_t)1 << (slice_log2 - 3)) : 512;
-    h->state_in_smem = cluster != 0 ? 1 : 0;
-    h->sweep_cluster = cluster;
+    h->smem_bytes = use_tern ? gpsat_kernels::tern_smem_bytes(h->tern_state_bytes) : ((size_t)1 << (slice_log2 - 3));
+    h->state_in_smem = 1;
     CU(cudaEventRecord(h->ev0, h->stream));
     CU(gpsat_kernels::launch_bcp_sweep(L, h->stream));
     CU(cudaEventRecord(h->ev1, h->stream));
@@ -900,11 +831,9 @@ int gpsat_create(gpsat_t **out, int32_t n_vars, int64_t n_clauses, const int64_t
     if (h->opts.bcp == GPSAT_BCP_OCCURRENCE) {
         // Occurrence index of the sweep kernels (host_formula.cpp: build_sweep_index).  The bucket index and with it the
         // ternary kernel (gpsat_bcp_sweep_tern_kernel) are used for pure 3-SAT whose literal ids fit 21 bits and whose
-        // base-3 state (five variables per byte) fits one SM's shared memory beside the lookup table;
-        // GPSAT_SWEEP_TERNARY=0 keeps the other kernels.
-        const char *e_tn = std::getenv("GPSAT_SWEEP_TERNARY");
+        // base-3 state (five variables per byte) fits one SM's shared memory beside the lookup table.
         const int32_t state_bytes = (int32_t)((((int64_t)n_vars + 1 + 4) / 5 + 15) / 16 * 16);
-        const bool want_buckets = !(e_tn && std::atoi(e_tn) == 0) &&
+        const bool want_buckets = !(h->opts.sweep_flags & 1) &&
                                   gpsat_kernels::tern_smem_bytes(state_bytes) + 256 <= h->prop.sharedMemPerBlockOptin;
         gpsat_host::SweepIndex X;
         gpsat_host::build_sweep_index(h->D, want_buckets, X);

@@ -454,17 +454,19 @@ cudaError_t launch_eval_clauses(int32_t n_vars, int32_t n_clauses, const int32_t
 }  // namespace gpsat_kernels
 
 // ---------------------------------------------------------------------------------------------------------------
-// gpsat_bcp_sweep_kernel — BCP by clause evaluation over occurrence lists for LARGE clause databases (config 4:
-// n = 1e6, m = 4e6), where neither watch state nor assignments of a job fit in shared memory.
+// BCP by clause evaluation over occurrence lists for LARGE clause databases (config 4: n = 1e6, m = 4e6), where neither
+// watch state nor assignments of a job fit beside the formula in shared memory.
 //   ≙ ConflictAnalyzer::propagate_all_clauses + VariablesStateHandler::clause_status
 //     (ConflictAnalysis/ConflictAnalyzer.cu:173-245, SATSolver/VariablesStateHandler.cu:180-206) made incremental:
 //     only clauses containing a literal that just became false are evaluated.
-// One warp per job (cube).  The job's assignment is a 2-bit-per-variable bitmap in HBM (bit1 = assigned, bit0 =
-// value); its trail is the cube followed by the implied literals, which are written straight into the caller's
-// `implied` block.  Each lane owns one trail literal of the current batch of 32 and walks that literal's occurrence
-// list, so a warp keeps ~32 x (entries + 2 gathers) independent loads in flight; all cube literals are assigned
-// before propagation starts, as the reference does (VariablesStateHandler::set_assumptions, SATSolver.cu:231-246).
-// Unit propagation is confluent: status and, without conflict, the implied SET do not depend on the visiting order.
+// One CTA per job (cube); the trail is the cube followed by the implied literals, written straight into the caller's
+// `implied` block; all cube literals are assigned before propagation starts, as the reference does
+// (VariablesStateHandler::set_assumptions, SATSolver.cu:231-246).  Unit propagation is confluent: status and, without
+// conflict, the implied SET do not depend on the visiting order.  Two kernels:
+//   gpsat_bcp_sweep_tern_kernel  pure 3-SAT, n <= ~1.04 M: whole assignment on chip (base-3 digits), bucket index
+//   gpsat_bcp_sweep_cta_kernel   every other database: assigned-bit filter on chip, values in an L2-resident block
+// (round 1 also shipped a warp-per-job kernel with the bitmap in HBM and a thread-block-cluster kernel with the bitmap in
+// distributed shared memory; both were 3-20x slower — profiles/r01_sweep_ncu_e.json, r01_sweepc_ncu_f.json — and are gone.)
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
 
@@ -494,416 +496,6 @@ struct SweepArgs {
     int32_t *next_job;
 };
 
-__device__ __forceinline__ int sw_value(const uint32_t *vb, int x)
-{
-    // L2-coherent load: other lanes assign through atomics (performed at L2); a line cached in L1 could be stale and
-    // hide BOTH sides of a unit clause from the two lanes that visit it (lost implication)
-    const uint32_t w = __ldcg(vb + (x >> 5));      // var = x>>1, 16 vars per word -> word (x>>1)>>4
-    const uint32_t f = (w >> (((x >> 1) & 15) * 2)) & 3u;
-    return (f & 2u) ? (int)((f & 1u) == (uint32_t)(x & 1)) : 2;   // 1 true, 0 false, 2 unassigned
-}
-
-// assign literal x; returns previous field (0 = was unassigned)
-__device__ __forceinline__ uint32_t sw_assign(uint32_t *vb, int x)
-{
-    const int sh = ((x >> 1) & 15) * 2;
-    const uint32_t prev = atomicOr(vb + (x >> 5), (2u | (uint32_t)(x & 1)) << sh);
-    return (prev >> sh) & 3u;
-}
-
-__global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_kernel(const SweepArgs A)
-{
-    __shared__ int s_count[32];        // implied literals appended so far, per warp
-    __shared__ int s_conflict[32];     // 0 none, 1 conflict seen
-    __shared__ long long s_clause[32];
-    const int lane = (int)(threadIdx.x & 31u), wib = (int)(threadIdx.x >> 5);
-    const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
-    uint32_t *vb = A.valbits + (size_t)gwarp * (size_t)A.val_words;
-
-    while (true) {
-        int job = 0;
-        if (lane == 0) job = atomicAdd(A.next_job, 1);
-        job = __shfl_sync(0xffffffffu, job, 0);
-        if (job >= A.n_cubes) break;
-        const long long c0 = A.cube_offsets[job], c1 = A.cube_offsets[job + 1];
-        const int k = (int)(c1 - c0);
-        const int32_t *cube = A.cube_lits + c0;
-        int32_t *imp = A.implied + (long long)job * A.stride;
-        if (lane == 0) {
-            s_count[wib] = 0;
-            s_conflict[wib] = 0;
-            s_clause[wib] = -1;
-        }
-        __syncwarp();
-        // phase 0: the whole cube is assigned up front
-        for (int i = lane; i < k; i += 32) {
-            const int x = cube[i];
-            const uint32_t prev = sw_assign(vb, x);
-            if ((prev & 2u) && (prev & 1u) != (uint32_t)(x & 1)) s_conflict[wib] = 1;   // x and ~x in one cube
-        }
-        __syncwarp();
-        long long visited = 0, words = 0;
-        // phase 1: trail = cube ++ implied; 32 trail literals per batch, one per lane
-        int qhead = 0;
-        while (!s_conflict[wib]) {
-            const int total = k + min(s_count[wib], (int)A.stride);
-            if (qhead >= total) break;
-            const int t = qhead + lane;
-            if (t < total) {
-                const int p = t < k ? cube[t] : imp[t - k];
-                const int f = p ^ 1;
-                const int2 rg = __ldg(A.orange + f);
-                const int os = rg.x, oe = rg.y;
-                for (int e = os; e < oe; ++e) {
-                    int a, b, c = -1, unit = -1, n_false = 0, n_undef = 0;
-                    bool sat = false;
-                    if (A.uniform3) {
-                        const int2 pr = __ldg(A.occ_pair + e);
-                        if (pr.x < 0) continue;   // padding
-                        a = pr.x;
-                        b = pr.y;
-                        const int va = sw_value(vb, a), vb2 = sw_value(vb, b);
-                        sat = (va == 1) || (vb2 == 1);
-                        n_false = (va == 0) + (vb2 == 0);
-                        n_undef = (va == 2) + (vb2 == 2);
-                        unit = (va == 2) ? a : b;
-                        words += 2;
-                    } else {
-                        c = __ldg(A.occ_clause + e);
-                        if (c < 0) continue;      // padding
-                        const int lb = __ldg(A.coffsets + c), le = __ldg(A.coffsets + c + 1);
-                        for (int i = lb; i < le && !sat; ++i) {
-                            const int x = __ldg(A.clits + i);
-                            words++;
-                            if (x == f) continue;
-                            const int v = sw_value(vb, x);
-                            if (v == 1) sat = true;
-                            else if (v == 0) n_false++;
-                            else { n_undef++; unit = x; }
-                        }
-                    }
-                    visited++;
-                    if (sat || n_undef > 1) continue;
-                    if (n_undef == 0) {                               // every other literal false: conflict
-                        if (c < 0) c = __ldg(A.occ_clause + e);
-                        s_conflict[wib] = 1;
-                        s_clause[wib] = c;
-                        break;
-                    }
-                    const uint32_t prev = sw_assign(vb, unit);        // exactly one unassigned literal: imply it
-                    if (prev == 0) {
-                        const int pos = atomicAdd(&s_count[wib], 1);
-                        if (pos < A.stride) imp[pos] = unit;
-                    } else if ((prev & 1u) != (uint32_t)(unit & 1)) {  // lost a race against the opposite literal
-                        if (c < 0) c = __ldg(A.occ_clause + e);
-                        s_conflict[wib] = 1;
-                        s_clause[wib] = c;
-                        break;
-                    }
-                }
-            }
-            __syncwarp();
-            qhead = min(qhead + 32, total);   // literals appended during this batch start the next one
-        }
-        __syncwarp();
-        const int n_imp = s_count[wib];
-        const int conflict = s_conflict[wib];
-        // restore the bitmap to all-unassigned for the next job of this warp (only the words we touched)
-        for (int i = lane; i < k; i += 32) atomicAnd(vb + (cube[i] >> 5), ~(3u << (((cube[i] >> 1) & 15) * 2)));
-        const int n_written = min(n_imp, (int)A.stride);
-        for (int i = lane; i < n_written; i += 32) atomicAnd(vb + (imp[i] >> 5), ~(3u << (((imp[i] >> 1) & 15) * 2)));
-        if (n_imp > n_written)   // implied block too small: some assigned variables are not listed, clear everything
-            for (int i = lane; i < A.val_words; i += 32) vb[i] = 0u;
-        __syncwarp();
-        for (int o = 16; o > 0; o >>= 1) {
-            visited += __shfl_xor_sync(0xffffffffu, visited, o);
-            words += __shfl_xor_sync(0xffffffffu, words, o);
-        }
-        if (lane == 0) {
-            // truncated trail (implied block too small) without a conflict: no verdict for this cube
-            A.status[job] = conflict ? GPSAT_UNSAT : (n_imp > n_written ? GPSAT_JOB_OOM : GPSAT_UNDEF);
-            A.n_implied[job] = n_imp;
-            A.conflict_clause[job] = conflict ? s_clause[wib] : -1;
-            if (A.counters) {
-                A.counters[2 * job] = visited;
-                A.counters[2 * job + 1] = words;
-            }
-        }
-        __syncwarp();
-    }
-}
-
-
-// ---------------------------------------------------------------------------------------------------------------
-// gpsat_bcp_sweep_cluster_kernel — the same occurrence-list BCP with the job's assignment bitmap held ON CHIP:
-// one thread-block CLUSTER per job, the 2-bit-per-variable bitmap (250 KB at n = 1e6, more than one SM's shared
-// memory) is split across the shared memories of the cluster's CTAs and read / updated through distributed shared
-// memory (mapa + ld/atom.shared::cluster).  The HBM-bitmap kernel above spends 2/3 of its time on the two random
-// 4-byte bitmap gathers per visited entry, each of which costs a 32-byte DRAM sector (ncu: 15x more DRAM traffic
-// than algorithmic bytes); here those gathers never leave the SMs, and HBM/L2 only stream the formula index
-// (ostart + occurrence pairs), which is what the algorithmic byte count charges for.
-//   * all threads of the cluster (cluster_size x blockDim) each own one trail literal per round;
-//   * a round ends with two cluster barriers around a snapshot of (trail length, conflict flag) taken by the
-//     leader, so that every thread sees the same loop bounds;
-//   * units are assigned with a remote atomicOr and appended to the trail (the caller's `implied` block in HBM)
-//     through one atomic on the leader's counter.
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t dsm_addr(uint32_t local_addr, uint32_t rank)
-{
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ uint32_t dsm_ld(uint32_t addr)
-{
-    uint32_t v;
-    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void dsm_st(uint32_t addr, uint32_t v)
-{
-    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t dsm_atom_or(uint32_t addr, uint32_t v)
-{
-    uint32_t o;
-    asm volatile("atom.shared::cluster.or.b32 %0, [%1], %2;" : "=r"(o) : "r"(addr), "r"(v) : "memory");
-    return o;
-}
-__device__ __forceinline__ uint32_t dsm_atom_add(uint32_t addr, uint32_t v)
-{
-    uint32_t o;
-    asm volatile("atom.shared::cluster.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(addr), "r"(v) : "memory");
-    return o;
-}
-__device__ __forceinline__ void cluster_sync_all()
-{
-    __syncwarp();
-    asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_rank()
-{
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ uint32_t cluster_size()
-{
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-    return r;
-}
-
-// control words in the leader CTA (rank 0) of the cluster
-enum { CW_COUNT = 0, CW_CONFLICT, CW_CLAUSE, CW_JOB, CW_SNAP_TOTAL, CW_SNAP_CONFLICT, CW_WORDS };
-
-struct ClusterBits {
-    uint32_t base;        // shared-window address of this CTA's slice (same offset in every CTA of the cluster)
-    uint32_t base0;       // shared::cluster address of rank 0's slice
-    uint32_t stride;      // shared::cluster address distance between consecutive ranks (0: not linear, use mapa)
-    int slice_log2;       // words per slice = 1 << slice_log2
-    // `mapa` executes on the XU pipe (16 lanes per SM and cycle): one per lookup kept that pipe 89 % busy and made it
-    // the limiter of the kernel (profiles/r01_sweepc_ncu_f.json).  The cluster window is linear in the rank, so the
-    // remote address is one multiply-add; init() verifies the linearity and falls back to mapa otherwise.
-    __device__ __forceinline__ void init(const void *slice, int log2_words, uint32_t csize)
-    {
-        base = smem_u32(slice);
-        slice_log2 = log2_words;
-        base0 = dsm_addr(base, 0);
-        stride = csize > 1 ? dsm_addr(base, 1) - base0 : 0u;
-        for (uint32_t r = 2; r < csize; ++r)
-            if (dsm_addr(base, r) != base0 + r * stride) stride = 0u;
-        if (csize == 1) stride = 1u;   // any non-zero value: rank is always 0
-    }
-    // address of the word holding literal x's variable (16 variables per word)
-    __device__ __forceinline__ uint32_t word_addr(int x) const
-    {
-        const uint32_t w = (uint32_t)x >> 5;
-        const uint32_t off = (w & ((1u << slice_log2) - 1u)) << 2, r = w >> slice_log2;
-        return stride ? base0 + r * stride + off : dsm_addr(base + off, r);
-    }
-    __device__ __forceinline__ int value(int x) const   // 1 true, 0 false, 2 unassigned
-    {
-        const uint32_t f = (dsm_ld(word_addr(x)) >> (((x >> 1) & 15) * 2)) & 3u;
-        return (f & 2u) ? (int)((f & 1u) == (uint32_t)(x & 1)) : 2;
-    }
-    __device__ __forceinline__ uint32_t assign(int x) const   // returns the previous 2-bit field (0 = was unassigned)
-    {
-        const int sh = ((x >> 1) & 15) * 2;
-        return (dsm_atom_or(word_addr(x), (2u | (uint32_t)(x & 1)) << sh) >> sh) & 3u;
-    }
-};
-
-__global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_cluster_kernel(const SweepArgs A, const int slice_log2)
-{
-    extern __shared__ __align__(16) uint32_t s_slice[];
-    __shared__ uint32_t s_ctrl[CW_WORDS];
-    const uint32_t rank = cluster_rank(), csize = cluster_size();
-    const int cthreads = (int)(csize * blockDim.x), ctid = (int)(rank * blockDim.x + threadIdx.x);
-    const int slice_words = 1 << slice_log2;
-    ClusterBits bits;
-    bits.init(s_slice, slice_log2, csize);
-    const uint32_t ctrl0 = dsm_addr(smem_u32(s_ctrl), 0);   // the leader's control words
-
-    while (true) {
-        if (rank == 0 && threadIdx.x == 0) {
-            s_ctrl[CW_JOB] = (uint32_t)atomicAdd(A.next_job, 1);
-            s_ctrl[CW_COUNT] = 0;
-            s_ctrl[CW_CONFLICT] = 0;
-            s_ctrl[CW_CLAUSE] = 0xffffffffu;
-        }
-        {
-            uint4 *z = reinterpret_cast<uint4 *>(s_slice);
-            for (int i = (int)threadIdx.x; i < slice_words / 4; i += (int)blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
-        }
-        cluster_sync_all();
-        const int job = (int)dsm_ld(ctrl0 + 4 * CW_JOB);
-        if (job >= A.n_cubes) {        // same value in every thread of the cluster
-            cluster_sync_all();        // nobody leaves while a peer may still be reading its shared memory
-            break;
-        }
-        const long long c0 = A.cube_offsets[job], c1 = A.cube_offsets[job + 1];
-        const int k = (int)(c1 - c0);
-        const int32_t *cube = A.cube_lits + c0;
-        int32_t *imp = A.implied + (long long)job * A.stride;
-
-        // phase 0: the whole cube is assigned up front (VariablesStateHandler::set_assumptions)
-        for (int i = ctid; i < k; i += cthreads) {
-            const int x = __ldg(cube + i);
-            const uint32_t prev = bits.assign(x);
-            if ((prev & 2u) && (prev & 1u) != (uint32_t)(x & 1)) dsm_st(ctrl0 + 4 * CW_CONFLICT, 1u);   // x and ~x
-        }
-        cluster_sync_all();
-        if (rank == 0 && threadIdx.x == 0) {
-            s_ctrl[CW_SNAP_TOTAL] = (uint32_t)k;
-            s_ctrl[CW_SNAP_CONFLICT] = s_ctrl[CW_CONFLICT];
-        }
-        cluster_sync_all();
-
-        long long visited = 0, words = 0;
-        int qhead = 0;
-        while (true) {
-            const int total = (int)dsm_ld(ctrl0 + 4 * CW_SNAP_TOTAL);
-            const int conflict = (int)dsm_ld(ctrl0 + 4 * CW_SNAP_CONFLICT);
-            if (conflict || qhead >= total) break;
-            for (int t = qhead + ctid; t < total; t += cthreads) {
-                const int p = t < k ? __ldg(cube + t) : __ldcg(imp + (t - k));
-                const int f = p ^ 1;
-                const int2 rg = __ldg(A.orange + f);
-                const int os = rg.x, oe = rg.y;   // both even: the list is read as 16-byte loads of two entries
-                for (int e0 = os; e0 < oe; e0 += 4) {
-                    const int cnt = min(4, oe - e0);
-                    if (A.uniform3) {
-                        int2 pr[4];
-                        int va[4], vb[4];
-                        {
-                            const int4 q0 = __ldg(reinterpret_cast<const int4 *>(A.occ_pair + e0));
-                            pr[0] = make_int2(q0.x, q0.y);
-                            pr[1] = make_int2(q0.z, q0.w);
-                            pr[2] = pr[3] = make_int2(-1, -1);
-                            if (cnt > 2) {
-                                const int4 q1 = __ldg(reinterpret_cast<const int4 *>(A.occ_pair + e0 + 2));
-                                pr[2] = make_int2(q1.x, q1.y);
-                                pr[3] = make_int2(q1.z, q1.w);
-                            }
-                        }
-                        int real = 0;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (pr[j].x >= 0) {
-                                va[j] = bits.value(pr[j].x);
-                                vb[j] = bits.value(pr[j].y);
-                                real++;
-                            }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (pr[j].x >= 0) {
-                                if (va[j] == 1 || vb[j] == 1) continue;
-                                const int n_undef = (va[j] == 2) + (vb[j] == 2);
-                                if (n_undef > 1) continue;
-                                if (n_undef == 0) {   // every other literal false: conflict
-                                    dsm_st(ctrl0 + 4 * CW_CLAUSE, (uint32_t)__ldg(A.occ_clause + e0 + j));
-                                    dsm_st(ctrl0 + 4 * CW_CONFLICT, 1u);
-                                    continue;
-                                }
-                                const int unit = (va[j] == 2) ? pr[j].x : pr[j].y;
-                                const uint32_t prev = bits.assign(unit);
-                                if (prev == 0) {
-                                    const int pos = (int)dsm_atom_add(ctrl0 + 4 * CW_COUNT, 1u);
-                                    if (pos < A.stride) imp[pos] = unit;
-                                } else if ((prev & 1u) != (uint32_t)(unit & 1)) {   // lost a race against ~unit
-                                    dsm_st(ctrl0 + 4 * CW_CLAUSE, (uint32_t)__ldg(A.occ_clause + e0 + j));
-                                    dsm_st(ctrl0 + 4 * CW_CONFLICT, 1u);
-                                }
-                            }
-                        visited += real;
-                        words += 2 * real;
-                    } else {
-                        for (int j = 0; j < cnt; ++j) {
-                            const int c = __ldg(A.occ_clause + e0 + j);
-                            if (c < 0) continue;   // padding
-                            const int lb = __ldg(A.coffsets + c), le = __ldg(A.coffsets + c + 1);
-                            int unit = -1, n_undef = 0;
-                            bool sat = false;
-                            for (int i = lb; i < le && !sat; ++i) {
-                                const int x = __ldg(A.clits + i);
-                                words++;
-                                if (x == f) continue;
-                                const int v = bits.value(x);
-                                if (v == 1) sat = true;
-                                else if (v == 2) { n_undef++; unit = x; }
-                            }
-                            visited++;
-                            if (sat || n_undef > 1) continue;
-                            if (n_undef == 0) {
-                                dsm_st(ctrl0 + 4 * CW_CLAUSE, (uint32_t)c);
-                                dsm_st(ctrl0 + 4 * CW_CONFLICT, 1u);
-                                continue;
-                            }
-                            const uint32_t prev = bits.assign(unit);
-                            if (prev == 0) {
-                                const int pos = (int)dsm_atom_add(ctrl0 + 4 * CW_COUNT, 1u);
-                                if (pos < A.stride) imp[pos] = unit;
-                            } else if ((prev & 1u) != (uint32_t)(unit & 1)) {
-                                dsm_st(ctrl0 + 4 * CW_CLAUSE, (uint32_t)c);
-                                dsm_st(ctrl0 + 4 * CW_CONFLICT, 1u);
-                            }
-                        }
-                    }
-                }
-            }
-            __threadfence();          // trail entries written this round are read by other SMs in the next one
-            cluster_sync_all();
-            if (rank == 0 && threadIdx.x == 0) {
-                const int cnt = (int)min((long long)s_ctrl[CW_COUNT], (long long)A.stride);
-                s_ctrl[CW_SNAP_TOTAL] = (uint32_t)(k + cnt);
-                s_ctrl[CW_SNAP_CONFLICT] = s_ctrl[CW_CONFLICT];
-            }
-            cluster_sync_all();
-            qhead = total;
-        }
-        // per-job counters: one pair of global atomics per warp
-        for (int o = 16; o > 0; o >>= 1) {
-            visited += __shfl_xor_sync(0xffffffffu, visited, o);
-            words += __shfl_xor_sync(0xffffffffu, words, o);
-        }
-        if ((threadIdx.x & 31u) == 0 && A.counters) {
-            atomicAdd((unsigned long long *)(A.counters + 2 * job), (unsigned long long)visited);
-            atomicAdd((unsigned long long *)(A.counters + 2 * job + 1), (unsigned long long)words);
-        }
-        if (rank == 0 && threadIdx.x == 0) {
-            const int n_imp = (int)s_ctrl[CW_COUNT];
-            const int conflict = (int)s_ctrl[CW_CONFLICT];
-            A.status[job] = conflict ? GPSAT_UNSAT : (n_imp > A.stride ? GPSAT_JOB_OOM : GPSAT_UNDEF);
-            A.n_implied[job] = n_imp;
-            A.conflict_clause[job] = conflict ? (long long)(int)s_ctrl[CW_CLAUSE] : -1;
-        }
-        cluster_sync_all();   // the leader's control words are re-armed only after everybody is done with them
-    }
-}
-
-
 // ---------------------------------------------------------------------------------------------------------------
 // gpsat_bcp_sweep_cta_kernel — occurrence-list BCP with ONE CTA per job and a two-level assignment:
 //   A  "assigned" bit per variable in SHARED memory (n/8 bytes: 125 KB at n = 1e6, fits one SM);
@@ -912,9 +504,9 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_cluster_kernel(const 
 // authority for "append to the trail exactly once") or already carried the same / the opposite value — followed by
 // setting the A bit.  A lookup first tests A in shared memory: 87 % of the lookups of config 4 hit an unassigned
 // variable and end there; only when A is set is V read (V was written before A, so it is valid by then).
-// Compared with the cluster kernel this removes ALL traffic on the SM-to-SM network (ncu: the cluster kernel moves
-// 32 GB of 32-byte DSMEM sectors per launch for 2-bit lookups and is bound by that network), doubles the number of
-// jobs in flight (148 instead of 74) and turns the per-round cluster barriers into __syncthreads().
+// The filter may be SMALLER than the variable count (2^k bits indexed by var & mask, for databases whose exact filter
+// does not fit one SM): a set bit may then belong to an aliased variable and V decides — correctness does not depend on
+// the filter, only the share of lookups that end in shared memory does.
 // A stale A bit can only read "unassigned" for a variable assigned during the current round; the literal that made
 // it assigned is processed in a later round (after a barrier) and re-examines the clause, so no unit is lost.
 // ---------------------------------------------------------------------------------------------------------------
@@ -1494,30 +1086,7 @@ cudaError_t launch_bcp_sweep(const SweepLaunch &L, cudaStream_t stream)
         kfn<<<L.blocks, L.warps_per_block * 32, smem, stream>>>(A, L.slice_log2);
         return cudaGetLastError();
     }
-    if (L.cluster_size > 0) {
-        const size_t smem = (size_t)4 << L.slice_log2;
-        cudaError_t e = cudaFuncSetAttribute(gpsat_bcp_sweep_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        if (L.cluster_size > 8) {
-            e = cudaFuncSetAttribute(gpsat_bcp_sweep_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-            if (e != cudaSuccess) return e;
-        }
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)(L.blocks * L.cluster_size));
-        cfg.blockDim = dim3((unsigned)(L.warps_per_block * 32));
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = (unsigned)L.cluster_size;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, gpsat_bcp_sweep_cluster_kernel, A, (int)L.slice_log2);
-    }
-    gpsat_bcp_sweep_kernel<<<L.blocks, L.warps_per_block * 32, 0, stream>>>(A);
-    return cudaGetLastError();
+    return cudaErrorInvalidConfiguration;
 }
 
 cudaError_t sweep_cta_capacity(int filter_log2, int threads, int want_per_sm, int *blocks_per_sm)
@@ -1527,29 +1096,6 @@ cudaError_t sweep_cta_capacity(int filter_log2, int threads, int want_per_sm, in
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kfn, threads, smem);
-}
-
-// how many clusters of `cluster_size` CTAs (threads, dynamic shared memory as given) can be co-resident on the device
-cudaError_t sweep_cluster_capacity(int cluster_size, int threads, size_t smem, int *clusters)
-{
-    cudaError_t e = cudaFuncSetAttribute(gpsat_bcp_sweep_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    if (cluster_size > 8) {
-        e = cudaFuncSetAttribute(gpsat_bcp_sweep_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        if (e != cudaSuccess) return e;
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(cluster_size * 1024));
-    cfg.blockDim = dim3((unsigned)threads);
-    cfg.dynamicSmemBytes = smem;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cluster_size;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaOccupancyMaxActiveClusters(clusters, gpsat_bcp_sweep_cluster_kernel, &cfg);
 }
 
 }  // namespace gpsat_kernels

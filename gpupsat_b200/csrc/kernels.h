@@ -38,7 +38,7 @@ cudaError_t launch_eval_clauses(int32_t n_vars, int32_t n_clauses, const int32_t
                                 int32_t n_assignments, const uint8_t *assignment, int32_t *status, int32_t *unit,
                                 cudaStream_t stream);
 
-// BCP by clause evaluation over occurrence lists for large clause databases (warp per job, state in HBM)
+// BCP by clause evaluation over occurrence lists for large clause databases (one CTA per job)
 struct SweepLaunch {
     int32_t n_vars, n_clauses, n_cubes, uniform3;
     const int32_t *ostart;   // (begin, end) pairs of the padded occurrence lists (int2 per literal)
@@ -60,16 +60,13 @@ struct SweepLaunch {
     int64_t *conflict_clause;
     int64_t *counters;
     int32_t *next_job;
-    int blocks, warps_per_block;   // cluster kernel: blocks = number of clusters
-    int stream_index;              // CTA kernel: evict-first loads for the occurrence index
-    int cluster_size;              // 0: HBM-bitmap kernel (one warp per job); > 0: one cluster per job, bitmap in distributed
-                                   // shared memory; < 0: one CTA per job, assigned bits in shared memory + values in global
-    int slice_log2;                // cluster kernel: bitmap words per CTA = 1 << slice_log2; CTA kernel: log2 of the filter bits
-                                   // (cluster_size = -(CTAs per SM the kernel variant is compiled for))
+    int blocks, warps_per_block;
+    int stream_index;              // index loads: 0 evict-first 16-byte, 1 read-only 16-byte, 2 read-only 32-byte
+    int cluster_size;              // -(CTAs per SM the CTA-filter kernel variant is compiled for): -1 or -2
+    int slice_log2;                // CTA-filter kernel: log2 of the filter bits
 };
 cudaError_t launch_bcp_sweep(const SweepLaunch &L, cudaStream_t stream);
 size_t tern_smem_bytes(int32_t state_bytes);   // dynamic shared memory of the ternary kernel
-cudaError_t sweep_cluster_capacity(int cluster_size, int threads, size_t smem, int *clusters);
 cudaError_t sweep_cta_capacity(int filter_log2, int threads, int want_per_sm, int *blocks_per_sm);
 
 }  // namespace gpsat_kernels

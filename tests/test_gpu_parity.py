@@ -190,16 +190,13 @@ def _hub_3sat(n, m, hubs, hub_occ, seed):
     return offs, np.array([x for c in cl for x in c], dtype=np.int32)
 
 
-@pytest.mark.parametrize("env", [{}, {"GPSAT_SWEEP_PREFETCH": "1"}, {"GPSAT_SWEEP_SORT": "0"}, {"GPSAT_SWEEP_TERNARY": "0"}, {"GPSAT_SWEEP_CLUSTER": "2"},
-                                 {"GPSAT_SWEEP_CLUSTER": "0"}])
-def test_occurrence_bcp_index_and_state_layouts(env, monkeypatch):
-    """every large-database kernel — ternary state + bucket index (default for pure 3-SAT), one CTA per job with the
-    filter / global fields, cluster, HBM bitmap — gives the oracle's status and implied sets on an instance whose
-    hub literals have 40 occurrences (bucket overflow path) and whose cubes falsify them"""
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
-    n = 600
-    offs, lits = _hub_3sat(n, 2200, 6, 40, 5)
+@pytest.mark.parametrize("n,m,flags", [(600, 2200, 0), (600, 2200, 1), (3000, 12000, 1 | (10 << 8)), (3000, 12000, 0)])
+def test_occurrence_bcp_index_and_state_layouts(n, m, flags):
+    """both large-database kernels — ternary state + bucket index (default for pure 3-SAT) and one CTA per job with the
+    assigned-bit filter + global value fields (sweep_flags 1), the latter also with a filter SMALLER than the variable
+    count (three variables per filter bit) — give the oracle's status and implied sets on an instance whose hub
+    literals have 40 occurrences (bucket overflow path) and whose cubes falsify them"""
+    offs, lits = _hub_3sat(n, m, 6, 40, 5)
     rng = np.random.default_rng(6)
     J, K = 96, 24
     cubes = np.zeros((J, K), dtype=np.int32)
@@ -210,7 +207,7 @@ def test_occurrence_bcp_index_and_state_layouts(env, monkeypatch):
     cubes[3, 7] = cubes[3, 6]            # the same literal twice
     cubes[4, 9] = cubes[4, 8] ^ 1        # x and ~x: refuted without a clause to blame
     co = np.arange(0, cubes.size + 1, K, dtype=np.int64)
-    with g.Solver(n, offs, lits, bcp=g.binding.BCP_OCCURRENCE) as s:
+    with g.Solver(n, offs, lits, bcp=g.binding.BCP_OCCURRENCE, sweep_flags=flags) as s:
         s.set_cubes(cubes)
         got = s.propagate_all()
     want = Oracle(n, offs, lits).run(co, cubes.reshape(-1), mode=2)

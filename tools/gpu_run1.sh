@@ -1,7 +1,7 @@
-set -x
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2a_tests.log 2>&1; tail -15 gpurun_out/r2a_tests.log
-timeout 300 python tools/quick_c2.py "" > gpurun_out/r2a_quick.log 2>&1; cat gpurun_out/r2a_quick.log
-timeout 400 python tools/quick_mesh.py "stride=2" "stride=4" "stride=8" "mesh=2" "mesh=4" "mesh=2 share_learnts=1 share_max_len=2" > gpurun_out/r2a_mesh.log 2>&1; cat gpurun_out/r2a_mesh.log
-timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/r2a_bench.json 2> gpurun_out/r2a_bench.err; tail -c 3000 gpurun_out/r2a_bench.json; tail -5 gpurun_out/r2a_bench.err
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_cli.py -x -q > gpurun_out/r2y_tests.log 2>&1; tail -6 gpurun_out/r2y_tests.log
+# ncu: launch list of a short bench run, then one full capture of the CDCL kernel and of the ternary sweep kernel
+GPSAT_BENCH_C4=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r02_launches_a.csv python bench.py --steps 2 --warmup 1 > gpurun_out/r2y_ncu_bench.log 2>&1; tail -2 gpurun_out/r2y_ncu_bench.log | cut -c1-300
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gpsat_cdcl_kernel -s 2 -c 1 -o gpurun_out/r02_cdcl_a python tools/quick_c2.py "" > gpurun_out/r2y_ncu_cdcl.log 2>&1; tail -3 gpurun_out/r2y_ncu_cdcl.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gpsat_bcp_sweep_tern -s 2 -c 1 -o gpurun_out/r02_tern_a python tools/sweep_c4.py --jobs 1184 --lens 100000 --reps 1 > gpurun_out/r2y_ncu_tern.log 2>&1; tail -3 gpurun_out/r2y_ncu_tern.log
+ls -la gpurun_out/*.ncu-rep | tail -3

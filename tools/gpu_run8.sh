@@ -1,11 +1,13 @@
 mkdir -p gpurun_out
-nvidia-smi -L | wc -l
-timeout 600 python tools/quick_mesh.py "" "gpus=2" "gpus=4" "gpus=8" "gpus=8 mesh_flags=1" "gpus=8 split_gap=4" "gpus=8 split_hard=64" 2>&1 | grep -v children > gpurun_out/r2v_mesh.log; cat gpurun_out/r2v_mesh.log
-for n in 8 4; do
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2960$n bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/r2v_bench$n.json 2> gpurun_out/r2v_bench$n.err; python - <<PY
+timeout 900 python tools/run_configs_multi.py c5 --out gpurun_out/r2x_c5.json > gpurun_out/r2x_c5.log 2>&1; python - <<'PY'
 import json
-d=json.loads(open("gpurun_out/r2v_bench$n.json").read().strip().splitlines()[-1])
-print($n, {k:d[k] for k in ("value","ms_per_step","implications_per_step","parity")}, d["e2e"], [round(x["warp_busy_frac"],2) for x in d["multi_gpu"]["per_rank"]], [int(x["steals_per_step"]) for x in d["multi_gpu"]["per_rank"]], d["launch"])
+for r in json.load(open("gpurun_out/r2x_c5.json"))["rows"]:
+    print("c5", r["gpus"], "share", r["share_max_len"], r["verdict"], "closed", r["cubes_closed"], "ms", round(r["kernel_ms"],2), "confl", r["conflicts"], "recv", r["clauses_received_over_nvlink"], "steals", r["steals"], "busy", round(r["warp_busy_frac"],2))
 PY
-tail -2 gpurun_out/r2v_bench$n.err
-done
+tail -3 gpurun_out/r2x_c5.log
+timeout 900 python tools/run_configs_multi.py c3 --gpus 2 4 8 --seconds 6 --out gpurun_out/r2x_c3.json > gpurun_out/r2x_c3.log 2>&1; python - <<'PY'
+import json
+for r in json.load(open("gpurun_out/r2x_c3.json"))["rows"]:
+    print("c3", r["gpus"], "share", r["share_max_len"], r["verdict"], "closed", r["cubes_closed"], "closed/s", round(r["cubes_closed_per_s"],1), "confl/s", f'{r["conflicts_per_s"]:.3e}', "impl/s", f'{r["implications_per_s"]:.3e}', "recv", r["clauses_received_over_nvlink"], "wall", round(r["wall_s"],2), "busy", round(r["warp_busy_frac"],2))
+PY
+tail -3 gpurun_out/r2x_c3.log
