@@ -193,7 +193,12 @@ gpsat_cdcl_kernel(const gpsat_formula_view F, const gpsat_solve_params P, const 
                   const gpsat_run_buffers B)
 {
     extern __shared__ __align__(16) int gpsat_smem[];
-    const int warp_in_block = (int)(threadIdx.x >> 5);
+    // %tid.x through a volatile asm, read ONCE: the compiler otherwise rematerialises the per-warp state pointers from
+    // S2R %tid.x wherever it runs short of registers — 11 % of the instructions and 7 % of the stall samples of this
+    // kernel were such recomputations (profiles/r02_cdcl_lines_b.txt: kernels.cu:196/219, cdcl_warp.inl:1465)
+    unsigned tid_x;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_x));
+    const int warp_in_block = (int)(tid_x >> 5);
     const int warps_per_block = (int)(blockDim.x >> 5);
     const long long gwarp = (long long)blockIdx.x * warps_per_block + warp_in_block;
 
@@ -206,9 +211,9 @@ gpsat_cdcl_kernel(const gpsat_formula_view F, const gpsat_solve_params P, const 
         int *s_occ2 = s_cl2 + ((n_cl2 + 3) & ~3);
         int *s_os = s_occ2 + ((n_occ2 + 3) & ~3);
         const int *g_cl2 = (const int *)F.cl2, *g_occ2 = (const int *)F.occ2;
-        for (int i = (int)threadIdx.x; i < n_cl2; i += (int)blockDim.x) s_cl2[i] = g_cl2[i];
-        for (int i = (int)threadIdx.x; i < n_occ2; i += (int)blockDim.x) s_occ2[i] = g_occ2[i];
-        for (int i = (int)threadIdx.x; i < n_os; i += (int)blockDim.x) s_os[i] = F.ostart[i];
+        for (int i = (int)tid_x; i < n_cl2; i += (int)blockDim.x) s_cl2[i] = g_cl2[i];
+        for (int i = (int)tid_x; i < n_occ2; i += (int)blockDim.x) s_occ2[i] = g_occ2[i];
+        for (int i = (int)tid_x; i < n_os; i += (int)blockDim.x) s_os[i] = F.ostart[i];
         __syncthreads();
         Fv.cl2 = s_cl2;
         Fv.occ2 = s_occ2;

@@ -22,6 +22,14 @@ for i, k in enumerate(hdr):
         except ValueError:
             pass
         d[k] = {"unit": units[i], "value": vals[i]}
+try:
+    d["git_head"] = {"unit": "", "value": subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()}
+except Exception:
+    pass
+if len(sys.argv) > 3:      # extra key=value facts about the profiled launch (e.g. implications_of_this_launch=52670000)
+    for kv in sys.argv[3:]:
+        k, v = kv.split("=", 1)
+        d[k] = {"unit": "", "value": v}
 json.dump(d, open(sys.argv[2], "w"), indent=1)
 for k, v in d.items():
     print(k, v["value"], v["unit"])
