@@ -16,7 +16,7 @@
  *   decisions            DecisionMaker::new_literal / VSIDS (SATSolver/DecisionMaker.cu:45-55, DecisionStrategy/VSIDS.cu:77-124)
  *   restarts             GeometricRestartsManager (Restarts/GeometricRestartsManager.cu:16-31), used as SATSolver.cu:170-178
  *   job driver           SATSolver::solve / preprocess (SATSolver/SATSolver.cu:67-218,231-272)
- * Pinning: tests/test_oracle_vs_reference.py checks this file against oracle/_ref (the reference's own sources built
+ * Pinning: tests/test_oracle.py and tests/test_host_layers.py checks this file against oracle/_ref (the reference's own sources built
  * for the host) — verdicts on tests/cnf + uf20/uf50/PHP, BCP implication SETS and conflict status on every cube of
  * random instances — and tests/golden/ holds those reference outputs as committed fixtures for machines without
  * /root/reference.  The reference ships no vectors for implication lists or learnt clauses, so the
