@@ -394,6 +394,26 @@ def c4_sweep(device_index, peak):
                                  "so the DRAM traffic is below the algorithmic bytes; bound by shared-memory lookups"}}
 
 
+def native_reference_table():
+    """Extra (GPSAT_BENCH_NATIVE=1): config 1 in full on the SAME GPU — the reference built natively for sm_100a
+    (oracle/_ref/gpupsat_ref_native, test infrastructure) vs the drop-in CLI, -b 1 -t 1, "Total time on GPU" of each."""
+    import tempfile
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "gpupsat_ref_native")
+    if not os.path.exists(ref_bin):
+        return {"unavailable": "oracle/_ref/gpupsat_ref_native not built (make -C oracle native, needs /root/reference)"}
+    with tempfile.NamedTemporaryFile(suffix=".json") as f:
+        subprocess.run([sys.executable, os.path.join(ROOT, "tools", "run_native_reference.py"), "--full", "--timeout", "10",
+                        "--out", f.name], capture_output=True, text=True, timeout=900)
+        rows = json.load(open(f.name))["rows"]
+    both = [r for r in rows if r["reference_native"]["gpu_ms"] and r["gpupsat_b200"]["gpu_ms"]]
+    return {"instances": len(rows), "reference_finished": len(both),
+            "reference_timeouts_10s": sum(r["reference_native"]["verdict"] == "TIMEOUT" for r in rows),
+            "verdicts_agree_where_finished": all(r["reference_native"]["verdict"] == r["gpupsat_b200"]["verdict"] for r in both),
+            "median_gpu_ms_reference": statistics.median(r["reference_native"]["gpu_ms"] for r in both) if both else None,
+            "median_gpu_ms_gpupsat_b200": statistics.median(r["gpupsat_b200"]["gpu_ms"] for r in both) if both else None,
+            "rows": rows}
+
+
 def issue_bound(imp_per_s, clocks):
     """The bound the C2 kernel CAN be judged by: warp instructions issued against the issue slots of 148 SMs x 4
     schedulers at the SM clock sampled during the run.  Warp instructions per implication come from the newest ncu
@@ -607,6 +627,7 @@ def run_ours(args):
                                  "(DESIGN.md section 7)"},
             "cpu_baseline": cpu_base,
             "c4_sweep": c4,
+            "native_reference_c1": native_reference_table() if (n_gpus == 1 and os.environ.get("GPSAT_BENCH_NATIVE") == "1") else None,
             "multi_gpu": None if dist is None else {
                 "mode": exchange,
                 "collective": ("mesh over NVLink peer memory inside ONE launch per GPU (steals, clause push, termination); "

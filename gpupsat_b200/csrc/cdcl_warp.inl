@@ -231,7 +231,7 @@ struct WarpSolver {
                         const gint2 e = gpsat_ld2(occ2 + k);
                         const int s = e.x, len = e.y;
                         int other = -1, other_val = 2, repl = -1, nread = 0;
-                        GPSAT_NOUNROLL
+                        GPSAT_HOTLOOP
                         for (int i = 0; i < len; ++i) {
                             const gint2 q = gpsat_ld2(cl2 + s + i);
                             nread++;

@@ -195,3 +195,11 @@ __device__ __forceinline__ int gpsat_ld(const int *p) { return *p; }
 #endif
 
 #define GPSAT_LANEMASK_LT ((1u << lane) - 1u)
+// the clause walk of propagate(): rolled by default (code size); -DGPSAT_HOTLOOP_UNROLL=n to measure unrolling
+#if defined(GPSAT_WARP_EMU) || !defined(GPSAT_HOTLOOP_UNROLL)
+#define GPSAT_HOTLOOP GPSAT_NOUNROLL
+#else
+#define GPSAT_HOTLOOP_STR2(x) #x
+#define GPSAT_HOTLOOP_STR(x) GPSAT_HOTLOOP_STR2(unroll x)
+#define GPSAT_HOTLOOP _Pragma(GPSAT_HOTLOOP_STR(GPSAT_HOTLOOP_UNROLL))
+#endif

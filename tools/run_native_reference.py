@@ -14,14 +14,17 @@ REF = os.path.join(ROOT, "oracle", "_ref", "gpupsat_ref_native")
 OURS = os.path.join(ROOT, "gpupsat_b200", "gpupsat")
 
 
+TIMEOUT_S = 20.0
+
+
 def run(binary, path, mode, cwd):
     t = time.perf_counter()
     try:
-        out = subprocess.run([binary, path] + mode, capture_output=True, text=True, cwd=cwd, timeout=20)
+        out = subprocess.run([binary, path] + mode, capture_output=True, text=True, cwd=cwd, timeout=TIMEOUT_S)
         text = out.stdout
         rc = out.returncode
     except subprocess.TimeoutExpired:
-        return {"verdict": "TIMEOUT", "gpu_ms": None, "wall_s": 20.0, "rc": None}
+        return {"verdict": "TIMEOUT", "gpu_ms": None, "wall_s": TIMEOUT_S, "rc": None}
     wall = time.perf_counter() - t
     m = re.search(r"Total time on GPU: ([0-9.]+) ms", text)
     verdict = next((v for v in ("UNSATISFIABLE", "SATISFIABLE", "UNDEFINED") if re.search(rf"^{v}$", text, re.M)), "?")
@@ -31,16 +34,34 @@ def run(binary, path, mode, cwd):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="")
+    ap.add_argument("--full", action="store_true", help="config 1 in full: the reference's 6 tests/cnf files, uf20-91 and "
+                    "uf50-218 seeds 0-9, sequential mode (-b 1 -t 1)")
+    ap.add_argument("--timeout", type=float, default=20.0)
     args = ap.parse_args()
+    global TIMEOUT_S
+    TIMEOUT_S = args.timeout
     rows = []
     with tempfile.TemporaryDirectory() as d:
-        for n, m, seeds in ((20, 91, (0, 1)), (50, 218, (0, 1))):
+        cases = []
+        if args.full:
+            G = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_outputs.json")))
+            for name, rec in sorted(G["tests_cnf"].items()):
+                path = os.path.join(d, name)
+                open(path, "w").write(rec["dimacs"])
+                cases.append((path, [["-b", "1", "-t", "1"]]))
+            seeds = range(10)
+        else:
+            seeds = (0, 1)
+        for n, m in ((20, 91), (50, 218)):
             for seed in seeds:
                 offs, lits = random_ksat(n, m, seed)
                 path = os.path.join(d, f"uf{n}-{m}-{seed}.cnf")
                 open(path, "w").write(to_dimacs(offs, lits, n))
                 # parallel mode only where 2 * m * B * T nodes fit the reference's pool of 100 000
-                modes = [["-b", "1", "-t", "1"]] + ([["-b", "4", "-t", "32"]] if 2 * m * 128 <= 100000 else [])
+                modes = [["-b", "1", "-t", "1"]] + ([["-b", "4", "-t", "32"]] if (2 * m * 128 <= 100000 and not args.full) else [])
+                cases.append((path, modes))
+        for path, modes in cases:
+            if True:
                 for mode in modes:
                     row = {"instance": os.path.basename(path), "mode": " ".join(mode),
                            "reference_native": run(REF, path, mode, d), "gpupsat_b200": run(OURS, path, mode, d)}
