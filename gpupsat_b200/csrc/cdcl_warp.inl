@@ -199,35 +199,93 @@ struct WarpSolver {
 
     // ---- BCP -------------------------------------------------------------------------------------------------
     // returns GPSAT_NO_CONFLICT or the falsified clause's cref
+    // Grouped propagation: a 3-SAT literal has ~6 occurrence slots, so examining one literal per step leaves 26 lanes
+    // idle.  The warp takes a GROUP of consecutive trail literals whose occurrence lists fit 32 slots together (always at
+    // least one; a literal with more than 32 occurrences is a group of its own, examined 32 slots at a time) and examines
+    // all slots of the group at once against the assignment at group start.  A clause two of whose watched literals are
+    // falsified by two literals of the same group would be examined twice against the same state (and both lanes would
+    // move their watch onto the same replacement): the group is CUT before the literal that owns the second occurrence,
+    // which then opens the next group.  Then the learnt clauses watching the group's literals, literal after literal.
     GPSAT_DEV int propagate()
     {
         GPSAT_LANE_DECL
         while (qhead < trail_size) {
-            const int p = trail[qhead++];
-            const int f = p ^ 1;
-            // learnt watch vector of f: fetch its head now (one global round trip) so that the latency overlaps the scan
-            // of the original clauses; nothing in part (1) changes it
-            const bool has_lw = use_learnts && ((lwbits[f >> 5] >> (f & 31)) & 1u);
-            int wn = 0, wp = 0;
-            if (has_lw) {
-                wp = lw_head[3 * f];
-                wn = lw_head[3 * f + 1];
+            const int avail = (trail_size - qhead) < 32 ? (trail_size - qhead) : 32;
+            LANEVAR(int, gf);     // lane i: falsified literal i of the candidate group, its occurrence range,
+            LANEVAR(int, gos);    // and the head of its learnt watch vector (fetched now: one global round trip that
+            LANEVAR(int, goe);    // overlaps the scan of the original clauses; nothing in part (1) changes it)
+            LANEVAR(int, gwp);
+            LANEVAR(int, gwn);
+            LANES
+            {
+                LV(gf) = 0;
+                LV(gos) = 0;
+                LV(goe) = 0;
+                LV(gwp) = 0;
+                LV(gwn) = 0;
+                if (lane < avail) {
+                    const int f = trail[qhead + lane] ^ 1;
+                    LV(gf) = f;
+                    LV(gos) = gpsat_ld(ostart + f);
+                    LV(goe) = gpsat_ld(ostart + f + 1);
+                    if (use_learnts && ((lwbits[f >> 5] >> (f & 31)) & 1u)) {
+                        LV(gwp) = lw_head[3 * f];
+                        LV(gwn) = lw_head[3 * f + 1];
+                    }
+                }
             }
+            // group = literals 0 .. g-1; lane L of the (single) chunk examines slot gk of literal gli
+            LANEVAR(int, gli);
+            LANEVAR(int, gk);
+            LANES
+            {
+                LV(gli) = -1;
+                LV(gk) = 0;
+            }
+            int g = 0, total = 0;
+            const int os0 = SHFL(gos, 0);
+            const int cnt0 = SHFL(goe, 0) - os0;
+            if (cnt0 > 32) {
+                g = 1;
+                total = cnt0;
+            } else {
+                GPSAT_NOUNROLL
+                for (int t = 0; t < avail; ++t) {
+                    const int ost = SHFL(gos, t);
+                    const int c = SHFL(goe, t) - ost;
+                    if (t > 0 && total + c > 32) break;
+                    LANES
+                    {
+                        if (lane >= total && lane < total + c) {
+                            LV(gli) = t;
+                            LV(gk) = ost + lane - total;
+                        }
+                    }
+                    total += c;
+                    g++;
+                }
+            }
+            int cut = g;
 
-            // (1) original clauses: occurrence slots of f whose watch bit is set
-            const int os = gpsat_ld(ostart + f), oe = gpsat_ld(ostart + f + 1);
+            // (1) original clauses: the occurrence slots of the group whose watch bit is set
             GPSAT_NOUNROLL
-            for (int base = os; base < oe; base += 32) {
+            for (int base = 0; base < total; base += 32) {
                 LANEVAR(int, act);    // 0 none, 1 move, 2 unit, 3 conflict
                 LANEVAR(int, alit);   // unit literal, or new occurrence slot for a move
-                LANEVAR(int, acl);    // clause cref (first literal slot)
+                LANEVAR(int, acl);    // clause cref (first literal slot); -(lane + 1) when the lane examined nothing
+                LANEVAR(int, nrd);    // clause words read by this lane
                 LANES
                 {
-                    const int k = base + lane;
+                    if (cnt0 > 32) {   // one long list, 32 slots at a time
+                        LV(gli) = base + lane < total ? 0 : -1;
+                        LV(gk) = os0 + base + lane;
+                    }
+                    const int k = LV(gk);
                     LV(act) = 0;
                     LV(alit) = 0;
-                    LV(acl) = 0;
-                    if (k < oe && wbit(k)) {
+                    LV(acl) = -(lane + 1);
+                    LV(nrd) = -1;
+                    if (LV(gli) >= 0 && wbit(k)) {
                         const gint2 e = gpsat_ld2(occ2 + k);
                         const int s = e.x, len = e.y;
                         int other = -1, other_val = 2, repl = -1, nread = 0;
@@ -246,8 +304,7 @@ struct WarpSolver {
                             }
                             if (other >= 0 && repl >= 0) break;
                         }
-                        LV(l_watchers) += 1u;
-                        LV(l_words) += (unsigned)nread;
+                        LV(nrd) = nread;
                         LV(acl) = s;
                         if (other_val == 1) {
                             LV(act) = 0;
@@ -263,10 +320,24 @@ struct WarpSolver {
                     }
                 }
                 SYNCWARP();
+                if (g > 1) {   // a clause examined twice: cut the group before the literal of its second occurrence
+                    LANEVAR(unsigned, same);
+                    LANES { LV(same) = MATCH_ANY(acl); }
+                    const unsigned second = BALLOT(LV(nrd) >= 0 && (LV(same) & GPSAT_LANEMASK_LT) != 0u);
+                    if (second) cut = SHFL(gli, gpsat_ffs(second) - 1);   // lanes are in literal order: the lowest one has the smallest literal
+                }
                 LANES
                 {
+                    if (LV(gli) >= cut) {
+                        LV(act) = 0;
+                        LV(nrd) = -1;
+                    }
+                    if (LV(nrd) >= 0) {
+                        LV(l_watchers) += 1u;
+                        LV(l_words) += (unsigned)LV(nrd);
+                    }
                     if (LV(act) == 1) {
-                        const int k = base + lane, r = LV(alit);
+                        const int k = LV(gk), r = LV(alit);
                         gpsat_atomic_and(wbits + (k >> 5), ~(1u << (k & 31)));
                         gpsat_atomic_or(wbits + (r >> 5), 1u << (r & 31));
                     }
@@ -289,8 +360,15 @@ struct WarpSolver {
                     }
                 }
             }
+            qhead += cut;
 
-            // (2) learnt clauses watching f, MiniSat order, the warp cooperating on one clause at a time
+            // (2) learnt clauses watching the literals of the group, literal after literal
+            GPSAT_NOUNROLL
+            for (int t = 0; t < cut; ++t) {
+            const int f = SHFL(gf, t);
+            const int wp = SHFL(gwp, t);
+            const int wn = SHFL(gwn, t);
+            // MiniSat order, the warp cooperating on one clause at a time
             if (wn == 0) continue;
             c_lwatchers += wn;
             int confl = GPSAT_NO_CONFLICT;
@@ -400,6 +478,7 @@ struct WarpSolver {
             }
             SYNCWARP();
             if (confl != GPSAT_NO_CONFLICT) return confl;
+            }   // literals of the group
         }
         return GPSAT_NO_CONFLICT;
     }

@@ -34,6 +34,13 @@
         return m_;                                        \
     }())
 #define SHFL(name, src) (name[(src)])
+#define MATCH_ANY(name)                                   \
+    ([&]() -> unsigned {                                  \
+        unsigned m_ = 0;                                  \
+        for (int j_ = 0; j_ < 32; ++j_)                   \
+            if (name[j_] == name[lane]) m_ |= 1u << j_;   \
+        return m_;                                        \
+    }())
 #define SETLANE(name, src, value) (name[(src)] = (value))
 #define SYNCWARP() ((void)0)
 #define LANE0 for (int lane = 0; lane < 1; ++lane)
@@ -107,6 +114,7 @@ __device__ __forceinline__ int gpsat_lane_of(const T *s) { return s->lane_id; }
 #define LANES
 #define BALLOT(expr) __ballot_sync(0xffffffffu, (expr))
 #define SHFL(name, src) __shfl_sync(0xffffffffu, name, (src))
+#define MATCH_ANY(name) __match_any_sync(0xffffffffu, name)
 #define SETLANE(name, src, value) \
     do {                          \
         if (lane == (src)) name = (value); \

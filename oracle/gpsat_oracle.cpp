@@ -132,21 +132,42 @@ struct Oracle {
     }
 
     /* ---- BCP.  Returns reason-encoded conflict or INT32_MIN ------------------------------------------------ */
+    /* Canonical order: GROUPS of consecutive trail literals whose occurrence lists fit 32 slots
+     * together (at least one literal; a literal with more than 32 occurrences is a group of its own, examined 32 slots
+     * at a time).  All slots of a group are examined against the state at group start; if a clause is examined twice
+     * (two of its watched literals falsified by two literals of the group) the group is cut before the literal that owns
+     * the second occurrence.  Watch moves of the surviving slots are applied, then units / conflicts committed in slot
+     * order; then the learnt clauses watching the group's literals, literal after literal. */
     int propagate()
     {
         const int NOC = INT32_MIN;
         while (qhead < trail.size()) {
-            const int p = trail[qhead++];
-            const int f = p ^ 1;
-            /* original clauses containing f, in chunks of 32 occurrence slots (canonical order, see header) */
-            const std::vector<Occ> &ol = occ[f];
-            for (size_t base = 0; base < ol.size(); base += 32) {
-                const size_t end = std::min(ol.size(), base + 32);
-                struct Act { int kind, lit, clause, newpos; };
-                std::vector<Act> acts;
+            const size_t avail = std::min<size_t>(trail.size() - qhead, 32);
+            std::vector<int> gf(avail);
+            for (size_t i = 0; i < avail; i++) gf[i] = trail[qhead + i] ^ 1;
+            struct Slot { int li; size_t t; };
+            std::vector<Slot> slots;
+            size_t g = 0;
+            if (occ[gf[0]].size() > 32) {
+                g = 1;
+                for (size_t t = 0; t < occ[gf[0]].size(); t++) slots.push_back(Slot{0, t});
+            } else {
+                for (size_t i = 0; i < avail; i++) {
+                    const size_t c = occ[gf[i]].size();
+                    if (i > 0 && slots.size() + c > 32) break;
+                    for (size_t t = 0; t < c; t++) slots.push_back(Slot{(int)i, t});
+                    g++;
+                }
+            }
+            size_t cut = g;
+            for (size_t base = 0; base < slots.size(); base += 32) {
+                const size_t end = std::min(slots.size(), base + 32);
+                struct Act { int kind, lit, clause, newpos, li, nread; };
+                std::vector<Act> acts;   /* one per EXAMINED slot (kind 0 = nothing to do) */
                 acts.reserve(32);
-                for (size_t t = base; t < end; t++) {                       /* examine against the chunk-start state */
-                    const int c = ol[t].clause, mypos = ol[t].pos;
+                for (size_t q = base; q < end; q++) {                       /* examine against the group-start state */
+                    const Occ &o = occ[gf[slots[q].li]][slots[q].t];
+                    const int c = o.clause, mypos = o.pos;
                     const int64_t b = off[c];
                     const int len = (int)(off[c + 1] - b);
                     if (!watched[b + mypos]) continue;
@@ -164,20 +185,28 @@ struct Oracle {
                         }
                         if (other >= 0 && repl >= 0) break;
                     }
-                    R.watchers_visited++;
-                    R.clause_words_read += nread;
-                    if (other_val == 1) continue;
-                    if (repl >= 0) acts.push_back(Act{1, 0, c, repl});
-                    else if (other_val == 2) acts.push_back(Act{2, other, c, 0});
-                    else acts.push_back(Act{3, 0, c, 0});
-                    if (acts.back().kind == 1) acts.back().lit = mypos;
+                    Act a{0, 0, c, 0, slots[q].li, nread};
+                    if (other_val == 1) a.kind = 0;
+                    else if (repl >= 0) { a.kind = 1; a.lit = mypos; a.newpos = repl; }
+                    else if (other_val == 2) { a.kind = 2; a.lit = other; }
+                    else a.kind = 3;
+                    acts.push_back(a);
                 }
-                for (const Act &a : acts)                                    /* all watch moves of the chunk */
-                    if (a.kind == 1) {
-                        watched[off[a.clause] + a.lit] = 0;
-                        watched[off[a.clause] + a.newpos] = 1;
+                if (g > 1)                                                   /* a clause examined twice: cut the group */
+                    for (size_t x = 0; x < acts.size() && cut == g; x++)
+                        for (size_t y = 0; y < x; y++)
+                            if (acts[y].clause == acts[x].clause) { cut = (size_t)acts[x].li; break; }
+                for (const Act &a : acts)
+                    if ((size_t)a.li < cut) {
+                        R.watchers_visited++;
+                        R.clause_words_read += a.nread;
+                        if (a.kind == 1) {                                   /* all watch moves of the chunk */
+                            watched[off[a.clause] + a.lit] = 0;
+                            watched[off[a.clause] + a.newpos] = 1;
+                        }
                     }
                 for (const Act &a : acts) {                                  /* units / conflicts in slot order */
+                    if ((size_t)a.li >= cut) continue;
                     if (a.kind == 3) return a.clause;
                     if (a.kind == 2) {
                         const int v = lit_value(a.lit);
@@ -186,6 +215,9 @@ struct Oracle {
                     }
                 }
             }
+            qhead += cut;
+            for (size_t gi = 0; gi < cut; gi++) {
+            const int f = gf[gi];
             /* learnt clauses watching f: sequential two-watched-literal scheme with blockers */
             if (P.mode != MODE_SOLVE) continue;
             std::vector<LWatch> &ws = lw[f];
@@ -222,6 +254,7 @@ struct Oracle {
             }
             ws.resize(j);
             if (confl != NOC) return confl;
+            }   /* literals of the group */
         }
         return NOC;
     }

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--lens", default="50000,100000,200000")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--out", default="")
+    ap.add_argument("--flags", type=int, default=0, help="gpsat_opts.sweep_flags (test hooks: 2 register prefetch, 4 L2 prefetch)")
     args = ap.parse_args()
     n, m = 1_000_000, 4_000_000
     offs, lits, planted = planted_3sat_large(n, m, 4)
@@ -30,7 +31,7 @@ def main():
     except Exception:
         peak = 6650.0
     rows = []
-    with g.Solver(n, offs, lits, bcp=g.binding.BCP_OCCURRENCE) as s:
+    with g.Solver(n, offs, lits, bcp=g.binding.BCP_OCCURRENCE, sweep_flags=args.flags) as s:
         for L in [int(x) for x in args.lens.split(",")]:
             for J in [int(x) for x in args.jobs.split(",")]:
                 co, cl = sweep_trails(n, J, L, 4, planted)
