@@ -378,16 +378,28 @@ struct WarpSolver {
                 LANEVAR(int, ecr);
                 LANEVAR(int, ebl);
                 LANEVAR(int, keep);   // 0 dropped, 1 kept, 2 to examine
+                LANEVAR(int, hlen);   // header of the lane's clause (length, first two literals), fetched by all lanes at once:
+                LANEVAR(int, hl0);    // the clauses are then examined one after the other, and a clause is only ever
+                LANEVAR(int, hl1);    // modified while it is being examined, so these stay valid
                 LANES
                 {
                     const int i = base + lane;
                     LV(keep) = 0;
                     LV(ecr) = 0;
                     LV(ebl) = 0;
+                    LV(hlen) = 0;
+                    LV(hl0) = 0;
+                    LV(hl1) = 0;
                     if (i < wn) {
                         LV(ecr) = arena[wp + 2 * i];
                         LV(ebl) = arena[wp + 2 * i + 1];
                         LV(keep) = (confl != GPSAT_NO_CONFLICT || lit_value(LV(ebl)) == 1) ? 1 : 2;
+                        if (LV(keep) == 2) {
+                            const int *hc = arena + GPSAT_LEARNT_OFF(LV(ecr));
+                            LV(hlen) = hc[0];
+                            LV(hl0) = hc[1];
+                            LV(hl1) = hc[2];
+                        }
                     }
                 }
                 SYNCWARP();
@@ -402,8 +414,8 @@ struct WarpSolver {
                         continue;
                     }
                     int *cl = arena + GPSAT_LEARNT_OFF(cref) + 1;
-                    const int len = cl[-1];
-                    int l0 = cl[0], l1 = cl[1];
+                    const int len = SHFL(hlen, src);
+                    int l0 = SHFL(hl0, src), l1 = SHFL(hl1, src);
                     if (l0 == f) {
                         LANE0
                         {

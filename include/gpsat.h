@@ -123,8 +123,9 @@ typedef struct gpsat_opts {
     int32_t split_at_start;       /* 1: a cube may split before its first conflict while more than 1/8 of the warps are idle
                                      (default 0: measured slower on C2) */
     int32_t mesh_flags;           /* test hooks: 1 = never take children of other GPUs, 2 = never push clauses to them */
-    int32_t sweep_flags;          /* test hooks (GPSAT_BCP_OCCURRENCE): 1 = general kernel even for pure 3-SAT; bits 8..12 = log2 of the
-                                     assigned-bit filter (smaller than the variable count = aliased filter) */
+    int32_t sweep_flags;          /* test hooks (GPSAT_BCP_OCCURRENCE): 1 = general kernel even for pure 3-SAT; 2 = bucket one batch ahead in
+                                     registers; 4 = no L2 prefetch of the next buckets; bits 8..12 = log2 of the assigned-bit filter
+                                     (smaller than the variable count = aliased filter) */
     int32_t split_mode;           /* 0 (default): back to the cube, branch on the VSIDS-best literal p, keep p, hand out ~p;
                                      1: guiding path — hand out the untried side of the OLDEST open decision and keep searching
                                      where the cube is; 2: as 0 but keep ~p (measured on C2: DESIGN.md section 3) */

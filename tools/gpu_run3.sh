@@ -1,2 +1,2 @@
-mkdir -p gpurun_out
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:gpsat_cdcl_kernel -s 2 -c 1 -o gpurun_out/r02_cdcl_c python tools/quick_c2.py "" > gpurun_out/r2af_ncu_cdcl.log 2>&1; tail -2 gpurun_out/r2af_ncu_cdcl.log
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -2
+timeout 300 python tools/quick_mesh.py "" "" "stride=8" 2>&1 | grep -v children
