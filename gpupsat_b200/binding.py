@@ -30,7 +30,7 @@ class GpsatOpts(C.Structure):
                 ("arena_words", C.c_int64), ("dynamic_split", C.c_int32), ("split_gap", C.c_int32),
                 ("split_burst", C.c_int32), ("share_import_max", C.c_int32), ("split_hand_words", C.c_int32),
                 ("split_gap_hot", C.c_int32), ("split_at_start", C.c_int32), ("mesh_flags", C.c_int32), ("sweep_flags", C.c_int32),
-                ("split_mode", C.c_int32), ("max_learnts", C.c_int32), ("split_min", C.c_int32), ("phase_stats", C.c_int32), ("split_hard", C.c_int32)]
+                ("split_mode", C.c_int32), ("max_learnts", C.c_int32), ("split_min", C.c_int32), ("split_reserve", C.c_int32), ("phase_stats", C.c_int32), ("split_hard", C.c_int32)]
 
 
 class GpsatStats(C.Structure):

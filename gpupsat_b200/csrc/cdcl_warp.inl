@@ -67,7 +67,7 @@ struct WarpSolver {
     float restart_factor;
     long long max_conflicts;
     // dynamic splitting
-    int dynamic_split, split_force, split_gap, split_burst, split_gap_hot, split_hot_demand, split_at_start, split_mode, split_min, split_hard, inherited, root;
+    int dynamic_split, split_force, split_gap, split_burst, split_gap_hot, split_hot_demand, split_at_start, split_mode, split_min, split_hard, split_reserve, inherited, root;
     int *dq_lits, *dq_meta, *dq_ctrl, *root_pending, *dq_hand;
     int hand_words, dq_cap;
     int rel_slot, rel_seq;                 // queue slot this job was popped from (released once its content is consumed)
@@ -1182,7 +1182,7 @@ struct WarpSolver {
     {
         int d = gpsat_ld_volatile(dq_ctrl + GPSAT_DQC_IDLE) -
                 (gpsat_ld_volatile(dq_ctrl + GPSAT_DQC_TAIL) - gpsat_ld_volatile(dq_ctrl + GPSAT_DQC_HEAD)) -
-                gpsat_ld_volatile(dq_ctrl + GPSAT_DQC_INFLIGHT);
+                gpsat_ld_volatile(dq_ctrl + GPSAT_DQC_INFLIGHT) + split_reserve;
         // this GPU's idle warps take a new child before any other GPU can: what the peers advertise counts only once
         // the local warps are served (d <= 0: -d children are queued beyond local demand)
         if (d <= 0) {
@@ -1573,6 +1573,7 @@ GPSAT_DEV void gpsat_bind(WarpSolver &S, const gpsat_formula_view &F, const gpsa
     S.split_at_start = P.split_at_start;
     S.split_mode = P.split_mode;
     S.split_min = P.split_min;
+    S.split_reserve = P.split_reserve;
     S.split_hard = P.split_hard > 0 ? P.split_hard : 0x7fffffff;
     S.inherited = 0;
     S.root = 0;

@@ -312,6 +312,7 @@ gpsat_solve_params make_params(gpsat *h, int mode, int64_t implied_stride)
     P.split_hot_demand = std::max(1, h->blocks * h->warps_per_block / 8);
     P.split_at_start = h->opts.split_at_start > 0 ? 1 : 0;
     P.mesh_flags = h->opts.mesh_flags;
+    P.split_reserve = h->opts.split_reserve > 0 ? h->opts.split_reserve : (h->opts.split_reserve < 0 ? 0 : 32);   // measured: DESIGN.md section 3
     P.split_mode = h->opts.split_mode;
     P.phase_stats = (mode == GPSAT_MODE_SOLVE && h->opts.phase_stats) ? 1 : 0;
     P.split_min = h->opts.split_min > 0 ? h->opts.split_min : 0;

@@ -102,6 +102,7 @@ struct gpsat_solve_params {
     int32_t split_hot_demand;    // demand from which the hot gap applies (1/8 of this GPU's warps)
     int32_t split_at_start;      // 1: a cube may split before its first conflict while warps are idle
     int32_t mesh_flags;          // test hooks: 1 no stealing, 2 no clause push
+    int32_t split_reserve;       // children kept queued ahead of demand
     int32_t phase_stats;         // 1: per-phase time / count accumulators (≙ RuntimeStatistics, Statistics/RuntimeStatistics.cuh:17-66)
     int32_t split_mode;          // 0 back to the cube + VSIDS-best, 1 guiding path (oldest open decision), 2 as 0 with sides swapped
     int32_t split_min;           // hardness (own conflicts + inherited) a job needs before its first split

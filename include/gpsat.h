@@ -132,6 +132,8 @@ typedef struct gpsat_opts {
     int32_t max_learnts;          /* learnt clauses a job keeps before its first database reduction; 0 = default */
     int32_t split_min;            /* a cube splits only once it has proved hard: conflicts (its own + half of what its parent
                                      had when it was split off) before its first split; 0 = default */
+    int32_t split_reserve;        /* split-off cubes kept queued AHEAD of demand, so that a warp that runs out of work finds one at once
+                                     instead of waiting for a busy cube's next conflict; 0 = default, -1 = none */
     int32_t phase_stats;          /* 1: time and count per solver phase (gpsat_phase_stats), the counterpart of the reference's
                                      RuntimeStatistics timers (Statistics/RuntimeStatistics.cuh:17-66); default 0 */
     int32_t split_hard;           /* hardness from which a cube splits after EVERY conflict (and right when it starts) while warps

@@ -25,7 +25,7 @@ class SolveParams(C.Structure):
                 ("implied_stride", C.c_int64), ("dynamic_split", C.c_int32), ("split_force", C.c_int32),
                 ("split_gap", C.c_int32), ("split_burst", C.c_int32), ("share_import_max", C.c_int32),
                 ("split_gap_hot", C.c_int32), ("split_hot_demand", C.c_int32), ("split_at_start", C.c_int32),
-                ("mesh_flags", C.c_int32), ("phase_stats", C.c_int32), ("split_mode", C.c_int32), ("split_min", C.c_int32), ("split_hard", C.c_int32)]
+                ("mesh_flags", C.c_int32), ("split_reserve", C.c_int32), ("phase_stats", C.c_int32), ("split_mode", C.c_int32), ("split_min", C.c_int32), ("split_hard", C.c_int32)]
 
 
 def build(force=False):

@@ -519,3 +519,27 @@ def test_single_cube_propagate_equals_propagate_all_in_ternary_mode():
             assert st == allr["status"][j]
             if st == g.UNDEF:
                 assert set(imp.tolist()) == set(allr["implied"][j, : allr["n_implied"][j]].tolist())
+
+
+def test_cubes_longer_than_the_split_buffer_are_solved_in_place():
+    """a cube of more than GPSAT_DQ_MAXK - 1 = 63 literals cannot be copied into the warp's cube area (it
+    used to overrun it): it runs in place, without splitting or parking, and gets the oracle's status"""
+    offs, lits = random_ksat(300, 1150, 8)                  # under-constrained: long consistent cubes exist
+    cnf, pre = _prep(offs, lits)
+    rng = np.random.default_rng(5)
+    cubes, co = [], [0]
+    for j in range(24):
+        ln = int(rng.integers(60, 140))
+        vs = rng.choice(300, size=ln, replace=False)
+        c = (2 * vs + rng.integers(0, 2, size=ln)).astype(np.int32)
+        cubes.append(c)
+        co.append(co[-1] + ln)
+    co = np.array(co, dtype=np.int64)
+    cl = np.concatenate(cubes)
+    want = Oracle(cnf.n_vars, pre.offsets, pre.lits).run(co, cl, stop_on_sat=False)
+    with g.Solver(cnf.n_vars, pre.offsets, pre.lits, stop_on_sat=0) as s:      # dynamic_split on (the default)
+        s.set_cubes(cube_offsets=co, cube_lits=cl)
+        verdict, model, stats = s.solve()
+        rec = s.job_records()
+    assert np.array_equal(rec["status"], want["records"]["status"])
+    assert stats["jobs_done"] == 24
