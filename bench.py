@@ -495,7 +495,9 @@ def run_ours(args):
             verdict, model, st = s.solve()
             return st["kernel_ms"], st, verdict
         if exchange == "mesh":
-            verdict, model, st, info = mg.solve_mesh(s, dist, rank, n_gpus, dev, blk, n_roots)
+            # launches bounded to 2 s (a 14-34 ms solve is one launch): a rank whose peer died ends its step instead of
+            # spinning until the driver's timeout, and the parity object then says what happened
+            verdict, model, st, info = mg.solve_mesh(s, dist, rank, n_gpus, dev, blk, n_roots, budget_ms=2000.0, max_steps=30)
             return st["kernel_ms"], st, verdict
         verdict, model, st, info = mg.solve_sharded(s, dist, rank, n_gpus, dev, budget_ms=args.epoch_ms,
                                                     max_clauses_per_epoch=1024)
