@@ -549,6 +549,7 @@ struct WarpSolver {
             p = trail[index];
             index--;
             confl = reason[p >> 1];
+            SYNCWARP();   // every lane has read seen[] (the ballot above) before lane 0 clears the entry
             LANE0 { seen[p >> 1] = 0; }
             SYNCWARP();
             pathC--;
