@@ -488,6 +488,7 @@ def run_ours(args):
     block = mg.mesh_join(solver, dist, rank, n_gpus, dev) if exchange == "mesh" else None
 
     xinfo = {"epochs": 0, "imported_clauses": 0, "exchange_bytes_per_epoch": 0}
+    host_ms = {}
 
     def run_one(s, blk):
         """one complete solve on resident data; returns (kernel_ms of this rank, global-or-local stats, verdict)"""
@@ -498,6 +499,9 @@ def run_ours(args):
             # launches bounded to 2 s (a 14-34 ms solve is one launch): a rank whose peer died ends its step instead of
             # spinning until the driver's timeout, and the parity object then says what happened
             verdict, model, st, info = mg.solve_mesh(s, dist, rank, n_gpus, dev, blk, n_roots, budget_ms=2000.0, max_steps=30)
+            for k2, v2 in info["host_ms"].items():
+                host_ms[k2] = host_ms.get(k2, 0.0) + v2
+            host_ms["solves"] = host_ms.get("solves", 0) + 1
             return st["kernel_ms"], st, verdict
         verdict, model, st, info = mg.solve_sharded(s, dist, rank, n_gpus, dev, budget_ms=args.epoch_ms,
                                                     max_clauses_per_epoch=1024)
@@ -530,15 +534,24 @@ def run_ours(args):
 
         # e2e: through the C ABI from host buffers, create -> set_cubes [-> mesh join] -> solve -> destroy, every step
         e2e_ms, e2e_kernel_ms, e2e_imp = [], [], 0
+        e2e_host = {}
         for i in range(max(args.steps, 1) + 1):
             barrier()
             t0 = time.perf_counter()
             s2 = g.Solver(cnf.n_vars, offs, lits, device=local_rank, **extra)
+            t1 = time.perf_counter()
             s2.set_cubes(mine)
+            t2 = time.perf_counter()
             b2 = mg.mesh_join(s2, dist, rank, n_gpus, dev) if exchange == "mesh" else None
+            t3 = time.perf_counter()
             _ms2, st2, v2 = run_one(s2, b2)
+            t4 = time.perf_counter()
             s2.close()
             torch.cuda.synchronize()
+            t5 = time.perf_counter()
+            if i > 0:
+                for k2, v3 in (("create", t1 - t0), ("set_cubes", t2 - t1), ("mesh_join", t3 - t2), ("solve", t4 - t3), ("destroy", t5 - t4)):
+                    e2e_host[k2] = e2e_host.get(k2, 0.0) + 1e3 * v3 / max(args.steps, 1)
             if i == 0:
                 continue                                          # untimed warm-up of the e2e path (allocator caches)
             e2e_ms.append(1e3 * (time.perf_counter() - t0))
@@ -617,7 +630,8 @@ def run_ours(args):
             "parity": parity,
             "e2e": {"value": e2e_imp_all / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max / max(args.steps, 1),
-                    "kernel_ms_per_step": e2e_kernel_ms_max / max(args.steps, 1)},
+                    "kernel_ms_per_step": e2e_kernel_ms_max / max(args.steps, 1),
+                    "host_ms_rank0": e2e_host},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "gpsat_cdcl_kernel",
@@ -639,6 +653,7 @@ def run_ours(args):
                 "epochs_per_step": None if exchange == "mesh" else xinfo["epochs"] / max(steps + args.warmup, 1),
                 "exchange_bytes_per_epoch": None if exchange == "mesh" else xinfo["exchange_bytes_per_epoch"],
                 "result_block_bytes": 4 * int(block.numel()) if block is not None else None,
+                "host_ms_per_solve_rank0": {k2: v2 / max(host_ms.get("solves", 1), 1) for k2, v2 in host_ms.items() if k2 != "solves"} or None,
                 "per_rank": [{"warp_busy_frac": float(x[0]), "steals_per_step": float(x[1]),
                               "foreign_clauses_per_step": float(x[2])} for x in ranks_busy]},
             "clocks": clk,

@@ -135,25 +135,33 @@ def solve_mesh(solver, dist, rank: int, world: int, device, block, n_roots: int,
                max_steps: int | None = None):
     """One mesh solve.  Returns (verdict, model or None, global stats, info).  budget_ms = 0: one launch per GPU until
     the whole job is done; > 0: time-bounded steps (unfinished cubes park in place; used for the time-bounded configs)."""
+    import time
     import torch
 
+    tm = [time.perf_counter()]
     solver.solve_begin()
+    tm.append(time.perf_counter())
     if dist is not None and world > 1:
         dist.barrier()                    # nobody steals from a ring its owner has not reset yet
+    tm.append(time.perf_counter())
     steps = 0
     while True:
         done, _ = solver.solve_step(budget_ms)
         steps += 1
         if done or (max_steps is not None and steps >= max_steps):
             break
+    tm.append(time.perf_counter())
     local_verdict, model, local_stats = solver.solve_end()
     solver.mesh_results_pack(block)
     if device is not None and torch.device(device).type == "cuda":
         torch.cuda.current_stream(device).synchronize()
+    tm.append(time.perf_counter())
     reduce_results(dist, block, n_roots, world)
     if device is not None and torch.device(device).type == "cuda":
         torch.cuda.current_stream(device).synchronize()       # unpack runs on the library's own stream
+    tm.append(time.perf_counter())
     verdict, stats = solver.mesh_results_unpack(block)
+    tm.append(time.perf_counter())
     for k in ("kernel_ms", "kernel_launches", "warp_busy_frac", "steals", "foreign_clauses", "pool_clauses", "blocks",
               "warps_per_block", "smem_bytes_per_block", "state_in_smem"):
         stats[k] = local_stats[k]
@@ -169,4 +177,6 @@ def solve_mesh(solver, dist, rank: int, world: int, device, block, n_roots: int,
         model = m.cpu().numpy()
     else:
         model = None
-    return verdict, model, stats, {"steps": steps, "sat_rank": sat_rank, "local_verdict": local_verdict}
+    phases = dict(zip(("begin", "barrier", "steps", "end_pack", "reduce", "unpack"),
+                      (1e3 * (b - a) for a, b in zip(tm, tm[1:]))))     # host milliseconds of this rank
+    return verdict, model, stats, {"steps": steps, "sat_rank": sat_rank, "local_verdict": local_verdict, "host_ms": phases}
