@@ -670,6 +670,10 @@ int propagate_all_occurrence(gpsat *h, int32_t *status, int32_t *n_implied, int3
         if (h->cube_lits_sorted.p)
             L.cube_lits = h->cube_lits_sorted.p, L.cube_short = h->cube_short.p + h->cube_base;   // per-cube info follows the narrowed job list
         L.tern_prefetch = (h->opts.sweep_flags & 2) ? 1 : 0;     // measured: 5.59 ms without, 5.67 ms with the bucket fetched one batch ahead in registers
+        L.tern_first_hit = (h->opts.sweep_flags & 64) ? 0 : 1;    // first hit of a bucket kept during the scan: 4.07 -> 3.91 ms at L = 1e5 (64 switches it off)
+        // test hook 32: lane-private code table (no bank conflicts on the second lookup) when it fits beside the state
+        L.tern_private_lut = ((h->opts.sweep_flags & 32) &&
+                              gpsat_kernels::tern_smem_bytes(h->tern_state_bytes, true) + 256 <= h->prop.sharedMemPerBlockOptin) ? 1 : 0;
         blocks = h->prop.multiProcessorCount;
         if (h->opts.blocks > 0) blocks = std::min(blocks, h->opts.blocks);
         if ((int64_t)blocks > (int64_t)nc) blocks = (int)std::max<size_t>(nc, 1);
@@ -683,7 +687,7 @@ int propagate_all_occurrence(gpsat *h, int32_t *status, int32_t *n_implied, int3
     h->kernel_launches = 0;
     h->blocks = blocks;
     h->warps_per_block = wpb;
-    h->smem_bytes = use_tern ? gpsat_kernels::tern_smem_bytes(h->tern_state_bytes) : ((size_t)1 << (slice_log2 - 3));
+    h->smem_bytes = use_tern ? gpsat_kernels::tern_smem_bytes(h->tern_state_bytes, L.tern_private_lut != 0) : ((size_t)1 << (slice_log2 - 3));
     h->state_in_smem = 1;
     CU(cudaEventRecord(h->ev0, h->stream));
     CU(gpsat_kernels::launch_bcp_sweep(L, h->stream));

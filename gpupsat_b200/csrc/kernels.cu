@@ -748,27 +748,45 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) gpsat_bcp_sweep_cta_ke
 #define GPSAT_TERN_LUT_ROW 20          // bytes per table row: 5 words, odd, so that the few byte values that occur spread over the banks
 #define GPSAT_TERN_LUT_BYTES 5120
 
-struct TernJob {
-    // dynamic shared memory: [LUT 5 KB | state bytes]
+// kPriv: the second lookup goes to a LANE-PRIVATE copy of the table (2-bit codes, 16 per word, word w of lane l at
+// [w * 32 + l]: every lane reads its own bank, no conflict whatever the byte values are) — 20 KB instead of 5 KB
+#define GPSAT_TERN_LUT2_WORDS 160      // 2560 codes (byte * 10 + rs), 16 per word
+#define GPSAT_TERN_LUT2_BYTES (GPSAT_TERN_LUT2_WORDS * 32 * 4)
+
+template <bool kPriv> struct TernJob {
+    // dynamic shared memory: [LUT | state bytes]
+    static constexpr uint32_t kLutBytes = kPriv ? GPSAT_TERN_LUT2_BYTES : GPSAT_TERN_LUT_BYTES;
+    static constexpr uint32_t kTrue = kPriv ? 3u : 4u;
     uint8_t *smem;
+    uint32_t lane;
     int32_t *imp;
     long long stride;
     int *s_count, *s_conflict, *s_conf_f, *s_conf_j;
-    __device__ __forceinline__ int code(uint32_t x) const   // 0 false, 1 unassigned, 4 true
+    // code of the literal with in-byte index rs (2 * digit position + sign) given the state byte
+    __device__ __forceinline__ uint32_t lut(uint32_t byte, uint32_t rs) const
+    {
+        if constexpr (kPriv) {
+            const uint32_t e = byte * 10u + rs;
+            return (reinterpret_cast<const uint32_t *>(smem)[(e >> 4) * 32u + lane] >> ((e & 15u) * 2u)) & 3u;
+        } else {
+            return smem[byte * GPSAT_TERN_LUT_ROW + rs];
+        }
+    }
+    __device__ __forceinline__ int code(uint32_t x) const   // 0 false, 1 unassigned, kTrue true
     {
         const uint32_t q = __umulhi(x, 0x1999999Au);   // x / 10 (exact below 2^30)
-        return smem[(uint32_t)smem[GPSAT_TERN_LUT_BYTES + q] * GPSAT_TERN_LUT_ROW + (x - 10u * q)];
+        return (int)lut(smem[kLutBytes + q], x - 10u * q);
     }
     // previous digit of the variable: 0 it was unassigned (and now carries x), 1 it was false, 2 it was true
     __device__ __forceinline__ uint32_t assign(uint32_t x) const
     {
         const uint32_t var = x >> 1, q = var / 5u, r = var - 5u * q, sh = (q & 3u) * 8u;
         const uint32_t p3 = r == 4u ? 81u : (0x1B090301u >> (8u * r)) & 255u;   // 1, 3, 9, 27, 81
-        uint32_t *w = reinterpret_cast<uint32_t *>(smem + GPSAT_TERN_LUT_BYTES) + (q >> 2);
+        uint32_t *w = reinterpret_cast<uint32_t *>(smem + kLutBytes) + (q >> 2);
         uint32_t old = *reinterpret_cast<volatile uint32_t *>(w);
         while (true) {
-            const uint32_t c = smem[((old >> sh) & 255u) * GPSAT_TERN_LUT_ROW + 2u * r];   // code of the NEGATIVE literal of var
-            if (c != 1u) return c == 4u ? 1u : 2u;
+            const uint32_t c = lut((old >> sh) & 255u, 2u * r);   // code of the NEGATIVE literal of var
+            if (c != 1u) return c == kTrue ? 1u : 2u;
             const uint32_t seen = atomicCAS(w, old, old + (((1u + (x & 1u)) * p3) << sh));
             if (seen == old) return 0u;
             old = seen;
@@ -790,7 +808,16 @@ struct TernJob {
             conflict_at(f, j);
             return;
         }
-        const uint32_t unit = ca ? a : b;
+        resolve_unit(ca ? a : b, 1, f, j);
+    }
+    // a clause found unit (s == 1, on `unit`) or all-false (s == 0) when it was looked at; `unit` may have been assigned
+    // by another thread since: assign() tells
+    __device__ __forceinline__ void resolve_unit(uint32_t unit, int s, uint32_t f, int j) const
+    {
+        if (s == 0) {
+            conflict_at(f, j);
+            return;
+        }
         const uint32_t prev = assign(unit);
         if (prev == 0) {
             const int pos = atomicAdd(s_count, 1);
@@ -815,14 +842,25 @@ template <int kJ> struct TernEntry {
 
 // entries kJ .. kEnd-1 of a bucket, branch-free: bit j of the result is set when entry j needs attention (unit /
 // conflict)
-template <int kEnd, int kJ = 0>
-__device__ __forceinline__ uint32_t tern_scan(const TernJob &J, const uint32_t (&w)[16])
+// kFirst: the FIRST such entry is remembered as it goes by (two predicated moves per entry) — fu its literal that is
+// not false (the unit), fs the code sum (0: conflict) — so that the usual case, one hit in the bucket, is resolved
+// without the 11-way select of tern_pick and without a second evaluation
+template <int kEnd, bool kFirst, int kJ = 0, class JobT>
+__device__ __forceinline__ uint32_t tern_scan(const JobT &J, const uint32_t (&w)[16], uint32_t &fu, int &fs, uint32_t seen = 0u)
 {
     if constexpr (kJ < kEnd) {
-        const int s = J.code(tern_field<TernEntry<kJ>::bit>(w)) + J.code(tern_field<TernEntry<kJ>::bit + 21>(w));
-        return (s <= 1 ? 1u << kJ : 0u) | tern_scan<kEnd, kJ + 1>(J, w);
+        const uint32_t a = tern_field<TernEntry<kJ>::bit>(w), b = tern_field<TernEntry<kJ>::bit + 21>(w);
+        const int ca = J.code(a), s = ca + J.code(b);
+        if constexpr (kFirst) {
+            if (s <= 1 && seen == 0u) {
+                fu = ca ? a : b;
+                fs = s;
+            }
+        }
+        const uint32_t now = seen | (s <= 1 ? 1u << kJ : 0u);
+        return tern_scan<kEnd, kFirst, kJ + 1, JobT>(J, w, fu, fs, now);
     } else {
-        return 0u;
+        return seen;
     }
 }
 // the two other literals of entry j (run-time j: a select over the 11 compile-time positions)
@@ -860,7 +898,7 @@ __device__ __forceinline__ void tern_load_bucket(const uint4 *bucket, uint32_t f
     w[12] = q3.x; w[13] = q3.y; w[14] = q3.z; w[15] = q3.w;
 }
 
-template <bool kPrefetch>
+template <bool kPrefetch, bool kPriv, bool kFirst>
 __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_tern_kernel(const SweepArgs A)
 {
     extern __shared__ __align__(16) uint8_t s_dyn[];   // [LUT | state bytes]
@@ -869,19 +907,33 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_tern_kernel(const Swe
     const uint32_t lane = (uint32_t)tid & 31u, warp = (uint32_t)tid >> 5;
     const int state_bytes = A.tern_state_bytes;        // multiple of 16
     const uint32_t sentinel_true = 2u * (uint32_t)A.n_vars + 1u;   // literal of the sentinel variable n, always true
-    TernJob J;
+    typedef TernJob<kPriv> Job;
+    constexpr uint32_t kLutBytes = Job::kLutBytes;
+    Job J;
     J.smem = s_dyn;
+    J.lane = lane;
     J.stride = A.stride;
     J.s_count = &s_count;
     J.s_conflict = &s_conflict;
     J.s_conf_f = &s_conf_f;
     J.s_conf_j = &s_conf_j;
 
-    for (int i = tid; i < GPSAT_TERN_LUT_BYTES; i += nthreads) {
-        const uint32_t byte = (uint32_t)i / GPSAT_TERN_LUT_ROW, rs = (uint32_t)i % GPSAT_TERN_LUT_ROW, r = rs >> 1, sgn = rs & 1u;
+    auto code_of = [](uint32_t byte, uint32_t rs) -> uint32_t {
+        const uint32_t r = rs >> 1, sgn = rs & 1u;
         const uint32_t p3 = r == 0 ? 1u : r == 1 ? 3u : r == 2 ? 9u : r == 3 ? 27u : 81u;
         const uint32_t digit = r < 5 ? (byte / p3) % 3u : 0u;
-        s_dyn[i] = digit == 0 ? 1 : (digit - 1u == sgn ? 4 : 0);
+        return digit == 0 ? 1u : (digit - 1u == sgn ? Job::kTrue : 0u);
+    };
+    if constexpr (kPriv) {
+        for (int i = tid; i < GPSAT_TERN_LUT2_WORDS * 32; i += nthreads) {   // the 32 lanes' copies are identical
+            const uint32_t e0 = ((uint32_t)i >> 5) * 16u;
+            uint32_t word = 0;
+            for (uint32_t c = 0; c < 16u; ++c) word |= code_of((e0 + c) / 10u, (e0 + c) % 10u) << (2u * c);
+            reinterpret_cast<uint32_t *>(s_dyn)[i] = word;
+        }
+    } else {
+        for (int i = tid; i < GPSAT_TERN_LUT_BYTES; i += nthreads)
+            s_dyn[i] = (uint8_t)code_of((uint32_t)i / GPSAT_TERN_LUT_ROW, (uint32_t)i % GPSAT_TERN_LUT_ROW);
     }
 
     while (true) {
@@ -891,7 +943,7 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_tern_kernel(const Swe
             s_conflict = 0;
         }
         {
-            uint4 *z = reinterpret_cast<uint4 *>(s_dyn + GPSAT_TERN_LUT_BYTES);
+            uint4 *z = reinterpret_cast<uint4 *>(s_dyn + kLutBytes);
             for (int i = tid; i < state_bytes / 16; i += nthreads) z[i] = make_uint4(0, 0, 0, 0);
         }
         __syncthreads();
@@ -911,7 +963,7 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_tern_kernel(const Swe
         if (distinct) {
             // every variable at most once: its digit goes from 0 to 1 or 2 with ONE fire-and-forget shared-memory add
             // (no carry can reach a neighbour's digit), four loads in flight per thread
-            uint32_t *sw = reinterpret_cast<uint32_t *>(s_dyn + GPSAT_TERN_LUT_BYTES);
+            uint32_t *sw = reinterpret_cast<uint32_t *>(s_dyn + kLutBytes);
             for (int i0 = tid; i0 < k; i0 += 4 * nthreads) {
                 uint32_t x[4];
 #pragma unroll
@@ -969,20 +1021,26 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_tern_kernel(const Swe
                 // the host sorts a cube's literals by occurrence count (gpsat_set_cubes), so the 32 lists of a batch
                 // have nearly the same length and the scan stops at the longest of them instead of visiting padding
                 const int cmax = __reduce_max_sync(0xffffffffu, cnt);
-                uint32_t hits;
+                uint32_t hits, fu = 0;
+                int fs = 0;
                 switch (cmax) {
                 case 0: hits = 0u; break;
-                case 1: case 2: hits = tern_scan<2>(J, w); break;
-                case 3: hits = tern_scan<3>(J, w); break;
-                case 4: hits = tern_scan<4>(J, w); break;
-                case 5: hits = tern_scan<5>(J, w); break;
-                case 6: hits = tern_scan<6>(J, w); break;
-                case 7: hits = tern_scan<7>(J, w); break;
-                case 8: hits = tern_scan<8>(J, w); break;
-                case 9: hits = tern_scan<9>(J, w); break;
-                default: hits = tern_scan<GPSAT_TERN_ENTRIES>(J, w); break;
+                case 1: case 2: hits = tern_scan<2, kFirst>(J, w, fu, fs); break;
+                case 3: hits = tern_scan<3, kFirst>(J, w, fu, fs); break;
+                case 4: hits = tern_scan<4, kFirst>(J, w, fu, fs); break;
+                case 5: hits = tern_scan<5, kFirst>(J, w, fu, fs); break;
+                case 6: hits = tern_scan<6, kFirst>(J, w, fu, fs); break;
+                case 7: hits = tern_scan<7, kFirst>(J, w, fu, fs); break;
+                case 8: hits = tern_scan<8, kFirst>(J, w, fu, fs); break;
+                case 9: hits = tern_scan<9, kFirst>(J, w, fu, fs); break;
+                default: hits = tern_scan<GPSAT_TERN_ENTRIES, kFirst>(J, w, fu, fs); break;
                 }
-                while (hits) {   // one in four literals has an entry that needs attention
+                if (kFirst && hits) {   // one in four literals has an entry that needs attention, nearly always just one
+                    const int j = __ffs((int)hits) - 1;
+                    hits &= hits - 1u;
+                    J.resolve_unit(fu, fs, f, j);
+                }
+                while (hits) {
                     const int j = __ffs((int)hits) - 1;
                     hits &= hits - 1u;
                     uint32_t a = 0, b = 0;
@@ -1042,9 +1100,9 @@ cta_sweep_kernel_t pick_cta_sweep(int threads, int per_sm)
 
 namespace gpsat_kernels {
 
-size_t tern_smem_bytes(int32_t state_bytes)
+size_t tern_smem_bytes(int32_t state_bytes, bool private_lut)
 {
-    return (size_t)state_bytes + GPSAT_TERN_LUT_BYTES;
+    return (size_t)state_bytes + (private_lut ? GPSAT_TERN_LUT2_BYTES : GPSAT_TERN_LUT_BYTES);
 }
 
 cudaError_t launch_bcp_sweep(const SweepLaunch &L, cudaStream_t stream)
@@ -1076,8 +1134,14 @@ cudaError_t launch_bcp_sweep(const SweepLaunch &L, cudaStream_t stream)
     A.counters = L.counters;
     A.next_job = L.next_job;
     if (L.bucket) {   // ternary kernel: whole job state in shared memory, bucket index
-        const size_t smem = tern_smem_bytes(L.tern_state_bytes);
-        auto kfn = L.tern_prefetch ? gpsat_bcp_sweep_tern_kernel<true> : gpsat_bcp_sweep_tern_kernel<false>;
+        const size_t smem = tern_smem_bytes(L.tern_state_bytes, L.tern_private_lut != 0);
+        typedef void (*tern_kernel_t)(const SweepArgs);
+        static const tern_kernel_t table[8] = {
+            gpsat_bcp_sweep_tern_kernel<false, false, false>, gpsat_bcp_sweep_tern_kernel<true, false, false>,
+            gpsat_bcp_sweep_tern_kernel<false, true, false>,  gpsat_bcp_sweep_tern_kernel<true, true, false>,
+            gpsat_bcp_sweep_tern_kernel<false, false, true>,  gpsat_bcp_sweep_tern_kernel<true, false, true>,
+            gpsat_bcp_sweep_tern_kernel<false, true, true>,   gpsat_bcp_sweep_tern_kernel<true, true, true>};
+        tern_kernel_t kfn = table[(L.tern_prefetch ? 1 : 0) | (L.tern_private_lut ? 2 : 0) | (L.tern_first_hit ? 4 : 0)];
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         kfn<<<L.blocks, 1024, smem, stream>>>(A);

@@ -49,6 +49,8 @@ struct SweepLaunch {
     int32_t tern_state_bytes = 0;
     const int32_t *cube_short = nullptr;   // per cube: leading literals (sorted order) whose lists have at most 5 entries
     int tern_prefetch = 0;
+    int tern_first_hit = 0;     // the first hit of a bucket is resolved from literals kept during the scan
+    int tern_private_lut = 0;   // second lookup in a lane-private copy of the code table (20 KB, no bank conflicts)
     int l2_prefetch = 0;                // bucket of the next batch prefetched into L2 (no register cost; no gain measured)              // bucket fetched one batch ahead (registers), trail literal two
     const int64_t *cube_offsets;
     const int32_t *cube_lits;
@@ -66,7 +68,7 @@ struct SweepLaunch {
     int slice_log2;                // CTA-filter kernel: log2 of the filter bits
 };
 cudaError_t launch_bcp_sweep(const SweepLaunch &L, cudaStream_t stream);
-size_t tern_smem_bytes(int32_t state_bytes);   // dynamic shared memory of the ternary kernel
+size_t tern_smem_bytes(int32_t state_bytes, bool private_lut = false);   // dynamic shared memory of the ternary kernel
 cudaError_t sweep_cta_capacity(int filter_log2, int threads, int want_per_sm, int *blocks_per_sm);
 
 }  // namespace gpsat_kernels

@@ -22,7 +22,8 @@ def main():
     ap.add_argument("--lens", default="50000,100000,200000")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--out", default="")
-    ap.add_argument("--flags", type=int, default=0, help="gpsat_opts.sweep_flags (test hooks: 2 register prefetch, 4 L2 prefetch)")
+    ap.add_argument("--flags", default="0", help="gpsat_opts.sweep_flags, comma list (test hooks: 2 register prefetch, 4 no L2 prefetch, "
+                    "32 lane-private code table, 64 first hit kept during the scan)")
     args = ap.parse_args()
     n, m = 1_000_000, 4_000_000
     offs, lits, planted = planted_3sat_large(n, m, 4)
@@ -31,7 +32,8 @@ def main():
     except Exception:
         peak = 6650.0
     rows = []
-    with g.Solver(n, offs, lits, bcp=g.binding.BCP_OCCURRENCE, sweep_flags=args.flags) as s:
+    for flags in [int(x) for x in args.flags.split(",")]:
+      with g.Solver(n, offs, lits, bcp=g.binding.BCP_OCCURRENCE, sweep_flags=flags) as s:
         for L in [int(x) for x in args.lens.split(",")]:
             for J in [int(x) for x in args.jobs.split(",")]:
                 co, cl = sweep_trails(n, J, L, 4, planted)
@@ -50,7 +52,7 @@ def main():
                 words = int(rec["clause_words_read"].sum())
                 props = J * L + imp                      # trail literals whose occurrence lists were walked
                 alg_bytes = 8 * visited + 4 * words + 8 * imp
-                row = {"jobs": J, "trail_len": L, "kernel_ms": best, "implications": imp, "literals_propagated": props,
+                row = {"sweep_flags": flags, "jobs": J, "trail_len": L, "kernel_ms": best, "implications": imp, "literals_propagated": props,
                        "entries_visited": visited, "implications_per_s": imp / (best * 1e-3),
                        "literals_per_s": props / (best * 1e-3), "algorithmic_GBps": alg_bytes / (best * 1e-3) / 1e9,
                        "hbm_frac": alg_bytes / (best * 1e-3) / 1e9 / peak, "status_undef": int((rec["status"] == 2).sum())}
