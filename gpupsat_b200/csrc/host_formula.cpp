@@ -536,7 +536,9 @@ void build_sweep_index(const DeviceFormula &D, bool want_buckets, SweepIndex &ou
         uint32_t *w = out.bucket.data() + 16 * f;
         const int32_t os = f < n_lit_ids ? out.orange[2 * f] : 0;
         const int32_t cnt = f < n_lit_ids ? D.ostart[f + 1] - D.ostart[f] : 0;
-        w[0] = (uint32_t)cnt;
+        // occurrences (8 bits, saturating) | half the (even) index of the list's first entry (24 bits, all ones: does not fit)
+        const uint32_t half = (uint32_t)os >> 1;
+        w[0] = (uint32_t)std::min<int32_t>(cnt, 255) | ((half < 0xFFFFFFu ? half : 0xFFFFFFu) << 8);
         for (int j = 0; j < kBucketEntries; j++) {
             const int bit = bucket_entry_bit(j);
             put(w, bit, j < cnt ? (uint32_t)out.occ_pair[2 * (size_t)(os + j)] : pad);

@@ -54,7 +54,8 @@ int build_device_formula(int32_t n_vars, int64_t n_clauses, const int64_t *offse
 //       padded to an even length with -1, so a kernel reads it as 16-byte loads of two entries and finds (begin, end)
 //       with ONE 8-byte load.  Per entry the clause index and, for pure 3-SAT, the two other literals of the clause.
 //   bucket  (pure 3-SAT whose literal ids, with those of a sentinel variable n, fit 21 bits) the list packed into its
-//       head, one 64-byte bucket (16 words) per literal id 0 .. 2n+1: word 0 the occurrence count, entries 0..4 from
+//       head, one 64-byte bucket (16 words) per literal id 0 .. 2n+1: word 0 = min(occurrence count, 255) | (index of the list in occ_pair / 2) << 8
+//       (0xFFFFFF when that does not fit), entries 0..4 from
 //       bit 32 and 5..10 from bit 256 at 42 bits each (other literal a in the low 21 bits, b above it); unused
 //       entries hold the sentinel's positive literal 2n+1 twice.
 struct SweepIndex {

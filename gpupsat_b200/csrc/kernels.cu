@@ -728,7 +728,8 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) gpsat_bcp_sweep_cta_ke
 //   showed 38 % of its stall samples on those reads / atomics and 12 of 32 lanes active on average).
 // Index: one 64-byte bucket per literal, the occurrence list packed INTO its head (host_formula.cpp:
 //   build_sweep_index):
-//   word 0            number of occurrences of the literal
+//   word 0            number of occurrences of the literal (8 bits, saturating) | half the index of its list in the
+//                     plain pair list (24 bits): where entries 11.. are, without asking orange first
 //   bits  32 .. 241   entries 0..4   } 42 bits per entry: the two OTHER literals of the clause, 21 bits each;
 //   bits 256 .. 507   entries 5..10  } unused entries hold the always-true literal of a sentinel variable n
 //   so a literal is ONE round trip of one or two adjacent sectors instead of head -> list (two dependent round trips,
@@ -1016,7 +1017,13 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_tern_kernel(const Swe
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(A.bucket + 4 * (size_t)f1));
                     tern_load_bucket(A.bucket, f, w, A.stream_index, base + 32 <= n_short);
                 }
-                const int cnt = (int)w[0];
+                // word 0: occurrences (8 bits, saturating) | half the index of the list's first entry in the plain pair
+                // list (24 bits, all ones: too large, ask orange) — the tail of a long list is ONE further round trip,
+                // started here so that it runs under the scan
+                const int cnt = (int)(w[0] & 255u);
+                const uint32_t tail_at = w[0] >> 8;
+                if (cnt > GPSAT_TERN_ENTRIES && tail_at != 0xFFFFFFu)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(A.occ_pair + 2 * (size_t)tail_at + GPSAT_TERN_ENTRIES));
                 visited += cnt;
                 // the host sorts a cube's literals by occurrence count (gpsat_set_cubes), so the 32 lists of a batch
                 // have nearly the same length and the scan stops at the longest of them instead of visiting padding
@@ -1047,9 +1054,17 @@ __global__ void __launch_bounds__(1024, 1) gpsat_bcp_sweep_tern_kernel(const Swe
                     tern_pick<0>(w, j, a, b);
                     J.resolve(a, b, f, j);
                 }
-                if (cnt > GPSAT_TERN_ENTRIES) {   // rare: the tail of a long list comes from the plain pair index
-                    const int os = __ldg(A.orange + f).x;
-                    for (int j = GPSAT_TERN_ENTRIES; j < cnt; ++j) {
+                if (cnt > GPSAT_TERN_ENTRIES) {   // 2 % of the literals: the tail of a long list comes from the plain pair index
+                    long long os = 2 * (long long)tail_at;
+                    int end = cnt;
+                    if (cnt == 255 || tail_at == 0xFFFFFFu) {   // saturated fields: (begin, end) of the padded list
+                        const int2 oc = __ldg(A.orange + f);
+                        os = oc.x;
+                        end = oc.y - oc.x;
+                        if (__ldg(A.occ_pair + oc.y - 1).x < 0) end--;   // padded to an even length with -1
+                        visited += end - cnt;
+                    }
+                    for (int j = GPSAT_TERN_ENTRIES; j < end; ++j) {
                         const int2 q = __ldg(A.occ_pair + os + j);
                         J.resolve((uint32_t)q.x, (uint32_t)q.y, f, j);
                     }

@@ -190,15 +190,16 @@ def _hub_3sat(n, m, hubs, hub_occ, seed):
     return offs, np.array([x for c in cl for x in c], dtype=np.int32)
 
 
-@pytest.mark.parametrize("n,m,flags", [(600, 2200, 0), (600, 2200, 1), (3000, 12000, 1 | (10 << 8)), (3000, 12000, 0),
-                                       (600, 2200, 32), (3000, 12000, 64), (3000, 12000, 96), (600, 2200, 64 | 2)])
-def test_occurrence_bcp_index_and_state_layouts(n, m, flags):
+@pytest.mark.parametrize("n,m,flags,hub_occ", [(600, 2200, 0, 40), (600, 2200, 1, 40), (3000, 12000, 1 | (10 << 8), 40),
+                                               (3000, 12000, 0, 40), (600, 2200, 32, 40), (3000, 12000, 64, 40),
+                                               (3000, 12000, 96, 40), (600, 2200, 64 | 2, 40), (3000, 12000, 0, 300)])
+def test_occurrence_bcp_index_and_state_layouts(n, m, flags, hub_occ):
     """both large-database kernels — ternary state + bucket index (default for pure 3-SAT) and one CTA per job with the
     assigned-bit filter + global value fields (sweep_flags 1), the latter also with a filter SMALLER than the variable
     count (three variables per filter bit) — give the oracle's status and implied sets on an instance whose hub
     literals have 40 occurrences (bucket overflow path) and whose cubes falsify them; flags 32 / 64: the ternary
     kernel's lane-private code table / first hit kept during the scan"""
-    offs, lits = _hub_3sat(n, m, 6, 40, 5)
+    offs, lits = _hub_3sat(n, m, 6, hub_occ, 5)     # 300: more than the 8-bit count field of a bucket holds
     rng = np.random.default_rng(6)
     J, K = 96, 24
     cubes = np.zeros((J, K), dtype=np.int32)
@@ -215,7 +216,7 @@ def test_occurrence_bcp_index_and_state_layouts(n, m, flags):
     want = Oracle(n, offs, lits).run(co, cubes.reshape(-1), mode=2)
     assert got["status"][4] == g.UNSAT and got["conflict_clause"][4] == -1
     occ = np.bincount(lits, minlength=2 * n)
-    assert occ.max() >= 40
+    assert occ.max() >= hub_occ
     assert np.array_equal(got["status"], want["records"]["status"])
     assert (got["status"] == g.UNSAT).any() and (got["status"] == g.UNDEF).any()
     for j in range(J):

@@ -142,7 +142,8 @@ def test_roundtrip_dimacs(tmp_path):
 
 # ---- index of the large-database sweep kernel (host_formula.cpp: build_sweep_index / order_cubes_for_sweep) ----------
 def _decode_bucket(words):
-    """(count, [(a, b)] * 11) of one 64-byte bucket, read the way the kernel does (tern_field in kernels.cu)"""
+    """(count field, list-pointer field, [(a, b)] * 11) of one 64-byte bucket, read the way the kernel does (tern_field
+    in kernels.cu)"""
     bits = 0
     for i, w in enumerate(words):
         bits |= int(w) << (32 * i)
@@ -150,7 +151,7 @@ def _decode_bucket(words):
     for j in range(11):
         o = 32 + 42 * j if j < 5 else 256 + 42 * (j - 5)
         entries.append(((bits >> o) & 0x1FFFFF, (bits >> (o + 21)) & 0x1FFFFF))
-    return int(words[0]), entries
+    return int(words[0]) & 255, int(words[0]) >> 8, entries
 
 
 def test_bucket_index_holds_every_occurrence_list():
@@ -159,6 +160,7 @@ def test_bucket_index_holds_every_occurrence_list():
     n, m = 300, 1300
     offs, lits = random_ksat(n, m, 3)
     extra = [[1, 2 * v, 2 * v + 3] for v in range(2, 32)]                     # literal 1 gets a list of 30+ entries
+    extra += [[3, 2 * v, 2 * v + 5] for v in range(3, 290)]                    # literal 3 more than the count field holds
     lits = np.concatenate([lits, np.array(extra, dtype=np.int32).reshape(-1)])
     offs = np.arange(0, len(lits) + 1, 3, dtype=np.int64)
     bucket, orange = emu.bucket_index(n, offs, lits)
@@ -169,13 +171,16 @@ def test_bucket_index_holds_every_occurrence_list():
             want[int(c[i])].append(tuple(int(x) for k, x in enumerate(c) if k != i))
     pad = 2 * n + 1
     assert max(len(v) for v in want.values()) > 11
+    assert max(len(v) for v in want.values()) > 255
     for f in range(2 * n):
-        cnt, entries = _decode_bucket(bucket[f])
-        assert cnt == len(want[f]) and orange[f, 1] - orange[f, 0] in (cnt, cnt + 1)
+        cnt8, ptr, entries = _decode_bucket(bucket[f])
+        cnt = len(want[f])
+        assert cnt8 == min(cnt, 255) and orange[f, 1] - orange[f, 0] in (cnt, cnt + 1)
+        assert 2 * ptr == orange[f, 0]                                         # where entries 11.. are read from
         for j in range(11):
             assert entries[j] == (want[f][j] if j < cnt else (pad, pad)), (f, j)
     for f in (2 * n, 2 * n + 1):                                               # the sentinel's buckets: empty, all padding
-        cnt, entries = _decode_bucket(bucket[f])
+        cnt, ptr, entries = _decode_bucket(bucket[f])
         assert cnt == 0 and all(e == (pad, pad) for e in entries)
     # not pure 3-SAT -> no bucket index
     assert emu.bucket_index(4, np.array([0, 2, 5]), np.array([0, 3, 1, 4, 6], dtype=np.int32)) is None
