@@ -24,13 +24,28 @@
 #include "gpsat_device.h"
 #include "warp_lockstep.h"
 
-struct WarpSolver {
+// kPacked: cl2 / occ2 are the block's staged copy in shared memory, one 32-bit word per pair (x in the low half, y in
+// the high half — every field of a formula small enough to be staged fits 16 bits); otherwise int2 in global memory
+template <bool kPacked> struct WarpSolverT {
     int lane_id;          // this thread's lane, read once (see GPSAT_LANE_DECL)
-    // ---- read-only formula index (global, L1/L2 resident)
+    // ---- read-only formula index (global, L1/L2 resident, or staged in shared memory)
     int n_vars, n_clauses, n_lits, wbits_words;
     const gint2 *cl2;
     const int *ostart;
     const gint2 *occ2;
+    GPSAT_DEV gint2 ld_pair(const gint2 *base, int i) const
+    {
+        if (kPacked) {
+            const uint32_t w = reinterpret_cast<const uint32_t *>(base)[i];
+            gint2 r;
+            r.x = (int)(w & 0xFFFFu);
+            r.y = (int)(w >> 16);
+            return r;
+        }
+        return gpsat_ld2(base + i);
+    }
+    GPSAT_DEV gint2 ld_cl2(int i) const { return ld_pair(cl2, i); }
+    GPSAT_DEV gint2 ld_occ2(int i) const { return ld_pair(occ2, i); }
     const uint32_t *wbits0;
     const int *vsids0;
     const uint8_t *val0;
@@ -286,12 +301,12 @@ struct WarpSolver {
                     LV(acl) = -(lane + 1);
                     LV(nrd) = -1;
                     if (LV(gli) >= 0 && wbit(k)) {
-                        const gint2 e = gpsat_ld2(occ2 + k);
+                        const gint2 e = ld_occ2(k);
                         const int s = e.x, len = e.y;
                         int other = -1, other_val = 2, repl = -1, nread = 0;
                         GPSAT_HOTLOOP
                         for (int i = 0; i < len; ++i) {
-                            const gint2 q = gpsat_ld2(cl2 + s + i);
+                            const gint2 q = ld_cl2(s + i);
                             nread++;
                             if (q.y == k) continue;
                             const int v = lit_value(q.x);
@@ -507,7 +522,7 @@ struct WarpSolver {
         do {
             const bool orig = confl >= 0;
             const int s = orig ? confl : GPSAT_LEARNT_OFF(confl) + 1;
-            const int len = orig ? gpsat_ld2(cl2 + s - 1).x : arena[s - 1];
+            const int len = orig ? ld_cl2(s - 1).x : arena[s - 1];
             GPSAT_NOUNROLL
             for (int b = 0; b < len; b += 32) {
                 LANEVAR(int, q);
@@ -518,7 +533,7 @@ struct WarpSolver {
                     LV(q) = 0;
                     const int i = b + lane;
                     if (i < len) {
-                        const int x = orig ? gpsat_ld2(cl2 + s + i).x : arena[s + i];
+                        const int x = orig ? ld_cl2(s + i).x : arena[s + i];
                         const int v = x >> 1;
                         LV(q) = x;
                         if (x != p && !seen[v] && level[v] > 0) {
@@ -1532,11 +1547,13 @@ struct WarpSolver {
         }
     }
 };
+typedef WarpSolverT<false> WarpSolver;
 
 // ---------------------------------------------------------------------------------------------------------------
 // glue shared by the kernel and the test-only emulator: point a WarpSolver at its memory, run one job, record it
 // ---------------------------------------------------------------------------------------------------------------
-GPSAT_DEV void gpsat_bind(WarpSolver &S, const gpsat_formula_view &F, const gpsat_solve_params &P,
+template <class WS>
+GPSAT_DEV void gpsat_bind(WS &S, const gpsat_formula_view &F, const gpsat_solve_params &P,
                           const gpsat_state_layout &Ly, int *state, int *arena, int *park, const gpsat_run_buffers &B)
 {
     S.park = park;
@@ -1622,7 +1639,8 @@ GPSAT_DEV void gpsat_bind(WarpSolver &S, const gpsat_formula_view &F, const gpsa
 
 // Runs one job (an original cube, or a child produced by a split) and folds its outcome into the record of the
 // original cube it descends from.
-GPSAT_DEV void gpsat_run_and_record(WarpSolver &S, int root, const int *cube, int k, const int *hand,
+template <class WS>
+GPSAT_DEV void gpsat_run_and_record(WS &S, int root, const int *cube, int k, const int *hand,
                                     const gpsat_solve_params &P, const gpsat_run_buffers &B, bool resume = false)
 {
     GPSAT_LANE_DECL_S
@@ -1657,7 +1675,7 @@ GPSAT_DEV void gpsat_run_and_record(WarpSolver &S, int root, const int *cube, in
     if (P.mode == GPSAT_MODE_PROPAGATE) {
         if (B.conflict_clause) {
             long long cidx = -1;
-            if (status == GPSAT_UNSAT && confl != GPSAT_NO_CONFLICT && confl >= 0) cidx = gpsat_ld2(S.cl2 + confl - 1).y;
+            if (status == GPSAT_UNSAT && confl != GPSAT_NO_CONFLICT && confl >= 0) cidx = S.ld_cl2(confl - 1).y;
             LANE0 { B.conflict_clause[job] = cidx; }
         }
         // implied literals = trail entries with a reason, cube variables excluded, trail order
@@ -1777,7 +1795,8 @@ GPSAT_DEV int gpsat_ring_pop(int *ctrl, int *meta, int cap, bool sys)
 // then children of split cubes from this GPU's ring, then — mesh — children queued on the other GPUs of the box, read
 // over NVLink peer memory; a warp with nothing to do advertises itself as idle (so that long-running cubes split) and
 // leaves when no job is open anywhere, the stop flag is up, or the step budget is spent.
-GPSAT_DEV void gpsat_warp_loop(WarpSolver &S, const gpsat_solve_params &P, const gpsat_run_buffers &B, int *stage)
+template <class WS>
+GPSAT_DEV void gpsat_warp_loop(WS &S, const gpsat_solve_params &P, const gpsat_run_buffers &B, int *stage)
 {
     GPSAT_LANE_DECL_S
     int is_idle = 0, idle_spins = 0, rot = 0;

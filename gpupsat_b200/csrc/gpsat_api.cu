@@ -325,20 +325,22 @@ gpsat_solve_params make_params(gpsat *h, int mode, int64_t implied_stride)
 // launch geometry: as many resident warps per SM as shared memory (per-job state) and registers allow
 int plan_geometry(gpsat *h, int mode)
 {
-    gpsat_make_layout(h->D.n_vars, h->D.n_lits, &h->Ly);
+    gpsat_make_layout(h->D.n_vars, h->D.n_lits, h->opts.phase_stats, &h->Ly);
     const size_t bytes_per_warp = (size_t)h->Ly.total_words * 4;
     const size_t smem_block_max = h->prop.sharedMemPerBlockOptin;                 // 227 KB on B200
     const size_t smem_sm = h->prop.sharedMemPerMultiprocessor;                    // 228 KB
     int w = h->opts.warps_per_block;
     const int w_max = gpsat_kernels::cdcl_max_warps_per_block();
     const size_t smem_max = std::min(smem_block_max, smem_sm - 1024);
-    // read-only formula index staged once per block when it leaves room for at least 8 warps of state
-    const size_t f_words = (size_t)((2 * (h->D.n_lits + h->D.n_clauses) + 3) & ~(int64_t)3) +
-                           (size_t)((2 * h->D.n_lits + 3) & ~(int64_t)3) + (size_t)((2 * (int64_t)h->D.n_vars + 1 + 3) & ~(int64_t)3);
+    // read-only formula index staged once per block — one word per (x, y) pair of cl2 / occ2, every field below 2^16 —
+    // when it leaves room for at least 8 warps of state
+    const size_t f_words = (size_t)((h->D.n_lits + h->D.n_clauses + 3) & ~(int64_t)3) +
+                           (size_t)((h->D.n_lits + 3) & ~(int64_t)3) + (size_t)((2 * (int64_t)h->D.n_vars + 1 + 3) & ~(int64_t)3);
+    const bool packs = h->D.n_lits + h->D.n_clauses < 65536 && 2 * (int64_t)h->D.n_vars < 65536;
     h->state_in_smem = 1;
     h->formula_in_smem = 0;
     h->formula_smem_words = 0;
-    if (mode == GPSAT_MODE_SOLVE && f_words * 4 + 8 * bytes_per_warp <= smem_max) {
+    if (mode == GPSAT_MODE_SOLVE && packs && f_words * 4 + 8 * bytes_per_warp <= smem_max) {
         h->formula_in_smem = 1;
         h->formula_smem_words = (int)f_words;
     }

@@ -190,7 +190,7 @@ static inline void gpsat_make_mesh_layout(int32_t n_vars, int32_t hand_words, in
 }
 
 // per-warp state block: word offsets of each array (every array starts on a 16-byte boundary)
-static inline void gpsat_make_layout(int32_t n_vars, int64_t n_lits, gpsat_state_layout *ly)
+static inline void gpsat_make_layout(int32_t n_vars, int64_t n_lits, int32_t phase_stats, gpsat_state_layout *ly)
 {
     int32_t at = 0;
     const int32_t n = n_vars > 0 ? n_vars : 1;
@@ -211,7 +211,8 @@ static inline void gpsat_make_layout(int32_t n_vars, int64_t n_lits, gpsat_state
     GPSAT_TAKE(lbuf, ly->lbuf_words);
     GPSAT_TAKE(cube, GPSAT_DQ_MAXK);
     GPSAT_TAKE(lwbits, (2 * n + 31) / 32);
-    GPSAT_TAKE(ph, 2 * GPSAT_N_PHASES + GPSAT_N_PHASES + 2);   // int64 ns[8] | int32 count[8] | int64 backtracked levels
+    // int64 ns[8] | int32 count[8] | int64 backtracked levels — only when the run keeps phase statistics
+    GPSAT_TAKE(ph, phase_stats ? 2 * GPSAT_N_PHASES + GPSAT_N_PHASES + 2 : 0);
 #undef GPSAT_TAKE
     ly->total_words = at;
 }

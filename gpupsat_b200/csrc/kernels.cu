@@ -11,7 +11,8 @@
 #include "kernels.h"
 #include "cdcl_warp.inl"
 
-#define GPSAT_MAX_THREADS 640   // 20 warps per block: up to 102 registers per thread
+#define GPSAT_MAX_THREADS 768       // widest block: 21 to 24 warps, 6 on some scheduler — 80 registers per thread
+#define GPSAT_WIDE_THREADS 640      // blocks of up to 20 warps get up to 96 registers per thread
 
 namespace {
 
@@ -184,11 +185,14 @@ gpsat_queue_init_kernel(int *ctrl, int *meta, int dq_cap, int *root_pending, int
 
 // kSmemState:   the per-job state blocks live in dynamic shared memory.
 // kSmemFormula: the read-only formula index (cl2, occ2, ostart) is staged once per block in shared memory, in front
-//               of the state blocks, and every warp of the block reads it from there.
+//               of the state blocks, and every warp of the block reads it from there; the (x, y) pairs of cl2 / occ2
+//               are packed into one word each on the way (a formula that fits has fewer than 65 536 slots), which
+//               halves the staged copy: C2 31 KB instead of 61 KB, room for 23 warps of state instead of 20.
+// kThreads:     launch bound — the register budget follows from it.
 // Both are template parameters (not run-time selects) so that the pointers provably derive from the shared window
 // and compile to LDS/STS/ATOMS instead of generic loads.
-template <bool kSmemState, bool kSmemFormula>
-__global__ void __launch_bounds__(GPSAT_MAX_THREADS, 1)
+template <bool kSmemState, bool kSmemFormula, int kThreads>
+__global__ void __launch_bounds__(kThreads, 1)
 gpsat_cdcl_kernel(const gpsat_formula_view F, const gpsat_solve_params P, const gpsat_state_layout Ly,
                   const gpsat_run_buffers B)
 {
@@ -205,14 +209,20 @@ gpsat_cdcl_kernel(const gpsat_formula_view F, const gpsat_solve_params P, const 
     gpsat_formula_view Fv = F;
     int *state_base = gpsat_smem;
     if (kSmemFormula) {
-        // layout: cl2 | occ2 | ostart, each rounded up to 4 words
-        const int n_cl2 = 2 * (F.n_lits + F.n_clauses), n_occ2 = 2 * F.n_lits, n_os = 2 * F.n_vars + 1;
+        // layout: cl2 | occ2 | ostart, each rounded up to 4 words; one word per (x, y) pair (gpsat_formula_smem_words)
+        const int n_cl2 = F.n_lits + F.n_clauses, n_occ2 = F.n_lits, n_os = 2 * F.n_vars + 1;
         int *s_cl2 = gpsat_smem;
         int *s_occ2 = s_cl2 + ((n_cl2 + 3) & ~3);
         int *s_os = s_occ2 + ((n_occ2 + 3) & ~3);
-        const int *g_cl2 = (const int *)F.cl2, *g_occ2 = (const int *)F.occ2;
-        for (int i = (int)tid_x; i < n_cl2; i += (int)blockDim.x) s_cl2[i] = g_cl2[i];
-        for (int i = (int)tid_x; i < n_occ2; i += (int)blockDim.x) s_occ2[i] = g_occ2[i];
+        const int2 *g_cl2 = (const int2 *)F.cl2, *g_occ2 = (const int2 *)F.occ2;
+        for (int i = (int)tid_x; i < n_cl2; i += (int)blockDim.x) {
+            const int2 q = g_cl2[i];
+            s_cl2[i] = (int)((uint32_t)q.x | ((uint32_t)q.y << 16));
+        }
+        for (int i = (int)tid_x; i < n_occ2; i += (int)blockDim.x) {
+            const int2 q = g_occ2[i];
+            s_occ2[i] = (int)((uint32_t)q.x | ((uint32_t)q.y << 16));
+        }
         for (int i = (int)tid_x; i < n_os; i += (int)blockDim.x) s_os[i] = F.ostart[i];
         __syncthreads();
         Fv.cl2 = s_cl2;
@@ -251,18 +261,19 @@ gpsat_cdcl_kernel(const gpsat_formula_view F, const gpsat_solve_params P, const 
         gpsat_comm_loop(C);
         return;
     }
-    WarpSolver S;
+    WarpSolverT<kSmemFormula> S;
     gpsat_bind(S, Fv, P, Ly, state, arena, park, B);
     gpsat_warp_loop(S, P, B, stage);
 }
 
 typedef void (*cdcl_kernel_t)(const gpsat_formula_view, const gpsat_solve_params, const gpsat_state_layout,
                               const gpsat_run_buffers);
-cdcl_kernel_t pick_kernel(bool smem_state, bool smem_formula)
+cdcl_kernel_t pick_kernel(bool smem_state, bool smem_formula, int threads)
 {
-    if (smem_state && smem_formula) return gpsat_cdcl_kernel<true, true>;
-    if (smem_state) return gpsat_cdcl_kernel<true, false>;
-    return gpsat_cdcl_kernel<false, false>;
+    const bool wide = threads <= GPSAT_WIDE_THREADS;
+    if (smem_state && smem_formula) return wide ? gpsat_cdcl_kernel<true, true, GPSAT_WIDE_THREADS> : gpsat_cdcl_kernel<true, true, GPSAT_MAX_THREADS>;
+    if (smem_state) return wide ? gpsat_cdcl_kernel<true, false, GPSAT_WIDE_THREADS> : gpsat_cdcl_kernel<true, false, GPSAT_MAX_THREADS>;
+    return gpsat_cdcl_kernel<false, false, GPSAT_WIDE_THREADS>;
 }
 
 // One thread per (assignment, clause).  Clause literals are read from the compact CSR (4 B per literal, coalesced
@@ -379,7 +390,7 @@ cudaError_t launch_cdcl(const gpsat_formula_view &F, const gpsat_solve_params &P
                         cudaStream_t stream)
 {
     if (warps_per_block * 32 > GPSAT_MAX_THREADS) return cudaErrorInvalidConfiguration;
-    cdcl_kernel_t k = pick_kernel(B.state_in_smem != 0, B.formula_in_smem != 0);
+    cdcl_kernel_t k = pick_kernel(B.state_in_smem != 0, B.formula_in_smem != 0, warps_per_block * 32);
     if (smem_bytes > 0) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return e;
@@ -391,7 +402,7 @@ cudaError_t launch_cdcl(const gpsat_formula_view &F, const gpsat_solve_params &P
 cudaError_t cdcl_occupancy(int warps_per_block, size_t smem_bytes, bool smem_state, bool smem_formula,
                            int *blocks_per_sm)
 {
-    cdcl_kernel_t k = pick_kernel(smem_state, smem_formula);
+    cdcl_kernel_t k = pick_kernel(smem_state, smem_formula, warps_per_block * 32);
     if (smem_bytes > 0) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return e;
@@ -404,7 +415,7 @@ int cdcl_max_warps_per_block() { return GPSAT_MAX_THREADS / 32; }
 cudaError_t cdcl_attributes(int *regs_per_thread, size_t *local_bytes)
 {
     cudaFuncAttributes a;
-    cudaError_t e = cudaFuncGetAttributes(&a, gpsat_cdcl_kernel<true, true>);
+    cudaError_t e = cudaFuncGetAttributes(&a, gpsat_cdcl_kernel<true, true, GPSAT_MAX_THREADS>);
     if (e != cudaSuccess) return e;
     *regs_per_thread = a.numRegs;
     *local_bytes = a.localSizeBytes;
