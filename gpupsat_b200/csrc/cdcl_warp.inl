@@ -26,7 +26,12 @@
 
 // kPacked: cl2 / occ2 are the block's staged copy in shared memory, one 32-bit word per pair (x in the low half, y in
 // the high half — every field of a formula small enough to be staged fits 16 bits); otherwise int2 in global memory
+template <bool kPacked> struct gpsat_idx { typedef int type; };
+template <> struct gpsat_idx<true> { typedef uint16_t type; };
+
 template <bool kPacked> struct WarpSolverT {
+    // element of level / trail / trail_lim: 16 bits beside a staged formula (2n < 65 536), so that more warps' state fits
+    typedef typename gpsat_idx<kPacked>::type idx_t;
     int lane_id;          // this thread's lane, read once (see GPSAT_LANE_DECL)
     // ---- read-only formula index (global, L1/L2 resident, or staged in shared memory)
     int n_vars, n_clauses, n_lits, wbits_words;
@@ -52,10 +57,10 @@ template <bool kPacked> struct WarpSolverT {
     // ---- per-job state (shared memory when it fits, else this warp's global block)
     uint8_t *val;
     uint8_t *seen;
-    int *level;
+    idx_t *level;
     int *reason;
-    int *trail;
-    int *trail_lim;
+    idx_t *trail;
+    idx_t *trail_lim;
     uint32_t *wbits;
     int *vs;
     int *lbuf;
@@ -141,9 +146,9 @@ template <bool kPacked> struct WarpSolverT {
         {
             int v = x >> 1;
             val[v] = (uint8_t)(x & 1);
-            level[v] = dlevel;
+            level[v] = (idx_t)dlevel;
             reason[v] = why;
-            trail[trail_size] = x;
+            trail[trail_size] = (idx_t)x;
         }
         trail_size++;
         SYNCWARP();
@@ -152,7 +157,7 @@ template <bool kPacked> struct WarpSolverT {
     GPSAT_DEV void new_level()
     {
         GPSAT_LANE_DECL
-        LANE0 { trail_lim[dlevel] = trail_size; }
+        LANE0 { trail_lim[dlevel] = (idx_t)trail_size; }
         dlevel++;
         SYNCWARP();
     }
@@ -1573,10 +1578,10 @@ GPSAT_DEV void gpsat_bind(WS &S, const gpsat_formula_view &F, const gpsat_solve_
     S.val0 = F.val0;
     S.val = (uint8_t *)(state + Ly.val);
     S.seen = (uint8_t *)(state + Ly.seen);
-    S.level = state + Ly.level;
+    S.level = (typename WS::idx_t *)(state + Ly.level);
     S.reason = state + Ly.reason;
-    S.trail = state + Ly.trail;
-    S.trail_lim = state + Ly.trail_lim;
+    S.trail = (typename WS::idx_t *)(state + Ly.trail);
+    S.trail_lim = (typename WS::idx_t *)(state + Ly.trail_lim);
     S.wbits = (uint32_t *)(state + Ly.wbits);
     S.vs = state + Ly.vs;
     S.lbuf = state + Ly.lbuf;

@@ -114,6 +114,7 @@ struct gpsat_state_layout {
     int32_t val, seen, level, reason, trail, trail_lim, wbits, vs, lbuf, cube, lwbits, ph;
     int32_t total_words;
     int32_t lbuf_words;
+    int32_t idx16;
 };
 
 struct gpsat_run_buffers {
@@ -190,7 +191,8 @@ static inline void gpsat_make_mesh_layout(int32_t n_vars, int32_t hand_words, in
 }
 
 // per-warp state block: word offsets of each array (every array starts on a 16-byte boundary)
-static inline void gpsat_make_layout(int32_t n_vars, int64_t n_lits, int32_t phase_stats, gpsat_state_layout *ly)
+// idx16: level / trail / trail_lim hold 16-bit elements (the kernel variant with the staged formula: 2n < 65 536)
+static inline void gpsat_make_layout(int32_t n_vars, int64_t n_lits, int32_t phase_stats, int32_t idx16, gpsat_state_layout *ly)
 {
     int32_t at = 0;
     const int32_t n = n_vars > 0 ? n_vars : 1;
@@ -201,10 +203,10 @@ static inline void gpsat_make_layout(int32_t n_vars, int64_t n_lits, int32_t pha
     } while (0)
     GPSAT_TAKE(val, (n + 3) / 4);
     GPSAT_TAKE(seen, (n + 3) / 4);
-    GPSAT_TAKE(level, n);
+    GPSAT_TAKE(level, idx16 ? (n + 1) / 2 : n);
     GPSAT_TAKE(reason, n);
-    GPSAT_TAKE(trail, n);
-    GPSAT_TAKE(trail_lim, n + 1);
+    GPSAT_TAKE(trail, idx16 ? (n + 1) / 2 : n);
+    GPSAT_TAKE(trail_lim, idx16 ? (n + 2) / 2 : n + 1);
     GPSAT_TAKE(wbits, (int32_t)((n_lits + 31) / 32));
     GPSAT_TAKE(vs, 2 * n);
     ly->lbuf_words = (n + 1) > 64 ? (n + 1) : 64;
@@ -215,6 +217,7 @@ static inline void gpsat_make_layout(int32_t n_vars, int64_t n_lits, int32_t pha
     GPSAT_TAKE(ph, phase_stats ? 2 * GPSAT_N_PHASES + GPSAT_N_PHASES + 2 : 0);
 #undef GPSAT_TAKE
     ly->total_words = at;
+    ly->idx16 = idx16;
 }
 
 static inline int32_t gpsat_park_words(int32_t n_vars) { return ((16 + GPSAT_DQ_MAXK + 3 * (n_vars > 0 ? n_vars : 1)) + 3) / 4 * 4; }

@@ -11,7 +11,8 @@
 #include "kernels.h"
 #include "cdcl_warp.inl"
 
-#define GPSAT_MAX_THREADS 768       // widest block: 21 to 24 warps, 6 on some scheduler — 80 registers per thread
+#define GPSAT_MAX_THREADS 896       // widest block: 25 to 28 warps, 7 on some scheduler — 72 registers per thread
+#define GPSAT_MID_THREADS 768       // 21 to 24 warps, 6 on some scheduler — 80 registers per thread
 #define GPSAT_WIDE_THREADS 640      // blocks of up to 20 warps get up to 96 registers per thread
 
 namespace {
@@ -270,9 +271,13 @@ typedef void (*cdcl_kernel_t)(const gpsat_formula_view, const gpsat_solve_params
                               const gpsat_run_buffers);
 cdcl_kernel_t pick_kernel(bool smem_state, bool smem_formula, int threads)
 {
-    const bool wide = threads <= GPSAT_WIDE_THREADS;
-    if (smem_state && smem_formula) return wide ? gpsat_cdcl_kernel<true, true, GPSAT_WIDE_THREADS> : gpsat_cdcl_kernel<true, true, GPSAT_MAX_THREADS>;
-    if (smem_state) return wide ? gpsat_cdcl_kernel<true, false, GPSAT_WIDE_THREADS> : gpsat_cdcl_kernel<true, false, GPSAT_MAX_THREADS>;
+    const int bound = threads <= GPSAT_WIDE_THREADS ? 0 : threads <= GPSAT_MID_THREADS ? 1 : 2;
+    if (smem_state && smem_formula)
+        return bound == 0 ? gpsat_cdcl_kernel<true, true, GPSAT_WIDE_THREADS>
+                          : bound == 1 ? gpsat_cdcl_kernel<true, true, GPSAT_MID_THREADS> : gpsat_cdcl_kernel<true, true, GPSAT_MAX_THREADS>;
+    if (smem_state)
+        return bound == 0 ? gpsat_cdcl_kernel<true, false, GPSAT_WIDE_THREADS>
+                          : bound == 1 ? gpsat_cdcl_kernel<true, false, GPSAT_MID_THREADS> : gpsat_cdcl_kernel<true, false, GPSAT_MAX_THREADS>;
     return gpsat_cdcl_kernel<false, false, GPSAT_WIDE_THREADS>;
 }
 

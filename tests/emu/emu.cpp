@@ -30,7 +30,7 @@ extern "C" int gpsat_emu_run(int32_t n_vars, int64_t n_clauses, const int64_t *o
     F.val0 = D.val0.data();
     gpsat_solve_params P = *params;
     gpsat_state_layout Ly;
-    gpsat_make_layout(n_vars, D.n_lits, P.phase_stats, &Ly);
+    gpsat_make_layout(n_vars, D.n_lits, P.phase_stats, 0, &Ly);
     std::vector<int32_t> state((size_t)Ly.total_words, 0);
     std::vector<int32_t> arena((size_t)P.arena_words, 0);
     *sat_job = -1;
