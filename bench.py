@@ -639,7 +639,7 @@ def run_ours(args):
                          "traffic": traffic, "peak_source": peak_src, "kernel": "gpsat_cdcl_kernel",
                          "algorithmic_bytes_per_launch": bytes_all / n_launch / n_gpus,
                          "issue": issue_bound(value / n_gpus, clk),
-                         "note": "61 KB formula index is staged in shared memory: this kernel is instruction-issue / latency "
+                         "note": "the formula index (31 KB packed) is staged in shared memory: this kernel is instruction-issue / latency "
                                  "bound and cannot be HBM bound; the HBM fraction is reported because the metric asks for "
                                  "it, `issue` is the bound it can be judged by. c4_sweep is the HBM-resident configuration "
                                  "(DESIGN.md section 7)"},
