@@ -108,7 +108,7 @@ typedef struct gpsat_opts {
     int64_t max_conflicts;        /* per job, 0 = none */
     int32_t share_learnts;        /* 1: short 1-UIP clauses go to the per-GPU pool and are imported by later jobs */
     int32_t share_max_len;        /* longest clause exported to the pool (at most 15: pool slots are 16 words) */
-    int32_t warps_per_block;      /* 0 = auto */
+    int32_t warps_per_block;      /* 0 = auto (as many as the state blocks allow, at most 24); up to 28 on request */
     int32_t blocks;               /* 0 = auto (SM count x resident blocks) */
     int64_t arena_words;          /* per-warp learnt-clause arena (int32 words); 0 = auto */
     int32_t dynamic_split;        /* 1 (default): at a restart a long-running cube hands half of its remaining search
@@ -124,8 +124,9 @@ typedef struct gpsat_opts {
                                      (default 0: measured slower on C2) */
     int32_t mesh_flags;           /* test hooks: 1 = never take children of other GPUs, 2 = never push clauses to them */
     int32_t sweep_flags;          /* test hooks (GPSAT_BCP_OCCURRENCE): 1 = general kernel even for pure 3-SAT; 2 = bucket one batch ahead in
-                                     registers; 4 = no L2 prefetch of the next buckets; bits 8..12 = log2 of the assigned-bit filter
-                                     (smaller than the variable count = aliased filter) */
+                                     registers; 4 = no L2 prefetch of the next buckets; 32 = lane-private code table; 64 = the first hit of a
+                                     bucket is NOT kept during the scan; bits 8..12 = log2 of the assigned-bit filter (smaller than the
+                                     variable count = aliased filter) */
     int32_t split_mode;           /* 0 (default): back to the cube, branch on the VSIDS-best literal p, keep p, hand out ~p;
                                      1: guiding path — hand out the untried side of the OLDEST open decision and keep searching
                                      where the cube is; 2: as 0 but keep ~p (measured on C2: DESIGN.md section 3) */
