@@ -13,7 +13,7 @@ for arg in (sys.argv[1:] or [""]):
     with g.Solver(250, pre.offsets, pre.lits, **opts) as s:
         s.set_cubes(cubes)
         ms, imp = [], 0
-        for r in range(7):
+        for r in range(int(os.environ.get("REPS", "7"))):
             v, m, st = s.solve()
             if r >= 2:
                 ms.append(st["kernel_ms"]); imp = st["implications"]
