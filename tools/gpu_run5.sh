@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-REPS=17 timeout 500 python tools/quick_c2.py "" "split_burst=1" "split_burst=2" "split_burst=1,split_gap=12" "split_burst=2,split_gap=12" "split_gap=12" "" "split_burst=1" 2>&1 | tee gpurun_out/quick_c2_split.txt
+timeout 300 python tools/run_configs_multi.py c5 --gpus 1 --out gpurun_out/r02_config5_php_10_9_e.json 2>&1 | cut -c1-260 | tail -6
