@@ -203,7 +203,9 @@ gpsat_cdcl_kernel(const gpsat_formula_view F, const gpsat_solve_params P, const 
     // kernel were such recomputations (profiles/r02_cdcl_lines_b.txt: kernels.cu:196/219, cdcl_warp.inl:1465)
     unsigned tid_x;
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_x));
-    const int warp_in_block = (int)(tid_x >> 5);
+    // through a warp reduction: its result lives in a UNIFORM register, so the compiler knows that the state pointers
+    // derived from it are the same for all lanes (uniform datapath) instead of spending vector registers on them
+    const int warp_in_block = (int)__reduce_min_sync(0xffffffffu, tid_x >> 5);
     const int warps_per_block = (int)(blockDim.x >> 5);
     const long long gwarp = (long long)blockIdx.x * warps_per_block + warp_in_block;
 

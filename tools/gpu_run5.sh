@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-timeout 300 python tools/run_configs_multi.py c5 --gpus 1 --out gpurun_out/r02_config5_php_10_9_e.json 2>&1 | cut -c1-260 | tail -6
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "bit_exact or dynamic_split or golden" 2>&1 | tail -2
+REPS=13 timeout 500 python tools/quick_c2.py "" "warps_per_block=28" "warps_per_block=20" "" 2>&1 | tee gpurun_out/quick_c2_uniform.txt
