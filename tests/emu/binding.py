@@ -44,9 +44,12 @@ def _p(a):
 def run(n_vars, offsets, lits, cube_offsets, cube_lits, *, mode=0, decision=1, restart_first=100, restart_factor=1.3,
         max_iterations=0, max_conflicts=0, max_learnts_first=None, learnt_refs_cap=16384, arena_words=1 << 19,
         stop_on_sat=True, share_learnts=0, share_max_len=8, pool=None, pool_cursor=None, dynamic_split=0,
-        split_force=0, split_gap=8, split_burst=4, budget_ticks=0, share_import_max=256):
+        split_force=0, split_gap=8, split_burst=4, budget_ticks=0, share_import_max=256, packed=False):
+    """packed: the kernel variant that runs beside a formula staged in shared memory (one word per cl2 / occ2 pair,
+    16-bit level / trail / trail_lim)"""
     build()
     lib = C.CDLL(SO)
+    lib.gpsat_emu_set_packed(C.c_int(1 if packed else 0))
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
     lits = np.ascontiguousarray(lits, dtype=np.int32)
     co = np.ascontiguousarray(cube_offsets, dtype=np.int64)

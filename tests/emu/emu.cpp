@@ -7,11 +7,17 @@
 #include "../../gpupsat_b200/csrc/cdcl_warp.inl"
 #include "../../gpupsat_b200/csrc/host_formula.h"
 
-extern "C" int gpsat_emu_run(int32_t n_vars, int64_t n_clauses, const int64_t *offsets, const int32_t *lits,
-                             const gpsat_solve_params *params, int32_t n_cubes, const int64_t *cube_offsets,
-                             const int32_t *cube_lits, gpsat_job_record *records, uint8_t *model, int32_t *sat_job,
-                             int32_t *implied, int32_t *n_implied, int64_t *conflict_clause, int32_t *pool,
-                             int32_t *pool_cursor, int32_t pool_cap_words, uint64_t budget_ticks, int32_t *n_launches)
+// kPacked: the variant the GPU runs beside a formula staged in shared memory — cl2 / occ2 pairs packed into one word,
+// 16-bit level / trail / trail_lim (WarpSolverT<true>, kernels.cu: gpsat_cdcl_kernel<.., kSmemFormula = true, ..>)
+static int g_emu_packed = 0;
+extern "C" void gpsat_emu_set_packed(int on) { g_emu_packed = on; }
+
+template <bool kPacked>
+static int emu_run(int32_t n_vars, int64_t n_clauses, const int64_t *offsets, const int32_t *lits,
+                   const gpsat_solve_params *params, int32_t n_cubes, const int64_t *cube_offsets,
+                   const int32_t *cube_lits, gpsat_job_record *records, uint8_t *model, int32_t *sat_job,
+                   int32_t *implied, int32_t *n_implied, int64_t *conflict_clause, int32_t *pool,
+                   int32_t *pool_cursor, int32_t pool_cap_words, uint64_t budget_ticks, int32_t *n_launches)
 {
     gpsat_host::DeviceFormula D;
     int rc = gpsat_host::build_device_formula(n_vars, n_clauses, offsets, lits, D);
@@ -28,9 +34,19 @@ extern "C" int gpsat_emu_run(int32_t n_vars, int64_t n_clauses, const int64_t *o
     F.wbits0 = D.wbits0.data();
     F.vsids0 = D.vsids0.data();
     F.val0 = D.val0.data();
+    std::vector<uint32_t> cl2p, occ2p;
+    if (kPacked) {   // what the kernel's staging loop does (kernels.cu)
+        if (D.n_lits + D.n_clauses >= 65536 || 2 * (int64_t)D.n_vars >= 65536) return -100;
+        cl2p.resize((size_t)(D.n_lits + D.n_clauses));
+        occ2p.resize((size_t)D.n_lits);
+        for (size_t i = 0; i < cl2p.size(); i++) cl2p[i] = (uint32_t)D.cl2[2 * i] | ((uint32_t)D.cl2[2 * i + 1] << 16);
+        for (size_t i = 0; i < occ2p.size(); i++) occ2p[i] = (uint32_t)D.occ2[2 * i] | ((uint32_t)D.occ2[2 * i + 1] << 16);
+        F.cl2 = cl2p.data();
+        F.occ2 = occ2p.data();
+    }
     gpsat_solve_params P = *params;
     gpsat_state_layout Ly;
-    gpsat_make_layout(n_vars, D.n_lits, P.phase_stats, 0, &Ly);
+    gpsat_make_layout(n_vars, D.n_lits, P.phase_stats, kPacked ? 1 : 0, &Ly);
     std::vector<int32_t> state((size_t)Ly.total_words, 0);
     std::vector<int32_t> arena((size_t)P.arena_words, 0);
     *sat_job = -1;
@@ -68,7 +84,7 @@ extern "C" int gpsat_emu_run(int32_t n_vars, int64_t n_clauses, const int64_t *o
     std::vector<int32_t> dq_hand(P.dynamic_split ? (size_t)GPSAT_DQ_CAP * B.hand_words : 1, 0);
     B.dq_hand = P.dynamic_split ? dq_hand.data() : nullptr;
     B.root_flag = root_flag.data();
-    WarpSolver S;
+    WarpSolverT<kPacked> S;
     std::memset(&S, 0, sizeof(S));
     // budgeted steps: relaunch the warp program until nothing is outstanding (≙ gpsat_solve_step in a loop)
     std::vector<int32_t> park((size_t)gpsat_park_words(n_vars), 0);
@@ -87,6 +103,21 @@ extern "C" int gpsat_emu_run(int32_t n_vars, int64_t n_clauses, const int64_t *o
     if (n_launches) *n_launches = launches;
     for (int j = 0; j < n_cubes; j++) records[j].status = gpsat_root_status(root_flag[j], root_pending[j]);
     return 0;
+}
+
+extern "C" int gpsat_emu_run(int32_t n_vars, int64_t n_clauses, const int64_t *offsets, const int32_t *lits,
+                             const gpsat_solve_params *params, int32_t n_cubes, const int64_t *cube_offsets,
+                             const int32_t *cube_lits, gpsat_job_record *records, uint8_t *model, int32_t *sat_job,
+                             int32_t *implied, int32_t *n_implied, int64_t *conflict_clause, int32_t *pool,
+                             int32_t *pool_cursor, int32_t pool_cap_words, uint64_t budget_ticks, int32_t *n_launches)
+{
+    if (g_emu_packed)
+        return emu_run<true>(n_vars, n_clauses, offsets, lits, params, n_cubes, cube_offsets, cube_lits, records, model,
+                             sat_job, implied, n_implied, conflict_clause, pool, pool_cursor, pool_cap_words, budget_ticks,
+                             n_launches);
+    return emu_run<false>(n_vars, n_clauses, offsets, lits, params, n_cubes, cube_offsets, cube_lits, records, model,
+                          sat_job, implied, n_implied, conflict_clause, pool, pool_cursor, pool_cap_words, budget_ticks,
+                          n_launches);
 }
 
 // ---- host-side index of the large-database sweep kernels (host_formula.cpp), exposed for the CPU tests --------------

@@ -156,3 +156,54 @@ def test_budgeted_steps_suspend_and_resume():
             assert stepped["launches"] > 1          # at least one job was parked and resumed by a later launch
         if stepped["sat_job"] >= 0:
             assert check_model(pre.offsets, pre.lits, stepped["model"])
+
+
+# ---- the variant that runs beside a formula staged in shared memory ---------------------------------------------------
+# (WarpSolverT<true>: cl2 / occ2 pairs packed into one word, 16-bit level / trail / trail_lim; kernels.cu stages the
+# packed copy, plan_geometry picks the 16-bit layout).  Same program, other element types: every counter must still be
+# the oracle's.
+@pytest.mark.parametrize("n,m,seed", [(20, 91, 1), (50, 218, 3), (100, 426, 0), (120, 511, 2), (150, 639, 0)])
+def test_packed_variant_sequential_solve(n, m, seed):
+    offs, lits = random_ksat(n, m, seed)
+    pre = g.Cnf.from_arrays(offs, lits).preprocess()
+    kw = dict(max_learnts_first=200) if n == 150 else dict(max_conflicts=60000)
+    a = Oracle(n, pre.offsets, pre.lits).run(*EMPTY, **kw)
+    b = emu.run(n, pre.offsets, pre.lits, *EMPTY, packed=True, **kw)
+    assert same(a["records"], b["records"]) == []
+    if a["records"]["status"][0] == g.SAT:
+        assert np.array_equal(a["model"], b["model"]) and check_model(pre.offsets, pre.lits, b["model"])
+
+
+def test_packed_variant_cubes_long_clauses_split_and_steps():
+    # cubes: solve and propagate, implied lists and conflict clauses
+    offs, lits = random_ksat(100, 426, 3)
+    pre = g.Cnf.from_arrays(offs, lits).preprocess()
+    co, cl = cube_csr(pre.choose_cubes(1, 8))
+    o = Oracle(100, pre.offsets, pre.lits)
+    for mode in (0, 1):
+        a = o.run(co, cl, mode=mode, stop_on_sat=False)
+        b = emu.run(100, pre.offsets, pre.lits, co, cl, mode=mode, stop_on_sat=False, packed=True)
+        assert same(a["records"], b["records"]) == []
+    assert np.array_equal(a["implied"], b["implied"]) and np.array_equal(a["conflict_clause"], b["conflict_clause"])
+    # clauses longer than a warp, ragged cubes
+    rng = np.random.default_rng(5)
+    n = 90
+    cls = []
+    for _ in range(60):
+        ln = int(rng.choice([2, 3, 3, 5, 40, 70]))
+        cls.append([int(2 * v + rng.integers(0, 2)) for v in rng.choice(n, size=ln, replace=False)])
+    offs2 = np.cumsum([0] + [len(c) for c in cls]).astype(np.int64)
+    lits2 = np.array([x for c in cls for x in c], dtype=np.int32)
+    cubes = [[], [1], [1, 0], [3, 4, 9, 11, 20], [2 * v for v in range(30)], [2 * v + 1 for v in range(45)]]
+    co2 = np.cumsum([0] + [len(c) for c in cubes]).astype(np.int64)
+    cl2 = np.array([x for c in cubes for x in c], dtype=np.int32)
+    for mode in (1, 0):
+        a = Oracle(n, offs2, lits2).run(co2, cl2, mode=mode, stop_on_sat=False)
+        b = emu.run(n, offs2, lits2, co2, cl2, mode=mode, stop_on_sat=False, packed=True)
+        assert same(a["records"], b["records"]) == []
+    # forced splitting and budgeted steps: same statuses as the plain run of the unpacked variant
+    base = emu.run(100, pre.offsets, pre.lits, co, cl, stop_on_sat=False)
+    split = emu.run(100, pre.offsets, pre.lits, co, cl, stop_on_sat=False, dynamic_split=1, split_force=1, packed=True)
+    stepped = emu.run(100, pre.offsets, pre.lits, co, cl, stop_on_sat=False, dynamic_split=1, budget_ticks=3, packed=True)
+    assert np.array_equal(base["records"]["status"], split["records"]["status"])
+    assert np.array_equal(base["records"]["status"], stepped["records"]["status"])
