@@ -325,52 +325,19 @@ gpsat_solve_params make_params(gpsat *h, int mode, int64_t implied_stride)
 // launch geometry: as many resident warps per SM as shared memory (per-job state) and registers allow
 int plan_geometry(gpsat *h, int mode)
 {
-    // two candidate state layouts: 32-bit level / trail / trail_lim, and the 16-bit one that goes with a staged formula
-    gpsat_state_layout ly32, ly16;
-    gpsat_make_layout(h->D.n_vars, h->D.n_lits, h->opts.phase_stats, 0, &ly32);
-    gpsat_make_layout(h->D.n_vars, h->D.n_lits, h->opts.phase_stats, 1, &ly16);
     const size_t smem_block_max = h->prop.sharedMemPerBlockOptin;                 // 227 KB on B200
     const size_t smem_sm = h->prop.sharedMemPerMultiprocessor;                    // 228 KB
-    int w = h->opts.warps_per_block;
-    const int w_max = gpsat_kernels::cdcl_max_warps_per_block();
-    const size_t smem_max = std::min(smem_block_max, smem_sm - 1024);
-    // read-only formula index staged once per block — one word per (x, y) pair of cl2 / occ2, every field below 2^16 —
-    // when it leaves room for at least 8 warps of state
-    const size_t f_words = (size_t)((h->D.n_lits + h->D.n_clauses + 3) & ~(int64_t)3) +
-                           (size_t)((h->D.n_lits + 3) & ~(int64_t)3) + (size_t)((2 * (int64_t)h->D.n_vars + 1 + 3) & ~(int64_t)3);
-    const bool packs = h->D.n_lits + h->D.n_clauses < 65536 && 2 * (int64_t)h->D.n_vars < 65536;
-    h->state_in_smem = 1;
-    h->formula_in_smem = 0;
-    h->formula_smem_words = 0;
-    if (mode == GPSAT_MODE_SOLVE && packs && f_words * 4 + 8 * (size_t)ly16.total_words * 4 <= smem_max &&
-        (w <= 0 || f_words * 4 + (size_t)w * ly16.total_words * 4 <= smem_max)) {
-        h->formula_in_smem = 1;
-        h->formula_smem_words = (int)f_words;
-    }
-    h->Ly = h->formula_in_smem ? ly16 : ly32;
-    const size_t bytes_per_warp = (size_t)h->Ly.total_words * 4;
-    const size_t room = smem_max - (size_t)h->formula_smem_words * 4;
-    if (w <= 0) {
-        // measured on C2: 20 warps (96 registers) 34.0 ms, 24 (80) 30.3 ms, 28 (72, more spills) 30.3 ms — 24 unless asked
-        const int w_auto = std::min(w_max, 24);
-        const int fit = (int)std::min<size_t>((size_t)w_auto, room / std::max<size_t>(bytes_per_warp, 1));
-        if (fit >= 4) {
-            w = fit;
-        } else {
-            h->state_in_smem = 0;
-            w = 16;
-        }
-    } else if ((size_t)w * bytes_per_warp > room) {
-        h->state_in_smem = 0;
-    }
-    if (!h->state_in_smem) {
-        h->formula_in_smem = 0;
-        h->formula_smem_words = 0;
-        h->Ly = ly32;
-    }
-    if (w > w_max) w = w_max;
-    h->warps_per_block = w;
-    h->smem_bytes = h->state_in_smem ? (size_t)w * h->Ly.total_words * 4 + (size_t)h->formula_smem_words * 4 : 0;
+    gpsat_geometry G;
+    gpsat_plan_warps(h->D.n_vars, h->D.n_lits, h->D.n_clauses, h->opts.phase_stats, mode == GPSAT_MODE_SOLVE ? 1 : 0,
+                     h->opts.warps_per_block, gpsat_kernels::cdcl_max_warps_per_block(), 24,
+                     (int64_t)std::min(smem_block_max, smem_sm - 1024), &G);
+    h->Ly = G.ly;
+    h->state_in_smem = G.state_in_smem;
+    h->formula_in_smem = G.formula_in_smem;
+    h->formula_smem_words = G.formula_smem_words;
+    h->warps_per_block = G.warps;
+    h->smem_bytes = (size_t)G.smem_bytes;
+    const int w = G.warps;
     int occ = 0;
     CU(gpsat_kernels::cdcl_occupancy(w, h->smem_bytes, h->state_in_smem != 0, h->formula_in_smem != 0, &occ));
     if (occ < 1) {

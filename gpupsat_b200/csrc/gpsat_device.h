@@ -220,6 +220,60 @@ static inline void gpsat_make_layout(int32_t n_vars, int64_t n_lits, int32_t pha
     ly->idx16 = idx16;
 }
 
+// Launch geometry of the CDCL kernel from the formula's size and the shared memory of an SM (pure arithmetic: the CPU
+// tests pin it, a silent change here costs 10 % of the throughput).
+//   * the formula index is staged in shared memory (one word per cl2 / occ2 pair, every field below 2^16) when that
+//     leaves room for at least 8 warps of 16-bit-layout state (and for the requested number of warps, if one is given);
+//   * as many warps as fit, at most w_auto_max (24: measured on C2 — 20 warps 34.0 ms, 24 30.3, 28 30.3) unless the
+//     caller asks for a number (up to w_max);
+//   * state in global memory (16 warps) when fewer than 4 warps of state fit, or the requested number does not.
+struct gpsat_geometry {
+    gpsat_state_layout ly;
+    int32_t warps, state_in_smem, formula_in_smem, formula_smem_words;
+    int64_t smem_bytes;
+};
+static inline void gpsat_plan_warps(int32_t n_vars, int64_t n_lits, int64_t n_clauses, int32_t phase_stats, int32_t solve_mode,
+                                    int32_t w_request, int32_t w_max, int32_t w_auto_max, int64_t smem_max, gpsat_geometry *g)
+{
+    gpsat_state_layout ly32, ly16;
+    gpsat_make_layout(n_vars, n_lits, phase_stats, 0, &ly32);
+    gpsat_make_layout(n_vars, n_lits, phase_stats, 1, &ly16);
+    const int64_t f_words = ((n_lits + n_clauses + 3) & ~(int64_t)3) + ((n_lits + 3) & ~(int64_t)3) +
+                            ((2 * (int64_t)n_vars + 1 + 3) & ~(int64_t)3);
+    const int packs = n_lits + n_clauses < 65536 && 2 * (int64_t)n_vars < 65536;
+    int32_t w = w_request > w_max ? w_max : w_request;
+    g->state_in_smem = 1;
+    g->formula_in_smem = 0;
+    g->formula_smem_words = 0;
+    if (solve_mode && packs && f_words * 4 + 8 * (int64_t)ly16.total_words * 4 <= smem_max &&
+        (w <= 0 || f_words * 4 + (int64_t)w * ly16.total_words * 4 <= smem_max)) {
+        g->formula_in_smem = 1;
+        g->formula_smem_words = (int32_t)f_words;
+    }
+    g->ly = g->formula_in_smem ? ly16 : ly32;
+    const int64_t bytes_per_warp = (int64_t)g->ly.total_words * 4;
+    const int64_t room = smem_max - (int64_t)g->formula_smem_words * 4;
+    if (w <= 0) {
+        const int64_t cap = w_auto_max < w_max ? w_auto_max : w_max;
+        const int64_t fit = room / (bytes_per_warp > 0 ? bytes_per_warp : 1);
+        if (fit >= 4) {
+            w = (int32_t)(fit < cap ? fit : cap);
+        } else {
+            g->state_in_smem = 0;
+            w = 16;
+        }
+    } else if ((int64_t)w * bytes_per_warp > room) {
+        g->state_in_smem = 0;
+    }
+    if (!g->state_in_smem) {
+        g->formula_in_smem = 0;
+        g->formula_smem_words = 0;
+        g->ly = ly32;
+    }
+    g->warps = w;
+    g->smem_bytes = g->state_in_smem ? (int64_t)w * g->ly.total_words * 4 + (int64_t)g->formula_smem_words * 4 : 0;
+}
+
 static inline int32_t gpsat_park_words(int32_t n_vars) { return ((16 + GPSAT_DQ_MAXK + 3 * (n_vars > 0 ? n_vars : 1)) + 3) / 4 * 4; }
 
 // outcome of an original cube from the flags of all jobs that descend from it

@@ -113,3 +113,14 @@ def order_cubes(n_vars, offsets, lits, cube_offsets, cube_lits):
                                    C.c_int32(len(co) - 1), _p(co), _p(cl), _p(out), _p(info))
     assert rc == 0
     return out[: int(co[-1] - co[0])], info
+
+
+def plan(n_vars, n_lits, n_clauses, *, phase_stats=0, solve=1, warps=0, w_max=28, w_auto_max=24, smem_max=232448):
+    """gpsat_plan_warps: launch geometry of the CDCL kernel for a formula of this size on an SM with smem_max bytes"""
+    build()
+    lib = C.CDLL(SO)
+    out = np.zeros(8, dtype=np.int64)
+    lib.gpsat_emu_plan(C.c_int32(n_vars), C.c_int64(n_lits), C.c_int64(n_clauses), C.c_int32(phase_stats), C.c_int32(solve),
+                       C.c_int32(warps), C.c_int32(w_max), C.c_int32(w_auto_max), C.c_int64(smem_max), _p(out))
+    keys = ("warps", "state_in_smem", "formula_in_smem", "formula_smem_words", "smem_bytes", "state_words", "idx16", "lbuf_words")
+    return dict(zip(keys, (int(x) for x in out)))

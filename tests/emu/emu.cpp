@@ -120,6 +120,22 @@ extern "C" int gpsat_emu_run(int32_t n_vars, int64_t n_clauses, const int64_t *o
                           n_launches);
 }
 
+// ---- launch geometry arithmetic of the CDCL kernel (gpsat_device.h: gpsat_plan_warps), exposed for the CPU tests -----
+extern "C" void gpsat_emu_plan(int32_t n_vars, int64_t n_lits, int64_t n_clauses, int32_t phase_stats, int32_t solve_mode,
+                               int32_t w_request, int32_t w_max, int32_t w_auto_max, int64_t smem_max, int64_t *out8)
+{
+    gpsat_geometry G;
+    gpsat_plan_warps(n_vars, n_lits, n_clauses, phase_stats, solve_mode, w_request, w_max, w_auto_max, smem_max, &G);
+    out8[0] = G.warps;
+    out8[1] = G.state_in_smem;
+    out8[2] = G.formula_in_smem;
+    out8[3] = G.formula_smem_words;
+    out8[4] = G.smem_bytes;
+    out8[5] = G.ly.total_words;
+    out8[6] = G.ly.idx16;
+    out8[7] = G.ly.lbuf_words;
+}
+
 // ---- host-side index of the large-database sweep kernels (host_formula.cpp), exposed for the CPU tests --------------
 extern "C" int gpsat_emu_bucket_index(int32_t n_vars, int64_t n_clauses, const int64_t *offsets, const int32_t *lits,
                                       uint32_t *bucket /* 16 * (2n + 2) */, int32_t *orange /* 2 * 2n */,

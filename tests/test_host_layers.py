@@ -263,3 +263,40 @@ def test_simple_job_chooser_matches_reference_live(reference_available, quiet):
             want = Reference(offs, lits).cubes_simple()
         got = g.Cnf.from_arrays(offs, lits).preprocess().choose_cubes(1, 1, g.binding.STRATEGY_SIMPLE)
         assert np.array_equal(got, want)
+
+
+# ---- launch geometry of the CDCL kernel (gpsat_device.h: gpsat_plan_warps) ----------------------------------------------
+def test_cdcl_launch_geometry_is_pinned():
+    """the arithmetic that decides how many warps of job state share an SM with the staged formula (B200: 227 KB
+    opt-in); the measured optimum for config 2 is 24 warps x 6.8 KB beside the 31 KB packed formula"""
+    from tests.emu import binding as emu
+    c2 = emu.plan(250, 3195, 1065)                                        # uf250-1065
+    assert c2 == {"warps": 24, "state_in_smem": 1, "formula_in_smem": 1, "formula_smem_words": 7960, "smem_bytes": 194656,
+                  "state_words": 1696, "idx16": 1, "lbuf_words": 251}
+    assert emu.plan(250, 3195, 1065, phase_stats=1)["state_words"] == 1696 + 28   # the statistic words only when kept
+    asked = emu.plan(250, 3195, 1065, warps=28)
+    assert asked["warps"] == 28 and asked["formula_in_smem"] == 1 and asked["smem_bytes"] <= 232448
+    assert emu.plan(250, 3195, 1065, warps=64)["warps"] == 28             # clamped to the widest kernel variant
+    # propagate-only runs stage nothing and keep 32-bit state
+    bcp = emu.plan(250, 3195, 1065, solve=0)
+    assert bcp["formula_in_smem"] == 0 and bcp["idx16"] == 0 and bcp["state_in_smem"] == 1 and bcp["warps"] == 24
+    # a formula whose slots do not fit 16 bits is not staged (and its state stays 32-bit) ...
+    mid = emu.plan(1500, 66000, 22000)
+    assert mid["formula_in_smem"] == 0 and mid["idx16"] == 0 and mid["state_in_smem"] == 1 and mid["warps"] == 4
+    assert mid["smem_bytes"] == mid["warps"] * mid["state_words"] * 4 <= 232448
+    # ... one that fits 16 bits but would leave no room for 8 warps is not staged either
+    tight = emu.plan(1000, 12780, 4260)
+    assert tight["formula_in_smem"] == 0 and tight["idx16"] == 0 and tight["state_in_smem"] == 1 and tight["warps"] == 7
+    # ... one that leaves room for 9 is
+    roomy = emu.plan(600, 7668, 2556)
+    assert roomy["formula_in_smem"] == 1 and roomy["idx16"] == 1 and roomy["warps"] == 9
+    assert roomy["smem_bytes"] == 4 * (roomy["formula_smem_words"] + 9 * roomy["state_words"]) <= 232448
+    # state too large for 4 warps (n = 5000), a million variables: state in global memory, 16 warps
+    for big in (emu.plan(5000, 63900, 21300), emu.plan(1_000_000, 12_000_000, 4_000_000)):
+        assert (big["warps"], big["state_in_smem"], big["formula_in_smem"], big["smem_bytes"], big["idx16"]) == (16, 0, 0, 0, 0)
+    # a requested geometry that does not fit falls back to global state instead of failing
+    forced = emu.plan(1500, 66000, 22000, warps=24)
+    assert forced["state_in_smem"] == 0 and forced["warps"] == 24 and forced["smem_bytes"] == 0
+    # PHP(10,9): small state, the warp count is the cap, not the memory
+    php = emu.plan(90, 1900, 415)
+    assert php["warps"] == 24 and php["formula_in_smem"] == 1
